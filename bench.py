@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py -- examples/sec of FFM training on B200 (BASELINE.json metric), one JSON line.
+
+  python bench.py --gpus 1 --steps K --warmup W                       # our arm (CUDA, libfwgpu.so)
+  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...   # N replicas, one per GPU
+  python bench.py --impl reference ...                                # the reference's CPU algorithm (oracle port), host cores
+
+A step = one training pass of the hot path over one batch of synthetic records of the named
+workload (default: BASELINE.json configs[1], "c2": FFM k=4, 8 fields, ffm_bit_precision=20, 10M
+examples per step).  `value` is measured with the records already resident in HBM; `e2e` goes
+through the C-ABI call that takes HOST buffers (H2D of the records and D2H of the predictions inside
+the timed region).  Multi-GPU = independent replicas on disjoint example shards (the path has no
+exchange step; DESIGN.md "multi-GPU"), reported as weak scaling.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--examples", type=int, default=0, help="examples per step (0 = workload default)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="examples in the cpu_baseline sample (0 = default)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+DEFAULT_EXAMPLES = {"c1": 10_000_000, "c2": 10_000_000, "c3": 2_000_000, "c4": 2_000_000}
+CPU_SAMPLE = {"c1": 4_000_000, "c2": 2_000_000, "c3": 100_000, "c4": 100_000}
+REF_STEP_EXAMPLES = {"c1": 8_000_000, "c2": 4_000_000, "c3": 200_000, "c4": 200_000}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons during the timed region (pynvml, 100 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.err = index, False, [], set(), None, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+                getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+            }
+            while not self.stop_flag:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, name in names.items():
+                        if r & bit:
+                            self.reasons.add(name)
+                except Exception:
+                    pass
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def summary(self):
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "note": self.err or "no samples"}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
+
+
+def dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+    return world, rank, local_rank, dist
+
+
+def cpu_baseline(w, n_sample, threads, seed=1):
+    """The reference's algorithm on the host cores: oracle port, Hogwild with `threads` workers
+    (hogwild.rs:24-103) or the sequential loop (main.rs:213-258) when threads == 1."""
+    from oracle import fw_oracle as fo
+    from tests import util
+
+    recs = w.records(n_sample, first=0, seed=seed)
+    ora = util.oracle_regressor(w.mi)
+    spec = util.oracle_spec(w.mi)
+    rec_off = np.arange(n_sample + 1, dtype=np.uint64) * w.record_len
+    secs, _ = ora.hogwild(spec, recs.reshape(-1), rec_off, threads, want_preds=False)
+    return n_sample / secs, secs
+
+
+def run_reference(args):
+    from fwumious_wabbit_b200 import synth
+
+    world, rank, local_rank, dist = 1, int(os.environ.get("RANK", "0")), 0, None
+    if rank != 0:
+        return  # rank 0 alone runs the CPU arm
+    w = synth.workload(args.workload)
+    threads = os.cpu_count() or 1
+    n = args.examples or REF_STEP_EXAMPLES[args.workload]
+    from oracle import fw_oracle as fo
+    from tests import util
+
+    ora = util.oracle_regressor(w.mi)
+    spec = util.oracle_spec(w.mi)
+    rec_off = np.arange(n + 1, dtype=np.uint64) * w.record_len
+    total_steps = args.warmup + args.steps
+    # a fresh slice of the stream per step, generated outside the timed region
+    t_sum = 0.0
+    for s in range(total_steps):
+        recs = w.records(n, first=s * n, seed=1)
+        secs, _ = ora.hogwild(spec, recs.reshape(-1), rec_off, threads, want_preds=False)
+        if s >= args.warmup:
+            t_sum += secs
+    value = n * args.steps / t_sum
+    line = {
+        "impl": "reference", "metric": "examples/sec FFM training", "value": value, "unit": "examples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_sum / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w.name}: {w.description}", "examples_per_step": n,
+                   "note": "reference Rust cannot be built here (no cargo/rustc); this is the C port of its algorithm (oracle/), Hogwild threads on the host cores"},
+        "cpu_baseline": {"value": value, "unit": "examples/s", "cores": threads, "kind": "port",
+                         "sample": f"{n} examples per step x {args.steps} steps of the {w.name} stream, Hogwild {threads} threads"},
+        "e2e": {"value": value, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+
+    import fwumious_wabbit_b200 as fw
+    from fwumious_wabbit_b200 import synth
+
+    world, rank, local_rank, dist = dist_setup(args.gpus)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    w = synth.workload(args.workload)
+    n = args.examples or DEFAULT_EXAMPLES[args.workload]
+    re = fw.Regressor(w.mi, device=local_rank)
+    stream = torch.cuda.ExternalStream(re.stream_ptr(), device=torch.device("cuda", local_rank))
+
+    # every rank trains its own replica on a disjoint shard of the stream
+    L = fw._lib.lib()
+    import ctypes as C
+
+    nbytes = n * w.record_len * 4
+    hp = C.c_void_p()
+    assert L.fwgpu_host_alloc(C.byref(hp), nbytes) == 0
+    recs = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n, w.record_len))
+    w.records(n, first=rank * n, seed=1, out=recs)
+    pp = C.c_void_p()
+    assert L.fwgpu_host_alloc(C.byref(pp), n * 4) == 0
+    preds = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(n,))
+    ds = re.upload_dataset(recs.reshape(-1), n_examples=n)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        re.sync()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- value: records resident in HBM ----------------
+    for _ in range(args.warmup):
+        re.learn_dataset(ds, 0, n, update=True, sync=False)
+    barrier()
+    re.set_profiling(True)
+    re.kernel_time(0); re.kernel_time(1)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = re.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        re.learn_dataset(ds, 0, n, update=True, sync=False)
+    ev1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    launches = re.launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    k_ms, k_n = re.kernel_time(0)
+    t_ms, t_n = re.kernel_time(1)
+    re.set_profiling(False)
+    sampler.join(timeout=2)
+    value = world * n * args.steps / (ms_total * 1e-3)
+
+    # ---------------- e2e: host buffers through the C ABI ----------------
+    e2e = None
+    if not args.no_e2e:
+        for _ in range(max(1, min(args.warmup, 2))):
+            re.learn_records(recs.reshape(-1), n_examples=n, update=True, out=preds, sync=False)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        for _ in range(args.steps):
+            re.learn_records(recs.reshape(-1), n_examples=n, update=True, out=preds, sync=False)
+        e1.record(stream)
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        e_ms = max_over_ranks(max(e0.elapsed_time(e1), 0.0))
+        e_ms = max(e_ms, max_over_ranks(wall_ms) * 0.0)  # device-timed; wall clock kept for the record below
+        e2e = {"value": world * n * args.steps / (e_ms * 1e-3), "unit": "examples/s",
+               "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(n * 4),
+               "ms_per_step": e_ms / args.steps, "wall_ms_per_step": max_over_ranks(wall_ms) / args.steps}
+        ll = float(-np.mean(np.where(recs[:, 1] == 1, np.log(np.clip(preds, 1e-7, 1)), np.log(np.clip(1 - preds, 1e-7, 1)))))
+        e2e["last_step_logloss"] = ll
+
+    # ---------------- roofline of the dominant kernel (k_learn) ----------------
+    peak, peak_src = measured_peaks()
+    alg_bytes = w.algorithmic_bytes_per_example(train=True)
+    roof = None
+    if k_n:
+        ex_per_launch = n * args.steps / k_n
+        achieved = alg_bytes * ex_per_launch / (k_ms / k_n * 1e-3) * 1e-9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", f"traffic_{w.name}.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": "k_learn", "peak_source": peak_src, "algorithmic_bytes_per_example": alg_bytes,
+                "examples_per_launch": ex_per_launch, "avg_launch_ms": k_ms / k_n, "launches_timed": int(k_n),
+                "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1)), "translate_ms_per_launch": (t_ms / t_n) if t_n else None}
+
+    # ---------------- cpu baseline (rank 0, N = 1 only) ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ns = args.cpu_sample or CPU_SAMPLE[args.workload]
+        v, secs = cpu_baseline(w, ns, 1)
+        cpu = {"value": v, "unit": "examples/s", "cores": 1, "kind": "port",
+               "sample": f"first {ns} examples of the same stream, sequential learn (reference default mode), {secs:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "examples/sec FFM training", "value": value, "unit": "examples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{w.name}: {w.description}", "examples_per_step_per_gpu": n,
+                       "parallelism": f"replicas x{world} (independent models, disjoint example shards)" if world > 1 else "single GPU",
+                       "l2_policy": f"inputs larger than L2: {nbytes >> 20} MiB of records per step; table ({(w.mi.ffm_k and ((1 << w.mi.ffm_bit_precision) * 8 >> 20))} MiB w+acc) is L2-resident by nature for c2",
+                       "optimizer": "AdagradLUT", "semantics": "Hogwild on device, chunked launches"},
+            "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    ds.free()
+    re.close()
+    L.fwgpu_host_free(hp)
+    L.fwgpu_host_free(pp)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

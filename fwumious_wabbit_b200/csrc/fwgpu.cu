@@ -1,0 +1,825 @@
+// fwgpu.cu -- the C ABI of include/fwgpu.h: context, HBM tables, batch staging, kernel launches.
+// Pure CUDA runtime; no torch, no CPU fallback (every entry point needs a live ctx on a GPU).
+#include "../../include/fwgpu.h"
+#include "fwgpu_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+using namespace fwgpu;
+
+static thread_local std::string g_create_error;
+
+#define CUDA_TRY(ctx, expr)                                                                                   \
+    do {                                                                                                      \
+        cudaError_t _e = (expr);                                                                              \
+        if (_e != cudaSuccess) {                                                                              \
+            (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                             \
+            return FWGPU_ERR_CUDA;                                                                            \
+        }                                                                                                     \
+    } while (0)
+
+static FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    f.d = d;
+    if (d == 0) { f.m = 0; f.s = 0; return f; }
+    uint32_t s = 0;
+    while ((1ull << s) < d) s++;
+    f.s = s;
+    f.m = (uint32_t)(((1ull << 32) * ((1ull << s) - d)) / d + 1);
+    return f;
+}
+
+// OptimizerAdagradLUT::init (optimizer.rs:121-144); host powf (glibc) exactly as the reference's Rust std does.
+static void build_lut(float lr, float power_t, float init_acc, float *lut)
+{
+    const float minus_power_t = -power_t;
+    for (uint32_t x = 0; x < FWGPU_LUT_SIZE; x++) {
+        uint32_t b0 = x << 20, b1 = (x + 1) << 20;
+        float f0, f1;
+        memcpy(&f0, &b0, 4);
+        memcpy(&f1, &b1, 4);
+        f0 += init_acc;
+        f1 += init_acc;
+        float val = lr * (powf(f0, minus_power_t) + powf(f1, minus_power_t)) * 0.5f;
+        if (std::isnan(val) || std::isinf(val)) val = lr;
+        lut[x] = val;
+    }
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t bytes = 0;
+};
+
+struct fwgpu_dataset {
+    uint32_t *records = nullptr;
+    uint32_t *rec_off = nullptr; // device, [n+1], or null (fixed)
+    uint64_t n_words = 0, n_examples = 0;
+    uint32_t fixed_len = 0, max_len = 0;
+};
+
+struct fwgpu_ctx {
+    int device = 0;
+    fwgpu_model_desc d{};
+    std::vector<uint8_t> ns_is_f32;
+    std::vector<uint32_t> combo_off, combo_ns, field_off, field_ns;
+    std::vector<float> combo_weight;
+    uint32_t n_field_refs = 0;
+    uint32_t optimizer = 0; // effective (SGD when immutable)
+    uint32_t F = 0, k = 0, Fk = 0, VEC = 1, cpr = 0;
+    uint64_t lr_len = 0, ffm_len = 0, ffm_alloc = 0;
+    float2 *lr = nullptr;
+    float *ffm_w = nullptr, *ffm_acc = nullptr;
+    float *lut_dev = nullptr; // 3 * 2048
+    float lut_host[3][FWGPU_LUT_SIZE];
+    // device copies of the translate spec
+    uint8_t *d_ns_is_f32 = nullptr;
+    uint32_t *d_combo_off = nullptr, *d_combo_ns = nullptr, *d_field_off = nullptr, *d_field_ns = nullptr;
+    float *d_combo_weight = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_ready[2]{}, ev_free[2]{};
+    bool ev_free_recorded[2] = {false, false};
+    // staging
+    DevBuf rec[2], rec_off_dev[2], meta, lr_ent, ffm_ent, preds, csr;
+    uint32_t *err_flag = nullptr;
+    uint32_t *err_host = nullptr; // pinned
+    int num_sms = 0;
+    size_t smem_optin = 0;
+    int force_T = 0;
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[2];
+    std::vector<cudaEvent_t> ev_pool;
+    double prof_ms[2] = {0, 0};
+    uint64_t prof_n[2] = {0, 0};
+    std::string err;
+    void set_error(const std::string &s) { err = s; }
+};
+
+static fwgpu_status ensure(fwgpu_ctx *c, DevBuf &b, size_t bytes)
+{
+    if (b.bytes >= bytes) return FWGPU_OK;
+    if (b.p) {
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+        CUDA_TRY(c, cudaFree(b.p));
+        b.p = nullptr;
+        b.bytes = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    CUDA_TRY(c, cudaMalloc(&b.p, want));
+    b.bytes = want;
+    return FWGPU_OK;
+}
+
+template <typename Tp> static fwgpu_status upload_vec(fwgpu_ctx *c, const std::vector<Tp> &v, Tp **out)
+{
+    size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(Tp);
+    CUDA_TRY(c, cudaMalloc((void **)out, bytes));
+    if (!v.empty()) CUDA_TRY(c, cudaMemcpy(*out, v.data(), v.size() * sizeof(Tp), cudaMemcpyHostToDevice));
+    return FWGPU_OK;
+}
+
+extern "C" const char *fwgpu_version(void) { return "fwgpu 0.1 sm_100a"; }
+
+extern "C" const char *fwgpu_last_error(const fwgpu_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" fwgpu_status fwgpu_host_alloc(void **out, uint64_t bytes)
+{
+    if (!out) return FWGPU_ERR_INVALID;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); return FWGPU_ERR_CUDA; }
+    return FWGPU_OK;
+}
+extern "C" void fwgpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
+extern "C" void fwgpu_destroy(fwgpu_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    cudaFree(c->lr); cudaFree(c->ffm_w); cudaFree(c->ffm_acc); cudaFree(c->lut_dev);
+    cudaFree(c->d_ns_is_f32); cudaFree(c->d_combo_off); cudaFree(c->d_combo_ns); cudaFree(c->d_field_off);
+    cudaFree(c->d_field_ns); cudaFree(c->d_combo_weight);
+    for (DevBuf *b : {&c->rec[0], &c->rec[1], &c->rec_off_dev[0], &c->rec_off_dev[1], &c->meta, &c->lr_ent, &c->ffm_ent, &c->preds, &c->csr})
+        if (b->p) cudaFree(b->p);
+    cudaFree(c->err_flag);
+    if (c->err_host) cudaFreeHost(c->err_host);
+    for (int i = 0; i < 2; i++) { if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]); if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]); }
+    for (int kk = 0; kk < 2; kk++) for (auto &pr : c->prof[kk]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (auto e : c->ev_pool) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_ctx *c)
+{
+    int ndev = 0;
+    cudaError_t e0 = cudaGetDeviceCount(&ndev);
+    if (e0 != cudaSuccess || ndev == 0) {
+        c->set_error(std::string("no CUDA device: ") + (e0 != cudaSuccess ? cudaGetErrorString(e0) : "device count 0") +
+                     " (fwgpu has no CPU fallback)");
+        return FWGPU_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) { c->set_error("device index out of range"); return FWGPU_ERR_INVALID; }
+    c->device = device;
+    CUDA_TRY(c, cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(c, cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) { c->set_error("fwgpu kernels are built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor)); return FWGPU_ERR_UNSUPPORTED; }
+    c->num_sms = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+
+    c->d = *desc;
+    const fwgpu_model_desc &d = c->d;
+    if (d.bit_precision == 0 || d.bit_precision > 31) { c->set_error("bit_precision must be in 1..31"); return FWGPU_ERR_INVALID; }
+    if (d.optimizer > FWGPU_OPT_ADAGRAD_LUT) { c->set_error("unknown optimizer"); return FWGPU_ERR_INVALID; }
+    if (d.nn_num_layers != 0) { c->set_error("dense head (nn_layers) is not implemented by the CUDA path yet"); return FWGPU_ERR_UNSUPPORTED; }
+    c->optimizer = d.immutable ? FWGPU_OPT_SGD : d.optimizer;
+    c->F = d.ffm_k > 0 ? d.ffm_num_fields : 0;
+    c->k = d.ffm_k;
+    c->Fk = c->F * c->k;
+    if (d.ffm_k > 0) {
+        if (d.ffm_num_fields == 0) { c->set_error("ffm_k > 0 needs ffm_num_fields > 0"); return FWGPU_ERR_INVALID; }
+        if (d.ffm_bit_precision == 0 || d.ffm_bit_precision > 31) { c->set_error("ffm_bit_precision must be in 1..31"); return FWGPU_ERR_INVALID; }
+        // regressor.rs:23 / block_ffm.rs:97-101: k * F^2 <= FFM_CONTRA_BUF_LEN
+        if ((uint64_t)d.ffm_k * d.ffm_num_fields * d.ffm_num_fields > 41472ull) {
+            c->set_error("ffm_k * number_of_fields^2 exceeds FFM_CONTRA_BUF_LEN (41472), as in the reference");
+            return FWGPU_ERR_UNSUPPORTED;
+        }
+        uint32_t kp = 1;
+        while (kp < d.ffm_k) kp <<= 1;
+        uint32_t vec = 4;
+        while (vec > 1 && (vec > kp || (c->Fk % vec) != 0)) vec >>= 1;
+        c->VEC = vec;
+        c->cpr = c->Fk / vec;
+    }
+    // translate spec copies
+    if (d.n_namespaces) {
+        if (d.ns_is_f32) c->ns_is_f32.assign(d.ns_is_f32, d.ns_is_f32 + d.n_namespaces);
+        else c->ns_is_f32.assign(d.n_namespaces, 0);
+    }
+    if (d.n_combos) {
+        if (!d.combo_off || !d.combo_ns || !d.combo_weight) { c->set_error("combo arrays missing"); return FWGPU_ERR_INVALID; }
+        c->combo_off.assign(d.combo_off, d.combo_off + d.n_combos + 1);
+        c->combo_ns.assign(d.combo_ns, d.combo_ns + c->combo_off.back());
+        c->combo_weight.assign(d.combo_weight, d.combo_weight + d.n_combos);
+        for (uint32_t i = 0; i < d.n_combos; i++) {
+            uint32_t m = c->combo_off[i + 1] - c->combo_off[i];
+            if (m == 0 || m > FWGPU_MAX_COMBO_NS) { c->set_error("a feature combo must have 1..8 namespaces"); return FWGPU_ERR_UNSUPPORTED; }
+        }
+        for (uint32_t ns : c->combo_ns) if (ns >= d.n_namespaces) { c->set_error("combo namespace index out of range"); return FWGPU_ERR_INVALID; }
+    } else {
+        c->combo_off.assign(1, 0);
+    }
+    if (d.ffm_k > 0 && d.field_off && d.field_ns) {
+        c->field_off.assign(d.field_off, d.field_off + d.ffm_num_fields + 1);
+        c->field_ns.assign(d.field_ns, d.field_ns + c->field_off.back());
+        for (uint32_t ns : c->field_ns) if (ns >= d.n_namespaces) { c->set_error("field namespace index out of range"); return FWGPU_ERR_INVALID; }
+    } else {
+        c->field_off.assign(c->F + 1, 0);
+    }
+    c->n_field_refs = (uint32_t)c->field_ns.size();
+    c->d.ns_is_f32 = nullptr; c->d.combo_off = nullptr; c->d.combo_ns = nullptr; c->d.combo_weight = nullptr;
+    c->d.field_off = nullptr; c->d.field_ns = nullptr;
+
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(c, cudaMalloc((void **)&c->err_flag, 4));
+    CUDA_TRY(c, cudaMemset(c->err_flag, 0, 4));
+    CUDA_TRY(c, cudaHostAlloc((void **)&c->err_host, 4, cudaHostAllocDefault));
+    *c->err_host = 0;
+
+    // LUTs (built for every optimizer kind; only read under AdagradLUT)
+    build_lut(d.learning_rate, d.power_t, d.init_acc_gradient, c->lut_host[0]);
+    build_lut(d.ffm_learning_rate, d.ffm_power_t, d.ffm_init_acc_gradient, c->lut_host[1]);
+    build_lut(d.nn_learning_rate, d.nn_power_t, d.nn_init_acc_gradient, c->lut_host[2]);
+    CUDA_TRY(c, cudaMalloc((void **)&c->lut_dev, sizeof(c->lut_host)));
+    CUDA_TRY(c, cudaMemcpy(c->lut_dev, c->lut_host, sizeof(c->lut_host), cudaMemcpyHostToDevice));
+
+    // tables
+    c->lr_len = 1ull << d.bit_precision;
+    CUDA_TRY(c, cudaMalloc((void **)&c->lr, c->lr_len * sizeof(float2)));
+    // initial_data(): Flex starts at init_acc (optimizer.rs:91-93), LUT at 0 (optimizer.rs:158-161)
+    const float lr_acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? d.init_acc_gradient : 0.0f;
+    k_init_lr<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr, c->lr_len, lr_acc0);
+    c->launches++;
+    if (d.ffm_k > 0) {
+        c->ffm_len = (1ull << d.ffm_bit_precision) + c->Fk; // block_ffm.rs:93-94
+        c->ffm_alloc = c->ffm_len + 64;
+        CUDA_TRY(c, cudaMalloc((void **)&c->ffm_w, c->ffm_alloc * sizeof(float)));
+        if (c->optimizer != FWGPU_OPT_SGD) CUDA_TRY(c, cudaMalloc((void **)&c->ffm_acc, c->ffm_alloc * sizeof(float)));
+        const float ffm_acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? d.ffm_init_acc_gradient : 0.0f;
+        const float one_over_k_root = 1.0f / sqrtf((float)d.ffm_k) / 50.0f; // block_ffm.rs:798
+        k_init_ffm<<<c->num_sms * 8, 256, 0, c->stream>>>(c->ffm_w, c->ffm_acc, (uint32_t)c->ffm_len, (uint32_t)c->ffm_alloc, one_over_k_root,
+                                                          ffm_acc0, d.ffm_init_width, d.ffm_init_zero_band, d.ffm_init_center);
+        c->launches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+
+    fwgpu_status st;
+    if ((st = upload_vec(c, c->ns_is_f32, &c->d_ns_is_f32))) return st;
+    if ((st = upload_vec(c, c->combo_off, &c->d_combo_off))) return st;
+    if ((st = upload_vec(c, c->combo_ns, &c->d_combo_ns))) return st;
+    if ((st = upload_vec(c, c->combo_weight, &c->d_combo_weight))) return st;
+    if ((st = upload_vec(c, c->field_off, &c->d_field_off))) return st;
+    if ((st = upload_vec(c, c->field_ns, &c->d_field_ns))) return st;
+    if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **out)
+{
+    if (!desc || !out) { g_create_error = "null argument"; return FWGPU_ERR_INVALID; }
+    *out = nullptr;
+    fwgpu_ctx *c = new fwgpu_ctx();
+    fwgpu_status st = create_impl(desc, device, c);
+    if (st != FWGPU_OK) {
+        g_create_error = c->err;
+        fwgpu_destroy(c);
+        return st;
+    }
+    *out = c;
+    return FWGPU_OK;
+}
+
+extern "C" void *fwgpu_stream(fwgpu_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" uint64_t fwgpu_launch_count(const fwgpu_ctx *c) { return c ? c->launches : 0; }
+
+static fwgpu_status check_err_flag(fwgpu_ctx *c)
+{
+    if (*c->err_host) {
+        uint32_t f = *c->err_host;
+        *c->err_host = 0;
+        cudaMemsetAsync(c->err_flag, 0, 4, c->stream);
+        cudaStreamSynchronize(c->stream);
+        c->set_error(std::string("an example exceeded the staging capacity (") + ((f & 1) ? "ffm features > max_ffm_per_example " : "") +
+                     ((f & 2) ? "translate slab overflow " : "") + "); its prediction is NaN and it was not learned. Raise max_ffm_per_example / max_lr_per_example.");
+        return FWGPU_ERR_TOO_LARGE;
+    }
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_sync(fwgpu_ctx *c)
+{
+    if (!c) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(c->err_host, c->err_flag, 4, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return check_err_flag(c);
+}
+
+// ---- profiling -------------------------------------------------------------------------------
+static cudaEvent_t get_event(fwgpu_ctx *c)
+{
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    fwgpu_ctx *c; int kind; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(fwgpu_ctx *c_, int kind_) : c(c_), kind(kind_)
+    {
+        if (c->profiling) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~ProfScope()
+    {
+        if (c->profiling) { cudaEventRecord(b, c->stream); c->prof[kind].push_back({a, b}); }
+    }
+};
+extern "C" fwgpu_status fwgpu_set_profiling(fwgpu_ctx *c, int enabled)
+{
+    if (!c) return FWGPU_ERR_INVALID;
+    c->profiling = enabled != 0;
+    return FWGPU_OK;
+}
+extern "C" fwgpu_status fwgpu_kernel_time(fwgpu_ctx *c, int kind, double *total_ms, uint64_t *launches)
+{
+    if (!c || kind < 0 || kind > 1) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    for (auto &pr : c->prof[kind]) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, pr.first, pr.second);
+        c->prof_ms[kind] += ms;
+        c->prof_n[kind]++;
+        c->ev_pool.push_back(pr.first);
+        c->ev_pool.push_back(pr.second);
+    }
+    c->prof[kind].clear();
+    if (total_ms) *total_ms = c->prof_ms[kind];
+    if (launches) *launches = c->prof_n[kind];
+    c->prof_ms[kind] = 0;
+    c->prof_n[kind] = 0;
+    return FWGPU_OK;
+}
+
+// ---- learn kernel launch ----------------------------------------------------------------------
+template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const LearnParams &p, size_t smem)
+{
+    auto kern = k_learn<T, VEC>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    constexpr int GROUPS = 256 / T;
+    uint32_t need = (p.n_examples + GROUPS - 1) / GROUPS;
+    uint32_t grid = std::min<uint32_t>(need, (uint32_t)(c->num_sms * per_sm));
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, 256, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
+template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnParams &p, size_t smem)
+{
+    switch (c->VEC) {
+    case 4: return launch_learn_tv<T, 4>(c, p, smem);
+    case 2: return launch_learn_tv<T, 2>(c, p, smem);
+    default: return launch_learn_tv<T, 1>(c, p, smem);
+    }
+}
+
+static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_cap, int update)
+{
+    if (n_examples == 0) return FWGPU_OK;
+    LearnParams p{};
+    p.lr = c->lr; p.ffm_w = c->ffm_w; p.ffm_acc = c->ffm_acc;
+    p.lut_lr = c->lut_dev; p.lut_ffm = c->lut_dev + FWGPU_LUT_SIZE;
+    p.meta = (const ExMeta *)c->meta.p; p.lr_ent = (const uint4 *)c->lr_ent.p; p.ffm_ent = (const uint4 *)c->ffm_ent.p;
+    p.preds = (float *)c->preds.p; p.n_examples = n_examples;
+    p.F = c->F; p.k = c->k; p.Fk = c->Fk; p.cpr = c->cpr; p.n_cap = std::max<uint32_t>(n_cap, 1);
+    p.div_cpr = make_fastdiv(std::max<uint32_t>(c->cpr, 1)); p.div_k = make_fastdiv(std::max<uint32_t>(c->k, 1)); p.div_F = make_fastdiv(std::max<uint32_t>(c->F, 1));
+    p.optimizer = c->optimizer;
+    p.lr_lr = c->d.learning_rate; p.lr_mpt = -c->d.power_t; p.ffm_lr = c->d.ffm_learning_rate; p.ffm_mpt = -c->d.ffm_power_t;
+    p.update = update; p.err_flag = c->err_flag;
+    size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 8;
+    size_t group_bytes = ((words * 4 + 15) / 16) * 16;
+    p.group_smem_bytes = (uint32_t)group_bytes;
+    int T = 32;
+    const uint32_t work = c->F * c->cpr;
+    if (work > 1536) T = 256; else if (work > 512) T = 128; else if (work > 128) T = 64;
+    if (c->force_T == 32 || c->force_T == 64 || c->force_T == 128 || c->force_T == 256) T = c->force_T;
+    size_t smem = group_bytes * (256 / T);
+    while (smem > c->smem_optin && T < 256) { T *= 2; smem = group_bytes * (256 / T); }
+    if (smem > c->smem_optin) {
+        c->set_error("example staging needs " + std::to_string(smem) + " B of shared memory (> " + std::to_string(c->smem_optin) + "): F*F*k or features per example too large");
+        return FWGPU_ERR_TOO_LARGE;
+    }
+    ProfScope ps(c, 0);
+    cudaError_t e;
+    switch (T) {
+    case 32: e = launch_learn_t<32>(c, p, smem); break;
+    case 64: e = launch_learn_t<64>(c, p, smem); break;
+    case 128: e = launch_learn_t<128>(c, p, smem); break;
+    default: e = launch_learn_t<256>(c, p, smem); break;
+    }
+    if (e != cudaSuccess) { c->set_error(std::string("k_learn launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+    return FWGPU_OK;
+}
+
+// ---- CSR batch entry --------------------------------------------------------------------------
+static fwgpu_status learn_batch_impl(fwgpu_ctx *c, const fwgpu_batch *b, float *preds_out, int update)
+{
+    if (!c || !b) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (update && c->d.immutable) { c->set_error("This regressor is immutable, you cannot call learn() with update = true"); return FWGPU_ERR_IMMUTABLE; }
+    const uint32_t n = b->n_examples;
+    if (n == 0) return FWGPU_OK;
+    if (!b->labels || !b->importance || !b->lr_off) { c->set_error("batch arrays missing"); return FWGPU_ERR_INVALID; }
+    const bool has_ffm = c->F > 0 && b->ffm_off;
+    const uint64_t n_lr = b->lr_off[n], n_ffm = has_ffm ? b->ffm_off[n] : 0;
+    uint32_t max_ffm = 0;
+    if (has_ffm) for (uint32_t i = 0; i < n; i++) max_ffm = std::max(max_ffm, b->ffm_off[i + 1] - b->ffm_off[i]);
+    // one device slab: labels | importance | lr_off | lr_hash | lr_val | lr_combo | ffm_off | ffm_hash | ffm_val | ffm_field
+    size_t off = 0;
+    auto take = [&](size_t words) { size_t o = off; off += ((words + 3) / 4) * 4; return o; };
+    size_t o_lab = take(n), o_imp = take(n), o_lro = take(n + 1), o_lrh = take(n_lr), o_lrv = take(n_lr), o_lrc = take(n_lr);
+    size_t o_fo = take(n + 1), o_fh = take(n_ffm), o_fv = take(n_ffm), o_ff = take(n_ffm);
+    fwgpu_status st;
+    if ((st = ensure(c, c->csr, off * 4))) return st;
+    if ((st = ensure(c, c->meta, (size_t)n * sizeof(ExMeta)))) return st;
+    if ((st = ensure(c, c->lr_ent, std::max<size_t>(n_lr, 1) * 16))) return st;
+    if ((st = ensure(c, c->ffm_ent, std::max<size_t>(n_ffm, 1) * 16))) return st;
+    if ((st = ensure(c, c->preds, (size_t)n * 4))) return st;
+    uint32_t *base = (uint32_t *)c->csr.p;
+    auto up = [&](size_t o, const void *src, size_t words) -> cudaError_t {
+        if (!words) return cudaSuccess;
+        return cudaMemcpyAsync(base + o, src, words * 4, cudaMemcpyHostToDevice, c->stream);
+    };
+    CUDA_TRY(c, up(o_lab, b->labels, n));
+    CUDA_TRY(c, up(o_imp, b->importance, n));
+    CUDA_TRY(c, up(o_lro, b->lr_off, n + 1));
+    CUDA_TRY(c, up(o_lrh, b->lr_hash, n_lr));
+    CUDA_TRY(c, up(o_lrv, b->lr_val, n_lr));
+    CUDA_TRY(c, up(o_lrc, b->lr_combo, n_lr));
+    if (has_ffm) {
+        CUDA_TRY(c, up(o_fo, b->ffm_off, n + 1));
+        CUDA_TRY(c, up(o_fh, b->ffm_hash, n_ffm));
+        CUDA_TRY(c, up(o_fv, b->ffm_val, n_ffm));
+        CUDA_TRY(c, up(o_ff, b->ffm_field, n_ffm));
+    }
+    PackParams pp{};
+    pp.n_examples = n;
+    pp.labels = (const float *)(base + o_lab); pp.importance = (const float *)(base + o_imp);
+    pp.lr_off = base + o_lro; pp.lr_hash = base + o_lrh; pp.lr_val = (const float *)(base + o_lrv); pp.lr_combo = base + o_lrc;
+    pp.ffm_off = has_ffm ? base + o_fo : nullptr; pp.ffm_hash = base + o_fh; pp.ffm_val = (const float *)(base + o_fv); pp.ffm_field = base + o_ff;
+    pp.n_lr = (uint32_t)n_lr; pp.n_ffm = (uint32_t)n_ffm;
+    pp.meta = (ExMeta *)c->meta.p; pp.lr_ent = (uint4 *)c->lr_ent.p; pp.ffm_ent = (uint4 *)c->ffm_ent.p;
+    uint64_t threads = std::max<uint64_t>(std::max<uint64_t>(n, n_lr), n_ffm);
+    {
+        ProfScope ps(c, 1);
+        k_pack<<<(uint32_t)((threads + 255) / 256), 256, 0, c->stream>>>(pp);
+        c->launches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    uint32_t n_cap = std::max(max_ffm, c->n_field_refs);
+    if ((st = launch_learn(c, n, n_cap, update))) return st;
+    if (preds_out) CUDA_TRY(c, cudaMemcpyAsync(preds_out, c->preds.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_learn_batch(fwgpu_ctx *c, const fwgpu_batch *b, float *preds_out, int update) { return learn_batch_impl(c, b, preds_out, update); }
+extern "C" fwgpu_status fwgpu_predict_batch(fwgpu_ctx *c, const fwgpu_batch *b, float *preds_out) { return learn_batch_impl(c, b, preds_out, 0); }
+
+// ---- raw-record entries -----------------------------------------------------------------------
+static uint32_t derive_lr_stride(const fwgpu_ctx *c, uint32_t max_dyn_pairs)
+{
+    if (c->d.max_lr_per_example) return c->d.max_lr_per_example;
+    // every combo contributes prod(count(ns)); with single-valued slots that is <= 1 each
+    uint64_t s = 0;
+    const uint64_t m = std::max<uint32_t>(1, max_dyn_pairs);
+    for (uint32_t i = 0; i + 1 < c->combo_off.size(); i++) {
+        uint64_t t = 1;
+        for (uint32_t j = c->combo_off[i]; j < c->combo_off[i + 1]; j++) t = std::min<uint64_t>(t * m, 1u << 16);
+        s += t;
+    }
+    s += c->d.add_constant ? 1 : 0;
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s, 1), 1u << 16);
+}
+static uint32_t derive_ffm_stride(const fwgpu_ctx *c, uint32_t max_dyn_pairs)
+{
+    if (c->d.max_ffm_per_example) return c->d.max_ffm_per_example;
+    uint64_t s = (uint64_t)c->n_field_refs * std::max<uint32_t>(1, max_dyn_pairs);
+    return (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s, 1), 1u << 16);
+}
+
+struct RecView {
+    const uint32_t *dev_records; // device pointer to the first word of the slice
+    const uint32_t *dev_rec_off; // device, [count+1] (absolute word offsets) or null
+    uint32_t off_base;           // subtract from rec_off values
+    uint32_t fixed_len;
+    uint32_t max_len;            // longest record in words (bounds the dynamic part)
+};
+
+static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_t count, float *preds_host, int update, bool run_learn,
+                                        uint32_t *lr_stride_out = nullptr, uint32_t *ffm_stride_out = nullptr)
+{
+    const uint32_t hdr = 3 + c->d.n_namespaces;
+    const uint32_t dyn_pairs = rv.max_len > hdr ? (rv.max_len - hdr + 1) / 2 : 0;
+    const uint32_t lr_stride = derive_lr_stride(c, dyn_pairs);
+    const uint32_t ffm_stride = c->F ? derive_ffm_stride(c, dyn_pairs) : 1;
+    if (lr_stride_out) *lr_stride_out = lr_stride;
+    if (ffm_stride_out) *ffm_stride_out = ffm_stride;
+    fwgpu_status st;
+    if ((st = ensure(c, c->meta, (size_t)count * sizeof(ExMeta)))) return st;
+    if ((st = ensure(c, c->lr_ent, (size_t)count * lr_stride * 16))) return st;
+    if ((st = ensure(c, c->ffm_ent, (size_t)count * ffm_stride * 16))) return st;
+    if ((st = ensure(c, c->preds, (size_t)count * 4))) return st;
+    TranslateParams tp{};
+    tp.records = rv.dev_records; tp.rec_off = rv.dev_rec_off; tp.fixed_len = rv.fixed_len; tp.n_examples = count;
+    tp.off_base = rv.off_base;
+    tp.n_namespaces = c->d.n_namespaces; tp.ns_is_f32 = c->d_ns_is_f32;
+    tp.n_combos = c->d.n_combos; tp.combo_off = c->d_combo_off; tp.combo_ns = c->d_combo_ns; tp.combo_weight = c->d_combo_weight;
+    tp.add_constant = c->d.add_constant; tp.n_fields = c->F; tp.field_off = c->d_field_off; tp.field_ns = c->d_field_ns;
+    tp.lr_mask = (uint32_t)((1ull << c->d.bit_precision) - 1); // feature_buffer.rs:140
+    uint32_t bits = 0;
+    while (c->d.ffm_k > (1u << bits)) bits++;                  // feature_buffer.rs:142-148
+    tp.ffm_mask = c->d.ffm_k ? (uint32_t)(((1ull << c->d.ffm_bit_precision) - 1) ^ ((1u << bits) - 1)) : 0;
+    tp.ffm_k = c->d.ffm_k;
+    tp.lr_stride = lr_stride; tp.ffm_stride = ffm_stride;
+    tp.meta = (ExMeta *)c->meta.p; tp.lr_ent = (uint4 *)c->lr_ent.p; tp.ffm_ent = (uint4 *)c->ffm_ent.p; tp.err_flag = c->err_flag;
+    {
+        ProfScope ps(c, 1);
+        k_translate<<<(count + 255) / 256, 256, 0, c->stream>>>(tp);
+        c->launches++;
+    }
+    CUDA_TRY(c, cudaGetLastError());
+    if (!run_learn) return FWGPU_OK;
+    if ((st = launch_learn(c, count, ffm_stride, update))) return st;
+    if (preds_host) CUDA_TRY(c, cudaMemcpyAsync(preds_host, c->preds.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream));
+    return FWGPU_OK;
+}
+
+static size_t chunk_examples(const fwgpu_ctx *c, uint32_t lr_stride, uint32_t ffm_stride)
+{
+    size_t slab = (size_t)(lr_stride + ffm_stride) * 16 + sizeof(ExMeta) + 4;
+    size_t target = (size_t)384 << 20;
+    if (const char *t = getenv("FWGPU_CHUNK_MB")) target = (size_t)atol(t) << 20;
+    size_t n = target / slab;
+    return std::max<size_t>(n, 4096);
+}
+
+static uint32_t host_max_len(const uint32_t *rec_off, uint64_t first, uint64_t count)
+{
+    uint32_t m = 0;
+    for (uint64_t i = first; i < first + count; i++) m = std::max(m, rec_off[i + 1] - rec_off[i]);
+    return m;
+}
+
+extern "C" fwgpu_status fwgpu_learn_records(fwgpu_ctx *c, const uint32_t *records, uint64_t n_words, const uint32_t *rec_off,
+                                            uint32_t n_examples, float *preds_out, int update)
+{
+    if (!c || (!records && n_examples)) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (update && c->d.immutable) { c->set_error("This regressor is immutable, you cannot call learn() with update = true"); return FWGPU_ERR_IMMUTABLE; }
+    if (n_examples == 0) return FWGPU_OK;
+    if (c->d.n_namespaces == 0) { c->set_error("model descriptor has no translate spec (n_namespaces == 0)"); return FWGPU_ERR_INVALID; }
+    uint32_t fixed_len = 0;
+    if (!rec_off) {
+        if (n_words % n_examples) { c->set_error("rec_off == NULL needs fixed-length records"); return FWGPU_ERR_INVALID; }
+        fixed_len = (uint32_t)(n_words / n_examples);
+    }
+    const uint32_t hdr = 3 + c->d.n_namespaces;
+    const uint32_t max_len = rec_off ? host_max_len(rec_off, 0, n_examples) : fixed_len;
+    if (max_len < hdr && !rec_off) { c->set_error("records shorter than header + namespace slots"); return FWGPU_ERR_INVALID; }
+    const uint32_t dyn_pairs = max_len > hdr ? (max_len - hdr + 1) / 2 : 0;
+    const size_t chunk = chunk_examples(c, derive_lr_stride(c, dyn_pairs), c->F ? derive_ffm_stride(c, dyn_pairs) : 1);
+    fwgpu_status st;
+    uint64_t done = 0;
+    int bi = 0;
+    while (done < n_examples) {
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, n_examples - done);
+        const uint64_t w0 = rec_off ? rec_off[done] : done * fixed_len;
+        const uint64_t w1 = rec_off ? rec_off[done + cnt] : (done + cnt) * fixed_len;
+        // copy stream: wait until the translate of the chunk that last used this buffer has finished
+        if ((st = ensure(c, c->rec[bi], (size_t)(w1 - w0) * 4))) return st;
+        if (rec_off && (st = ensure(c, c->rec_off_dev[bi], (size_t)(cnt + 1) * 4))) return st;
+        if (c->ev_free_recorded[bi]) CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->ev_free[bi], 0));
+        CUDA_TRY(c, cudaMemcpyAsync(c->rec[bi].p, records + w0, (size_t)(w1 - w0) * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        if (rec_off) CUDA_TRY(c, cudaMemcpyAsync(c->rec_off_dev[bi].p, rec_off + done, (size_t)(cnt + 1) * 4, cudaMemcpyHostToDevice, c->copy_stream));
+        CUDA_TRY(c, cudaEventRecord(c->ev_ready[bi], c->copy_stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_ready[bi], 0));
+        RecView rv{(const uint32_t *)c->rec[bi].p, rec_off ? (const uint32_t *)c->rec_off_dev[bi].p : nullptr, (uint32_t)w0, fixed_len, max_len};
+        if ((st = translate_and_learn(c, rv, cnt, nullptr, update, true))) return st;
+        CUDA_TRY(c, cudaEventRecord(c->ev_free[bi], c->stream)); // translate (and learn) of this chunk are ordered before it
+        c->ev_free_recorded[bi] = true;
+        if (preds_out) CUDA_TRY(c, cudaMemcpyAsync(preds_out + done, c->preds.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        done += cnt;
+        bi ^= 1;
+    }
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_translate_records(fwgpu_ctx *c, const uint32_t *records, uint64_t n_words, const uint32_t *rec_off, uint32_t n,
+                                                float *labels, float *importance, uint32_t *lr_off, uint32_t *lr_hash, float *lr_val,
+                                                uint32_t *lr_combo, uint64_t lr_cap, uint32_t *ffm_off, uint32_t *ffm_hash, float *ffm_val,
+                                                uint32_t *ffm_field, uint64_t ffm_cap)
+{
+    if (!c || !records || !lr_off || !ffm_off) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (n == 0) { lr_off[0] = 0; ffm_off[0] = 0; return FWGPU_OK; }
+    uint32_t fixed_len = 0;
+    if (!rec_off) {
+        if (n_words % n) { c->set_error("rec_off == NULL needs fixed-length records"); return FWGPU_ERR_INVALID; }
+        fixed_len = (uint32_t)(n_words / n);
+    }
+    const uint32_t max_len = rec_off ? host_max_len(rec_off, 0, n) : fixed_len;
+    fwgpu_status st;
+    if ((st = ensure(c, c->rec[0], (size_t)n_words * 4))) return st;
+    CUDA_TRY(c, cudaMemcpyAsync(c->rec[0].p, records, (size_t)n_words * 4, cudaMemcpyHostToDevice, c->stream));
+    if (rec_off) {
+        if ((st = ensure(c, c->rec_off_dev[0], (size_t)(n + 1) * 4))) return st;
+        CUDA_TRY(c, cudaMemcpyAsync(c->rec_off_dev[0].p, rec_off, (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    }
+    RecView rv{(const uint32_t *)c->rec[0].p, rec_off ? (const uint32_t *)c->rec_off_dev[0].p : nullptr, rec_off ? rec_off[0] : 0, fixed_len, max_len};
+    uint32_t lr_stride = 0, ffm_stride = 0;
+    if ((st = translate_and_learn(c, rv, n, nullptr, 0, false, &lr_stride, &ffm_stride))) return st;
+    std::vector<ExMeta> meta(n);
+    std::vector<uint4> lre((size_t)n * lr_stride), ffe((size_t)n * ffm_stride);
+    CUDA_TRY(c, cudaMemcpyAsync(meta.data(), c->meta.p, (size_t)n * sizeof(ExMeta), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(lre.data(), c->lr_ent.p, lre.size() * 16, cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaMemcpyAsync(ffe.data(), c->ffm_ent.p, ffe.size() * 16, cudaMemcpyDeviceToHost, c->stream));
+    if ((st = fwgpu_sync(c))) return st;
+    uint64_t nl = 0, nf = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        labels[i] = meta[i].label;
+        importance[i] = meta[i].importance;
+        lr_off[i] = (uint32_t)nl;
+        ffm_off[i] = (uint32_t)nf;
+        if (nl + meta[i].lr_cnt > lr_cap || nf + meta[i].ffm_cnt > ffm_cap) { c->set_error("output capacity too small"); return FWGPU_ERR_INVALID; }
+        for (uint32_t j = 0; j < meta[i].lr_cnt; j++) {
+            const uint4 &e = lre[(size_t)meta[i].lr_begin + j];
+            lr_hash[nl] = e.x; memcpy(&lr_val[nl], &e.y, 4); lr_combo[nl] = e.z; nl++;
+        }
+        for (uint32_t j = 0; j < meta[i].ffm_cnt; j++) {
+            const uint4 &e = ffe[(size_t)meta[i].ffm_begin + j];
+            ffm_hash[nf] = e.x; memcpy(&ffm_val[nf], &e.y, 4); ffm_field[nf] = e.z; nf++;
+        }
+    }
+    lr_off[n] = (uint32_t)nl;
+    ffm_off[n] = (uint32_t)nf;
+    return FWGPU_OK;
+}
+
+// ---- resident dataset -------------------------------------------------------------------------
+extern "C" fwgpu_status fwgpu_dataset_upload(fwgpu_ctx *c, const uint32_t *records, uint64_t n_words, const uint32_t *rec_off,
+                                             uint64_t n_examples, fwgpu_dataset **out)
+{
+    if (!c || !records || !out || n_examples == 0) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->d.n_namespaces == 0) { c->set_error("model descriptor has no translate spec (n_namespaces == 0)"); return FWGPU_ERR_INVALID; }
+    fwgpu_dataset *ds = new fwgpu_dataset();
+    ds->n_words = n_words; ds->n_examples = n_examples;
+    if (!rec_off) {
+        if (n_words % n_examples) { delete ds; c->set_error("rec_off == NULL needs fixed-length records"); return FWGPU_ERR_INVALID; }
+        ds->fixed_len = (uint32_t)(n_words / n_examples);
+        ds->max_len = ds->fixed_len;
+    } else {
+        if (n_words >= (1ull << 32)) { delete ds; c->set_error("variable-length datasets are limited to 2^32 words"); return FWGPU_ERR_UNSUPPORTED; }
+        ds->max_len = host_max_len(rec_off, 0, n_examples);
+    }
+    cudaError_t e = cudaMalloc((void **)&ds->records, n_words * 4);
+    if (e == cudaSuccess) e = cudaMemcpy(ds->records, records, n_words * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && rec_off) {
+        e = cudaMalloc((void **)&ds->rec_off, (n_examples + 1) * 4);
+        if (e == cudaSuccess) e = cudaMemcpy(ds->rec_off, rec_off, (n_examples + 1) * 4, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        cudaFree(ds->records); cudaFree(ds->rec_off); delete ds;
+        c->set_error(std::string("dataset upload: ") + cudaGetErrorString(e));
+        return FWGPU_ERR_CUDA;
+    }
+    *out = ds;
+    return FWGPU_OK;
+}
+
+extern "C" void fwgpu_dataset_free(fwgpu_ctx *c, fwgpu_dataset *ds)
+{
+    if (!ds) return;
+    if (c) { cudaSetDevice(c->device); cudaStreamSynchronize(c->stream); }
+    cudaFree(ds->records); cudaFree(ds->rec_off);
+    delete ds;
+}
+
+extern "C" fwgpu_status fwgpu_dataset_learn(fwgpu_ctx *c, fwgpu_dataset *ds, uint64_t first, uint64_t count, float *preds_out, int update)
+{
+    if (!c || !ds || first + count > ds->n_examples) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (update && c->d.immutable) { c->set_error("This regressor is immutable, you cannot call learn() with update = true"); return FWGPU_ERR_IMMUTABLE; }
+    const uint32_t hdr = 3 + c->d.n_namespaces;
+    const uint32_t dyn_pairs = ds->max_len > hdr ? (ds->max_len - hdr + 1) / 2 : 0;
+    const size_t chunk = chunk_examples(c, derive_lr_stride(c, dyn_pairs), c->F ? derive_ffm_stride(c, dyn_pairs) : 1);
+    fwgpu_status st;
+    uint64_t done = 0;
+    while (done < count) {
+        const uint32_t cnt = (uint32_t)std::min<uint64_t>(chunk, count - done);
+        const uint64_t e0 = first + done;
+        RecView rv;
+        if (ds->rec_off) rv = RecView{ds->records, ds->rec_off + e0, 0, 0, ds->max_len};
+        else rv = RecView{ds->records + e0 * ds->fixed_len, nullptr, 0, ds->fixed_len, ds->max_len};
+        if ((st = translate_and_learn(c, rv, cnt, preds_out ? preds_out + done : nullptr, update, true))) return st;
+        done += cnt;
+    }
+    return FWGPU_OK;
+}
+
+// ---- weights ----------------------------------------------------------------------------------
+extern "C" fwgpu_status fwgpu_block_len(const fwgpu_ctx *c, int block, uint64_t *n_weights, uint64_t *n_bytes)
+{
+    if (!c) return FWGPU_ERR_INVALID;
+    const bool sgd = c->optimizer == FWGPU_OPT_SGD;
+    uint64_t n = 0, bytes = 0;
+    if (block == FWGPU_BLOCK_LR) { n = c->lr_len; bytes = n * (sgd ? 4 : 8); }
+    else if (block == FWGPU_BLOCK_FFM) { n = c->ffm_len; bytes = n * (sgd ? 4 : 8); }
+    else return FWGPU_ERR_INVALID;
+    if (n_weights) *n_weights = n;
+    if (n_bytes) *n_bytes = bytes;
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_export_block(fwgpu_ctx *c, int block, void *dst, uint64_t dst_bytes)
+{
+    uint64_t n = 0, bytes = 0;
+    if (!c || !dst || fwgpu_block_len(c, block, &n, &bytes) != FWGPU_OK) return FWGPU_ERR_INVALID;
+    if (dst_bytes < bytes) { c->set_error("export buffer too small"); return FWGPU_ERR_INVALID; }
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const bool sgd = c->optimizer == FWGPU_OPT_SGD;
+    if (block == FWGPU_BLOCK_LR) {
+        if (!sgd) { // {f32 w, f32 acc} x len, block_helpers.rs:23-28
+            CUDA_TRY(c, cudaMemcpyAsync(dst, c->lr, bytes, cudaMemcpyDeviceToHost, c->stream));
+        } else {
+            fwgpu_status st;
+            if ((st = ensure(c, c->csr, n * 4))) return st;
+            k_lr_extract_w<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr, (float *)c->csr.p, n);
+            c->launches++;
+            CUDA_TRY(c, cudaMemcpyAsync(dst, c->csr.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        }
+    } else {
+        if (n == 0) return FWGPU_OK;
+        CUDA_TRY(c, cudaMemcpyAsync(dst, c->ffm_w, n * 4, cudaMemcpyDeviceToHost, c->stream)); // weights, then accumulators (block_ffm.rs:835-848)
+        if (!sgd) CUDA_TRY(c, cudaMemcpyAsync((char *)dst + n * 4, c->ffm_acc, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    return fwgpu_sync(c);
+}
+
+extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *src, uint64_t src_bytes, int with_optimizer_state)
+{
+    uint64_t n = 0, bytes = 0;
+    if (!c || !src || fwgpu_block_len(c, block, &n, &bytes) != FWGPU_OK) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const bool sgd = c->optimizer == FWGPU_OPT_SGD;
+    const bool with_acc = with_optimizer_state && !sgd;
+    const uint64_t need = n * (with_acc ? 8 : 4);
+    if (src_bytes < need) { c->set_error("import payload too small"); return FWGPU_ERR_INVALID; }
+    if (block == FWGPU_BLOCK_LR) {
+        if (with_acc) CUDA_TRY(c, cudaMemcpyAsync(c->lr, src, n * 8, cudaMemcpyHostToDevice, c->stream));
+        else {
+            fwgpu_status st;
+            if ((st = ensure(c, c->csr, n * 4))) return st;
+            CUDA_TRY(c, cudaMemcpyAsync(c->csr.p, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+            const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? c->d.init_acc_gradient : 0.0f;
+            k_lr_set_w<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr, (const float *)c->csr.p, n, acc0);
+            c->launches++;
+        }
+    } else {
+        if (n == 0) return FWGPU_OK;
+        CUDA_TRY(c, cudaMemcpyAsync(c->ffm_w, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (with_acc) CUDA_TRY(c, cudaMemcpyAsync(c->ffm_acc, (const char *)src + n * 4, n * 4, cudaMemcpyHostToDevice, c->stream));
+        else if (!sgd) {
+            const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? c->d.ffm_init_acc_gradient : 0.0f;
+            k_fill<<<c->num_sms * 4, 256, 0, c->stream>>>(c->ffm_acc, n, acc0);
+            c->launches++;
+        }
+    }
+    return fwgpu_sync(c);
+}
+
+extern "C" fwgpu_status fwgpu_get_lut(const fwgpu_ctx *c, int which, float *dst)
+{
+    if (!c || !dst || which < 0 || which > 2) return FWGPU_ERR_INVALID;
+    memcpy(dst, c->lut_host[which], sizeof(float) * FWGPU_LUT_SIZE);
+    return FWGPU_OK;
+}

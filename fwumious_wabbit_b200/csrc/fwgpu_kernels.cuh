@@ -1,0 +1,509 @@
+// fwgpu_kernels.cuh -- sm_100a device code for the LR/FFM learn/predict hot path.
+//
+// One fused kernel per mini-batch (k_learn) replaces, per example, the reference's
+//   BlockLR::forward_backward      (block_lr.rs:123-151)
+//   BlockFFM::forward_backward     (block_ffm.rs:122-314)
+//   BlockTriangle                  (block_misc.rs:798-884)
+//   BlockSigmoid::forward_backward (block_loss_functions.rs:105-153)
+//   OptimizerAdagradLUT/Flex/SGD   (optimizer.rs:15-162)
+// and k_translate replaces FeatureBufferTranslator::translate (feature_buffer.rs:178-338).
+//
+// Design (DESIGN.md has the long form):
+//   * a group of T threads (32..256) owns one example at a time; groups stride over the batch;
+//   * gather: the F field-summed latent rows C[z][0..F*k) = sum_{j in field z} v_j * W[h_j .. h_j+F*k)
+//     are built straight from HBM with 128-bit ld.global.cg loads into shared memory -- for the
+//     usual one-feature-per-field example that is exactly one coalesced pass over the n rows;
+//   * forward: sum_{z<f} <C[f][z-block], C[z][f-block]> (+ the intra-field term of multi-valued
+//     fields) + LR dot, reduced with warp shuffles; sigmoid as block_loss_functions.rs:125-141;
+//   * backward: per slot grad = g * v_i * (C[z][f-block] - [z==f] v_i w_i[f-block]); AdaGrad
+//     accumulator via ATOMG.ADD.F32x4 (returns the old value, so in-flight examples that hit the
+//     same slot each see a larger accumulator, as sequential updates would) and the weight step
+//     via REDG.ADD.F32x4 -- lock-free, nothing is lost: Hogwild on device.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fwgpu {
+
+struct FastDiv { uint32_t d, m, s; };
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f) { return (__umulhi(n, f.m) + n) >> f.s; } // n < 2^31
+
+struct __align__(16) ExMeta {
+    float label, importance;
+    uint32_t lr_begin, lr_cnt;
+    uint32_t ffm_begin, ffm_cnt, pad0, pad1;
+};
+
+enum { OPT_SGD = 0, OPT_FLEX = 1, OPT_LUT = 2 };
+
+struct LearnParams {
+    // tables (HBM)
+    float2 *lr;          // {w, acc} x (1 << bit_precision)            block_lr.rs:19-25
+    float *ffm_w;        // (1 << ffm_bit_precision) + F*k (+ pad)      block_ffm.rs:40
+    float *ffm_acc;      //                                            block_ffm.rs:41
+    const float *lut_lr; // 2048, optimizer.rs:121-144
+    const float *lut_ffm;
+    // batch (HBM): AoS entries {hash, value bits, combo|field, 0}
+    const ExMeta *meta;
+    const uint4 *lr_ent;
+    const uint4 *ffm_ent;
+    float *preds;
+    uint32_t n_examples;
+    // shape
+    uint32_t F, k, Fk, cpr; // cpr = chunks (of VEC floats) per row
+    uint32_t n_cap;         // staging capacity: features per example
+    FastDiv div_cpr, div_k, div_F;
+    uint32_t optimizer;
+    float lr_lr, lr_mpt, ffm_lr, ffm_mpt; // learning rate / minus power_t (Flex, SGD)
+    int update;
+    uint32_t *err_flag;     // bit0: example exceeded n_cap
+    uint32_t group_smem_bytes;
+};
+
+// ---------------------------------------------------------------------------------------------
+template <int VEC> struct Vec;
+template <> struct Vec<4> { using T = float4; };
+template <> struct Vec<2> { using T = float2; };
+template <> struct Vec<1> { using T = float; };
+
+template <int VEC> __device__ __forceinline__ void ldcg_vec(const float *p, float (&o)[VEC]);
+template <> __device__ __forceinline__ void ldcg_vec<4>(const float *p, float (&o)[4]) { float4 v = __ldcg(reinterpret_cast<const float4 *>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+template <> __device__ __forceinline__ void ldcg_vec<2>(const float *p, float (&o)[2]) { float2 v = __ldcg(reinterpret_cast<const float2 *>(p)); o[0] = v.x; o[1] = v.y; }
+template <> __device__ __forceinline__ void ldcg_vec<1>(const float *p, float (&o)[1]) { o[0] = __ldcg(p); }
+
+// atomic add returning the old vector (ATOMG.E.ADD.F32x4 on sm_100a)
+template <int VEC> __device__ __forceinline__ void atom_add_vec(float *p, const float (&v)[VEC], float (&old)[VEC]);
+template <> __device__ __forceinline__ void atom_add_vec<4>(float *p, const float (&v)[4], float (&old)[4]) { float4 o = atomicAdd(reinterpret_cast<float4 *>(p), make_float4(v[0], v[1], v[2], v[3])); old[0] = o.x; old[1] = o.y; old[2] = o.z; old[3] = o.w; }
+template <> __device__ __forceinline__ void atom_add_vec<2>(float *p, const float (&v)[2], float (&old)[2]) { float2 o = atomicAdd(reinterpret_cast<float2 *>(p), make_float2(v[0], v[1])); old[0] = o.x; old[1] = o.y; }
+template <> __device__ __forceinline__ void atom_add_vec<1>(float *p, const float (&v)[1], float (&old)[1]) { old[0] = atomicAdd(p, v[0]); }
+
+// reduction without return (REDG.E.ADD.F32x4)
+template <int VEC> __device__ __forceinline__ void red_add_vec(float *p, const float (&v)[VEC]);
+template <> __device__ __forceinline__ void red_add_vec<4>(float *p, const float (&v)[4]) { asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory"); }
+template <> __device__ __forceinline__ void red_add_vec<2>(float *p, const float (&v)[2]) { asm volatile("red.global.add.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v[0]), "f"(v[1]) : "memory"); }
+template <> __device__ __forceinline__ void red_add_vec<1>(float *p, const float (&v)[1]) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v[0]) : "memory"); }
+
+template <int T> __device__ __forceinline__ void group_sync(int group_in_block)
+{
+    if (T == 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group_in_block + 1), "r"(T) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// optimizer.rs calculate_update given the accumulator value *after* adding g^2
+__device__ __forceinline__ float opt_step(uint32_t optimizer, float grad, float new_acc, const float *__restrict__ lut, float lr, float mpt)
+{
+    if (optimizer == OPT_LUT) { // optimizer.rs:147-156
+        uint32_t key = __float_as_uint(new_acc) >> 20;
+        return grad * __ldg(lut + key);
+    }
+    if (optimizer == OPT_FLEX) { // optimizer.rs:76-89
+        float u = grad * lr * powf(new_acc, mpt);
+        return (isnan(u) || isinf(u)) ? 0.0f : u;
+    }
+    return grad * lr; // optimizer.rs:35-37
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_learn<T, VEC>: T threads per example, VEC floats per memory transaction.
+// Block = 256 threads = 256/T groups.  Dynamic smem = groups * p.group_smem_bytes.
+// Group smem layout (floats): C[F*Fk] | d[n_cap*k] | val[n_cap] | hash[n_cap] | field[n_cap] | fstart[F+1] | red[8]
+// ---------------------------------------------------------------------------------------------
+template <int T, int VEC>
+__global__ void __launch_bounds__(256) k_learn(const LearnParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int GROUPS = 256 / T;
+    constexpr int NW = T / 32;
+    const int gib = threadIdx.x / T;      // group in block
+    const int tg = threadIdx.x % T;       // thread in group
+    const int lane = threadIdx.x & 31;
+    const int wg = tg >> 5;               // warp in group
+
+    float *C = reinterpret_cast<float *>(smem_raw + (size_t)gib * p.group_smem_bytes);
+    const uint32_t F = p.F, k = p.k, Fk = p.Fk, cpr = p.cpr, ncap = p.n_cap;
+    float *d = C + (size_t)F * Fk;
+    float *val = d + (size_t)ncap * k;
+    uint32_t *hash = reinterpret_cast<uint32_t *>(val + ncap);
+    uint32_t *field = hash + ncap;
+    uint32_t *fstart = field + ncap;
+    float *red = reinterpret_cast<float *>(fstart + F + 1);
+
+    const float *__restrict__ W = p.ffm_w;
+
+    for (uint32_t ex = blockIdx.x * GROUPS + gib; ex < p.n_examples; ex += gridDim.x * GROUPS) {
+        const ExMeta m = p.meta[ex];
+        const uint32_t n = m.ffm_cnt, nlr = m.lr_cnt;
+        const uint4 *__restrict__ fe = p.ffm_ent + m.ffm_begin;
+        const uint4 *__restrict__ le = p.lr_ent + m.lr_begin;
+        if (n > ncap) { // uniform over the group
+            if (tg == 0) { atomicOr(p.err_flag, 1u); p.preds[ex] = __int_as_float(0x7fc00000); }
+            continue;
+        }
+        float part = 0.0f;
+
+        if (F > 0) {
+            // ---- stage the example's feature list ------------------------------------------------
+            for (uint32_t i = tg; i < n; i += T) {
+                uint4 e = __ldg(fe + i);
+                hash[i] = e.x; val[i] = __uint_as_float(e.y); field[i] = e.z;
+            }
+            // fstart[f] = first entry whose field >= f (entries are sorted by field; feature_buffer.rs:314-335)
+            for (uint32_t f = tg; f <= F; f += T) {
+                uint32_t i = 0;
+                while (i < n && __ldg(&fe[i].z) < f) i++;
+                fstart[f] = i;
+            }
+            group_sync<T>(gib);
+
+            // ---- gather: C[z][:] = sum_{e in field z} v_e * W[h_e : h_e + Fk]  (block_ffm.rs:165-217) ----
+            const uint32_t total = F * cpr;
+            for (uint32_t idx0 = tg; idx0 < total; idx0 += 4 * T) {
+                float w[4][VEC];
+                uint32_t zz[4], cc[4], e0[4], e1[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t idx = idx0 + u * T;
+                    e0[u] = e1[u] = 0;
+                    if (idx < total) {
+                        zz[u] = fdiv(idx, p.div_cpr);
+                        cc[u] = idx - zz[u] * cpr;
+                        e0[u] = fstart[zz[u]];
+                        e1[u] = fstart[zz[u] + 1];
+                        if (e1[u] > e0[u]) ldcg_vec<VEC>(W + hash[e0[u]] + cc[u] * VEC, w[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t idx = idx0 + u * T;
+                    if (idx >= total) continue;
+                    const uint32_t z = zz[u], x0 = cc[u] * VEC;
+                    float acc[VEC];
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) acc[j] = 0.0f;
+                    for (uint32_t e = e0[u]; e < e1[u]; e++) {
+                        float wv[VEC];
+                        if (e == e0[u]) {
+#pragma unroll
+                            for (int j = 0; j < VEC; j++) wv[j] = w[u][j];
+                        } else {
+                            ldcg_vec<VEC>(W + hash[e] + x0, wv);
+                        }
+                        const float v = val[e];
+#pragma unroll
+                        for (int j = 0; j < VEC; j++) {
+                            // first feature assigns w*v, the rest accumulate (separate roundings as in the reference)
+                            float t = __fmul_rn(wv[j], v);
+                            acc[j] = (e == e0[u]) ? t : __fadd_rn(acc[j], t);
+                            uint32_t x = x0 + j;
+                            if (x >= z * k && x < z * k + k) d[e * k + (x - z * k)] = wv[j]; // own-field block of feature e
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) C[z * Fk + x0 + j] = acc[j];
+                }
+            }
+            group_sync<T>(gib);
+
+            // ---- forward: FFM outputs through the triangle (block_ffm.rs:219-261, block_misc.rs:862-884) ----
+            // sum over z<f of 2*out[f][z] + out[f][f], with out[f][z] = 0.5*sum_k C[f][zk..]*C[z][fk..]
+            const uint32_t FF = F * F;
+            for (uint32_t idx = tg; idx < FF; idx += T) {
+                const uint32_t f = fdiv(idx, p.div_F), z = idx - f * F;
+                if (z < f) {
+                    const float *a = C + f * Fk + z * k, *b = C + z * Fk + f * k;
+                    float s = 0.0f;
+                    for (uint32_t q = 0; q < k; q++) s = fmaf(a[q], b[q], s);
+                    part += s;
+                } else if (z == f) {
+                    const uint32_t b0 = fstart[f], b1 = fstart[f + 1];
+                    if (b1 - b0 > 1) { // intra-field pairs of a multi-valued field; a lone feature contributes exactly 0
+                        const float *cf = C + f * Fk + f * k;
+                        float s = 0.0f;
+                        for (uint32_t e = b0; e < b1; e++) {
+                            const float v = val[e];
+                            for (uint32_t q = 0; q < k; q++) {
+                                float wq = d[e * k + q];
+                                float g_ = v * (cf[q] - wq * v); // block_ffm.rs:238-243
+                                s = fmaf(wq, g_, s);
+                            }
+                        }
+                        part += 0.5f * s;
+                    }
+                }
+            }
+        }
+
+        // ---- LR forward (block_lr.rs:28-47) -------------------------------------------------------
+        for (uint32_t i = tg; i < nlr; i += T) {
+            uint4 e = __ldg(le + i);
+            float2 cell = __ldcg(p.lr + e.x);
+            part = fmaf(cell.x, __uint_as_float(e.y), part);
+        }
+
+        // ---- reduce over the group -----------------------------------------------------------------
+        float wsum = warp_sum(part);
+        if (NW > 1) {
+            if (lane == 0) red[wg] = wsum;
+            group_sync<T>(gib);
+            wsum = 0.0f;
+#pragma unroll
+            for (int w_ = 0; w_ < NW; w_++) wsum += red[w_];
+        }
+
+        // ---- sigmoid + logloss gradient (block_loss_functions.rs:105-153) ---------------------------
+        float pr, g;
+        if (isnan(wsum)) { pr = 0.5f; g = 0.0f; }
+        else if (wsum < -50.0f) { pr = 1.0f / (1.0f + expf(50.0f)); g = 0.0f; }
+        else if (wsum > 50.0f) { pr = 1.0f / (1.0f + expf(-50.0f)); g = 0.0f; }
+        else { pr = 1.0f / (1.0f + expf(-wsum)); g = -(m.label - pr) * m.importance; }
+        if (tg == 0) p.preds[ex] = pr;
+
+        // regressor.rs:366-370: update && importance != 0; a zero gradient changes nothing
+        const bool do_update = p.update && m.importance != 0.0f && g != 0.0f;
+        if (do_update) {
+            // ---- FFM update (block_ffm.rs:265-288): every d_out[f][z] equals g (triangle backward mirrors it) ----
+            if (F > 0) {
+                const uint32_t total = n * cpr;
+                for (uint32_t idx = tg; idx < total; idx += T) {
+                    const uint32_t e = fdiv(idx, p.div_cpr), c = idx - e * cpr;
+                    const uint32_t f = field[e], h = hash[e], x0 = c * VEC;
+                    const float v = val[e];
+                    float grad[VEC], gg[VEC], old[VEC];
+#pragma unroll
+                    for (int j = 0; j < VEC; j++) {
+                        const uint32_t x = x0 + j;
+                        const uint32_t z = fdiv(x, p.div_k), q = x - z * k;
+                        float cz = C[z * Fk + f * k + q];
+                        if (z == f) cz = cz - d[e * k + q] * v;
+                        grad[j] = g * (v * cz);
+                        gg[j] = grad[j] * grad[j];
+                    }
+                    float upd[VEC];
+                    if (p.optimizer == OPT_SGD) {
+#pragma unroll
+                        for (int j = 0; j < VEC; j++) upd[j] = -(grad[j] * p.ffm_lr);
+                    } else {
+                        atom_add_vec<VEC>(p.ffm_acc + h + x0, gg, old);
+#pragma unroll
+                        for (int j = 0; j < VEC; j++) upd[j] = -opt_step(p.optimizer, grad[j], old[j] + gg[j], p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    }
+                    red_add_vec<VEC>(p.ffm_w + h + x0, upd);
+                }
+            }
+            // ---- LR update (block_lr.rs:135-151); duplicates of one hash inside an example are applied
+            //      in buffer order by the first occurrence's thread (pinned by regressor.rs:629-656) ----
+            for (uint32_t i = tg; i < nlr; i += T) {
+                const uint4 e = __ldg(le + i);
+                bool owner = true;
+                for (uint32_t j = 0; j < i; j++) if (__ldg(&le[j].x) == e.x) { owner = false; break; }
+                if (!owner) continue;
+                float *cell = reinterpret_cast<float *>(p.lr + e.x);
+                for (uint32_t j = i; j < nlr; j++) {
+                    const uint4 ej = (j == i) ? e : __ldg(le + j);
+                    if (ej.x != e.x) continue;
+                    const float grad = g * __uint_as_float(ej.y);
+                    float upd;
+                    if (p.optimizer == OPT_SGD) upd = grad * p.lr_lr;
+                    else {
+                        const float gg = grad * grad;
+                        const float old = atomicAdd(cell + 1, gg);
+                        upd = opt_step(p.optimizer, grad, old + gg, p.lut_lr, p.lr_lr, p.lr_mpt);
+                    }
+                    atomicAdd(cell, -upd);
+                }
+            }
+        }
+        group_sync<T>(gib); // C / meta are reused by the next example
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Translate: raw record -> AoS feature lists (feature_buffer.rs:178-338), one thread per example.
+// ---------------------------------------------------------------------------------------------
+struct TranslateParams {
+    const uint32_t *records;   // words
+    const uint32_t *rec_off;   // [n+1] word offsets, or nullptr with fixed_len
+    uint32_t off_base;         // subtracted from rec_off values (chunked uploads)
+    uint32_t fixed_len;
+    uint32_t n_examples;
+    uint32_t n_namespaces;
+    const uint8_t *ns_is_f32;
+    uint32_t n_combos;
+    const uint32_t *combo_off, *combo_ns;
+    const float *combo_weight;
+    uint32_t add_constant;
+    uint32_t n_fields;
+    const uint32_t *field_off, *field_ns;
+    uint32_t lr_mask, ffm_mask, ffm_k;
+    uint32_t lr_stride, ffm_stride; // entries per example slab
+    ExMeta *meta;
+    uint4 *lr_ent, *ffm_ent;
+    uint32_t *err_flag; // bit1: slab overflow
+};
+
+// feature_reader! (feature_buffer.rs:48-108) for a primitive namespace: number of features and accessors
+struct NsView { const uint32_t *rec; uint32_t tok, start, cnt; bool single, f32; };
+__device__ __forceinline__ NsView ns_view(const uint32_t *rec, uint32_t ns, const uint8_t *is_f32)
+{
+    NsView v;
+    v.rec = rec;
+    v.tok = rec[3 + ns];
+    v.f32 = is_f32 ? (is_f32[ns] != 0) : false;
+    v.single = (v.tok & 0x80000000u) == 0;
+    if (v.single) { v.start = 0; v.cnt = 1; }
+    else {
+        uint32_t s = (v.tok >> 16) & 0x3fffu, e = v.tok & 0xffffu;
+        v.start = s;
+        v.cnt = e > s ? (e - s + 1) / 2 : 0; // (start..end).step_by(2)
+    }
+    return v;
+}
+__device__ __forceinline__ uint32_t ns_hash(const NsView &v, uint32_t i) { return v.single ? v.tok : v.rec[v.start + 2 * i]; }
+__device__ __forceinline__ float ns_val(const NsView &v, uint32_t i) { return (v.single || v.f32) ? 1.0f : __uint_as_float(v.rec[v.start + 2 * i + 1]); }
+
+#define FWGPU_MAX_COMBO_NS 8
+__global__ void __launch_bounds__(256) k_translate(const TranslateParams p)
+{
+    const uint32_t ex = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ex >= p.n_examples) return;
+    const uint32_t *rec = p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len);
+    ExMeta m;
+    m.label = (float)rec[1];                 // feature_buffer.rs:190
+    m.importance = __uint_as_float(rec[2]);  // :191-192
+    m.lr_begin = ex * p.lr_stride;
+    m.ffm_begin = ex * p.ffm_stride;
+    m.pad0 = m.pad1 = 0;
+    uint4 *lr = p.lr_ent + (size_t)m.lr_begin;
+    uint4 *ffm = p.ffm_ent + (size_t)m.ffm_begin;
+    uint32_t nlr = 0, nffm = 0;
+    bool overflow = false;
+
+    for (uint32_t c = 0; c < p.n_combos; c++) { // :197-268
+        const uint32_t o0 = p.combo_off[c], m_ns = p.combo_off[c + 1] - o0;
+        const float w = p.combo_weight[c];
+        if (m_ns == 1) {
+            NsView v = ns_view(rec, p.combo_ns[o0], p.ns_is_f32);
+            for (uint32_t i = 0; i < v.cnt; i++) {
+                if (nlr < p.lr_stride) lr[nlr] = make_uint4(ns_hash(v, i) & p.lr_mask, __float_as_uint(ns_val(v, i) * w), c, 0);
+                else overflow = true;
+                nlr++;
+            }
+        } else {
+            // chained interaction: h = (h * 16777619) ^ h_next, value product; last namespace varies fastest
+            NsView vs[FWGPU_MAX_COMBO_NS];
+            uint32_t total = 1;
+            for (uint32_t j = 0; j < m_ns && j < FWGPU_MAX_COMBO_NS; j++) { vs[j] = ns_view(rec, p.combo_ns[o0 + j], p.ns_is_f32); total *= vs[j].cnt; }
+            for (uint32_t t = 0; t < total; t++) {
+                uint32_t idxs[FWGPU_MAX_COMBO_NS], r = t;
+                for (int j = (int)m_ns - 1; j >= 0; j--) { idxs[j] = r % vs[j].cnt; r /= vs[j].cnt; }
+                uint32_t h = ns_hash(vs[0], idxs[0]);
+                float val = ns_val(vs[0], idxs[0]);
+                for (uint32_t j = 1; j < m_ns; j++) {
+                    h = (h * 16777619u) ^ ns_hash(vs[j], idxs[j]);
+                    val = val * ns_val(vs[j], idxs[j]);
+                }
+                if (nlr < p.lr_stride) lr[nlr] = make_uint4(h & p.lr_mask, __float_as_uint(val * w), c, 0);
+                else overflow = true;
+                nlr++;
+            }
+        }
+    }
+    if (p.add_constant) { // :270-276
+        if (nlr < p.lr_stride) lr[nlr] = make_uint4(11650396u & p.lr_mask, __float_as_uint(1.0f), p.n_combos, 0);
+        else overflow = true;
+        nlr++;
+    }
+    if (p.ffm_k > 0) { // :279-335
+        for (uint32_t f = 0; f < p.n_fields; f++) {
+            for (uint32_t j = p.field_off[f]; j < p.field_off[f + 1]; j++) {
+                NsView v = ns_view(rec, p.field_ns[j], p.ns_is_f32);
+                for (uint32_t i = 0; i < v.cnt; i++) {
+                    if (nffm < p.ffm_stride) ffm[nffm] = make_uint4(ns_hash(v, i) & p.ffm_mask, __float_as_uint(ns_val(v, i)), f, 0);
+                    else overflow = true;
+                    nffm++;
+                }
+            }
+        }
+    }
+    m.lr_cnt = nlr;
+    m.ffm_cnt = nffm;
+    if (overflow) {
+        atomicOr(p.err_flag, 2u);
+        if (nlr > p.lr_stride) m.lr_cnt = p.lr_stride;
+        // an over-long ffm list keeps its true count so k_learn flags and skips the example
+    }
+    p.meta[ex] = m;
+}
+
+// CSR (host layout of fwgpu_batch) -> AoS
+struct PackParams {
+    uint32_t n_examples;
+    const float *labels, *importance;
+    const uint32_t *lr_off, *lr_hash, *lr_combo; const float *lr_val;
+    const uint32_t *ffm_off, *ffm_hash, *ffm_field; const float *ffm_val;
+    uint32_t n_lr, n_ffm;
+    ExMeta *meta; uint4 *lr_ent, *ffm_ent;
+};
+__global__ void __launch_bounds__(256) k_pack(const PackParams p)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.n_examples) {
+        ExMeta m;
+        m.label = p.labels[i]; m.importance = p.importance[i];
+        m.lr_begin = p.lr_off[i]; m.lr_cnt = p.lr_off[i + 1] - p.lr_off[i];
+        m.ffm_begin = p.ffm_off ? p.ffm_off[i] : 0; m.ffm_cnt = p.ffm_off ? p.ffm_off[i + 1] - p.ffm_off[i] : 0;
+        m.pad0 = m.pad1 = 0;
+        p.meta[i] = m;
+    }
+    if (i < p.n_lr) p.lr_ent[i] = make_uint4(p.lr_hash[i], __float_as_uint(p.lr_val[i]), p.lr_combo[i], 0);
+    if (i < p.n_ffm) p.ffm_ent[i] = make_uint4(p.ffm_hash[i], __float_as_uint(p.ffm_val[i]), p.ffm_field[i], 0);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table initialisation (block_lr.rs:97-105, block_ffm.rs:784-829)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float merand48(uint64_t seed)
+{
+    const uint64_t a = 0xeece66d5deece66dULL, c = 2147483647ULL;
+    uint64_t s = a * seed + c;
+    return __uint_as_float((uint32_t)((s >> 25) & 0x7FFFFFu) | 0x3F800000u) - 1.0f;
+}
+__global__ void k_init_ffm(float *w, float *acc, uint32_t len, uint32_t alloc_len, float one_over_k_root, float init_acc,
+                           float init_width, float zero_band, float center)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < alloc_len; i += (size_t)gridDim.x * blockDim.x) {
+        float wv = 0.0f;
+        if (i < len) {
+            if (init_width == 0.0f) wv = __fmul_rn(__fsub_rn(1.0f * merand48((uint64_t)len + i), 0.5f), one_over_k_root);
+            else {
+                float zero_half_band_width = init_width * zero_band * 0.5f;
+                float band_width = init_width * (1.0f - zero_band);
+                wv = __fsub_rn(__fmul_rn(merand48((uint64_t)i), band_width), band_width * 0.5f);
+                if (wv > 0.0f) wv += zero_half_band_width; else wv -= zero_half_band_width;
+                wv += center;
+            }
+        }
+        w[i] = wv;
+        if (acc) acc[i] = init_acc;
+    }
+}
+__global__ void k_init_lr(float2 *t, size_t len, float init_acc)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < len; i += (size_t)gridDim.x * blockDim.x) t[i] = make_float2(0.0f, init_acc);
+}
+__global__ void k_fill(float *p, size_t n, float v)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// LR export/import helpers: AoS {w,acc} <-> weights-only
+__global__ void k_lr_extract_w(const float2 *t, float *w, size_t n) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) w[i] = t[i].x; }
+__global__ void k_lr_set_w(float2 *t, const float *w, size_t n, float acc) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) t[i] = make_float2(w[i], acc); }
+
+} // namespace fwgpu

@@ -1,0 +1,111 @@
+"""Synthetic workloads of BASELINE.json's configs: records in the reference's cache format
+(parser.rs:57-74) produced by the C++ generator in csrc/host/synth.cpp, plus the matching
+ModelInstance (the flags SURVEY.md section 8d lists for each config)."""
+import ctypes as C
+import string
+
+import numpy as np
+
+from . import _lib
+from .model_instance import ModelInstance, Optimizer
+
+NS_LETTERS = string.ascii_uppercase + string.ascii_lowercase
+
+
+def _host():
+    L = _lib.lib()
+    if not getattr(L, "_synth_bound", False):
+        L.fwhost_murmur3_32.restype = C.c_uint32
+        L.fwhost_murmur3_32.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
+        L.fwhost_synth_records.restype = C.c_int
+        L.fwhost_synth_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_char_p, C.c_void_p,
+                                           C.c_uint64, C.c_int]
+        L.fwhost_synth_line.restype = C.c_int
+        L.fwhost_synth_line.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_char_p, C.c_void_p, C.c_uint64]
+        L._synth_bound = True
+    return L
+
+
+def murmur3_32(data: bytes, seed: int = 0) -> int:
+    return _host().fwhost_murmur3_32(data, len(data), seed)
+
+
+class Workload:
+    """name, ModelInstance, namespace letters and cardinalities."""
+
+    def __init__(self, name, mi, ns_names, cardinality, description):
+        self.name, self.mi, self.ns_names = name, mi, ns_names
+        self.cardinality = np.asarray(cardinality, dtype=np.uint32)
+        self.description = description
+
+    @property
+    def n_namespaces(self):
+        return len(self.ns_names)
+
+    @property
+    def record_len(self):
+        return 3 + self.n_namespaces
+
+    def records(self, n_examples, first=0, seed=1, out=None, threads=0):
+        """(n_examples, 3 + N) uint32 array of fixed-width records."""
+        if out is None:
+            out = np.empty((n_examples, self.record_len), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= n_examples * self.record_len
+        rc = _host().fwhost_synth_records(out.ctypes.data_as(C.c_void_p), n_examples, first, self.n_namespaces,
+                                          self.ns_names.encode(), self.cardinality.ctypes.data_as(C.c_void_p), seed, threads)
+        if rc != 0:
+            raise RuntimeError("fwhost_synth_records failed")
+        return out
+
+    def line(self, i, seed=1) -> str:
+        buf = C.create_string_buffer(64 + 24 * self.n_namespaces)
+        n = _host().fwhost_synth_line(buf, len(buf), i, self.n_namespaces, self.ns_names.encode(),
+                                      self.cardinality.ctypes.data_as(C.c_void_p), seed)
+        if n < 0:
+            raise RuntimeError("fwhost_synth_line failed")
+        return buf.value.decode()
+
+    # algorithmic bytes per example, SURVEY.md section 8(d)
+    def algorithmic_bytes_per_example(self, train=True):
+        mi = self.mi
+        F = len(mi.ffm_fields) if mi.ffm_k else 0
+        n_lr = mi.num_combos
+        inp = 4 * (3 + self.n_namespaces)
+        if train:
+            return 16 * F * F * mi.ffm_k + 16 * n_lr + inp + 4
+        return 4 * F * F * mi.ffm_k + 4 * n_lr + inp + 4
+
+
+def _mi(n_ns, *, ffm_k, ffm_bits, bits, interactions=(), lr=0.1, ffm_lr=0.05, power_t=0.5):
+    mi = ModelInstance()
+    mi.num_namespaces = n_ns
+    mi.feature_combo_descs = [([j], 1.0) for j in range(n_ns)] + [(list(c), 1.0) for c in interactions]
+    mi.add_constant_feature = True
+    mi.bit_precision = bits
+    mi.learning_rate, mi.power_t = lr, power_t
+    mi.ffm_k, mi.ffm_bit_precision = ffm_k, ffm_bits
+    mi.ffm_fields = [[j] for j in range(n_ns)] if ffm_k else []
+    mi.ffm_learning_rate, mi.ffm_power_t = ffm_lr, power_t
+    mi.optimizer = Optimizer.AdagradLUT  # --adaptive with fastmath (model_instance.rs:481-492)
+    mi.init_acc_gradient, mi.ffm_init_acc_gradient = 1.0, 0.0
+    return mi
+
+
+def workload(name: str) -> Workload:
+    """BASELINE.json configs: c1 (LR only), c2 (FFM k=4, 8 fields), c3 (FFM k=8, 39 fields, Criteo shape),
+    c4 (c3 with ffm_bit_precision 28)."""
+    if name == "c1":
+        # benchmark/generate.py shape with 6 random namespaces -> A..H; --interactions AB, -b 18, power_t 0
+        mi = _mi(8, ffm_k=0, ffm_bits=18, bits=18, interactions=[(0, 1)], lr=0.1, power_t=0.0)
+        return Workload("c1", mi, NS_LETTERS[:8], [1000] * 8,
+                        "LR-only, 8 namespaces A..H + interaction AB, bit_precision=18, AdagradLUT power_t=0")
+    if name == "c2":
+        mi = _mi(8, ffm_k=4, ffm_bits=20, bits=18)
+        return Workload("c2", mi, NS_LETTERS[:8], [100000] * 8,
+                        "FFM k=4, 8 fields (one namespace each, 1e5 Zipf ids), ffm_bit_precision=20, -b 18")
+    if name in ("c3", "c4"):
+        card = [100] * 13 + [10 ** (3 + (j % 5)) for j in range(26)]  # 13 binned numeric + 26 categorical 1e3..1e7
+        mi = _mi(39, ffm_k=8, ffm_bits=24 if name == "c3" else 28, bits=24)
+        return Workload(name, mi, NS_LETTERS[:39], card,
+                        f"FFM k=8, 39 fields (Criteo shape: 13 low-card + 26 high-card), ffm_bit_precision={mi.ffm_bit_precision}, -b 24")
+    raise KeyError(name)

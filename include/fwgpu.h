@@ -1,0 +1,188 @@
+/*
+ * fwgpu.h -- C ABI of the B200-native (sm_100a) replacement for Fwumious Wabbit's
+ * LR / FFM learn / predict hot path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, no C++/torch types.  Each entry point
+ * cites the reference interface it replaces (file:line under the reference's src/).  The
+ * reference has no FFI for training (its only extern "C" surface is predict-only, lib.rs:151-235);
+ * these are the functions a Rust host would bind with `extern "C"` in place of the trait-object
+ * calls it makes today -- INTEGRATION.md shows that binding.
+ *
+ * Conventions (modelled on lib.rs:47-48, 237-243 and SURVEY.md section 8b):
+ *   - every function returns fwgpu_status (0 = ok, < 0 = error); nothing unwinds across the ABI;
+ *     fwgpu_last_error(ctx) returns a human-readable message for the last failure on that ctx;
+ *   - one ctx per GPU; calls on one ctx are serialised on its compute stream, and are
+ *     asynchronous with respect to the host: results (predictions written to host buffers,
+ *     exported weights) are valid after fwgpu_sync() returns;
+ *   - caller-owned host buffers must stay alive and unmodified until the next fwgpu_sync();
+ *     pinned buffers (fwgpu_host_alloc) make the copies truly asynchronous;
+ *   - no CPU fallback exists: without a CUDA device fwgpu_create fails with FWGPU_ERR_CUDA.
+ */
+#ifndef FWGPU_H
+#define FWGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int32_t fwgpu_status;
+enum {
+    FWGPU_OK = 0,
+    FWGPU_ERR_INVALID = -1,     /* bad argument / descriptor                                  */
+    FWGPU_ERR_CUDA = -2,        /* CUDA runtime error (message in fwgpu_last_error)            */
+    FWGPU_ERR_UNSUPPORTED = -3, /* configuration outside what the kernels implement            */
+    FWGPU_ERR_TOO_LARGE = -4,   /* an example does not fit the kernel's shared-memory staging  */
+    FWGPU_ERR_IMMUTABLE = -5,   /* learn(update=1) on a forward-only ctx (regressor.rs:362-365) */
+    FWGPU_ERR_NCCL = -6
+};
+
+/* model_instance.rs:24-29 Optimizer */
+enum { FWGPU_OPT_SGD = 0, FWGPU_OPT_ADAGRAD_FLEX = 1, FWGPU_OPT_ADAGRAD_LUT = 2 };
+/* weight blocks in the order regressor.rs:426-442 serialises them */
+enum { FWGPU_BLOCK_LR = 0, FWGPU_BLOCK_FFM = 1, FWGPU_BLOCK_NN0 = 2 /* + layer index */ };
+
+#define FWGPU_MAX_NN_LAYERS 8
+#define FWGPU_LUT_SIZE 2048 /* optimizer.rs:101-102 */
+
+/*
+ * The part of ModelInstance (model_instance.rs:47-97) the hot path reads, plus the flattened
+ * feature_combo_descs / ffm_fields that FeatureBufferTranslator (feature_buffer.rs:138-172) needs
+ * for the raw-record entry points.  All arrays are copied by fwgpu_create.
+ */
+typedef struct fwgpu_model_desc {
+    /* optimizer hyper-parameters per block: block_lr.rs:63-65, block_ffm.rs:87-91, block_neural.rs:108-109 */
+    float learning_rate, power_t, init_acc_gradient;
+    float ffm_learning_rate, ffm_power_t, ffm_init_acc_gradient;
+    float nn_learning_rate, nn_power_t, nn_init_acc_gradient;
+    uint32_t bit_precision;     /* LR table = 1 << bit_precision cells (block_lr.rs:67)            */
+    uint32_t ffm_bit_precision; /* FFM table = (1 << ffm_bit_precision) + F*k (block_ffm.rs:93-94) */
+    uint32_t ffm_k;             /* 0 = no FFM block (regressor.rs:184)                             */
+    uint32_t ffm_num_fields;    /* F = ffm_fields.len()                                            */
+    uint32_t num_combos;        /* feature_combo_descs.len() + add_constant (block_lr.rs:52-55)    */
+    uint32_t optimizer;         /* FWGPU_OPT_*                                                     */
+    uint32_t immutable;         /* 1 = forward-only regressor (regressor.rs:471-534): SGD, no accumulators */
+    float ffm_init_width, ffm_init_zero_band, ffm_init_center; /* block_ffm.rs:796-822 */
+    /* dense head, topology "one" (regressor.rs:191-320); 0 layers = none */
+    uint32_t nn_num_layers;
+    uint32_t nn_width[FWGPU_MAX_NN_LAYERS];
+    uint32_t nn_relu[FWGPU_MAX_NN_LAYERS];
+    /* translate spec (only needed for fwgpu_*_records) */
+    uint32_t n_namespaces;        /* vwmap.rs:31 num_namespaces                               */
+    const uint8_t *ns_is_f32;     /* [n_namespaces] NamespaceFormat::F32 (vwmap.rs:16-20)      */
+    uint32_t n_combos;            /* feature_combo_descs.len() (without the constant)          */
+    const uint32_t *combo_off;    /* [n_combos+1] offsets into combo_ns                        */
+    const uint32_t *combo_ns;     /* namespace_index of every descriptor of every combo        */
+    const float *combo_weight;    /* [n_combos] FeatureComboDesc.weight                        */
+    uint32_t add_constant;        /* add_constant_feature                                      */
+    const uint32_t *field_off;    /* [ffm_num_fields+1] offsets into field_ns                  */
+    const uint32_t *field_ns;     /* namespace_index of every namespace of every field         */
+    uint32_t max_ffm_per_example; /* 0 = derive (one feature per field namespace); raise for multi-valued namespaces */
+    uint32_t max_lr_per_example;  /* 0 = derive                                                */
+} fwgpu_model_desc;
+
+/*
+ * A mini-batch of translated examples = B reference FeatureBuffers (feature_buffer.rs:10-31) in
+ * CSR form.  lr_*: HashAndValue{hash,value,combo_index}; ffm_*: HashAndValueAndSeq with the plain
+ * field index (contra_field_index / ffm_k), sorted by field inside each example exactly as
+ * translate emits them.  Hashes are already masked (feature_buffer.rs:140-148).
+ */
+typedef struct fwgpu_batch {
+    uint32_t n_examples;
+    const float *labels;       /* [B]  FeatureBuffer.label              */
+    const float *importance;   /* [B]  FeatureBuffer.example_importance */
+    const uint32_t *lr_off;    /* [B+1] */
+    const uint32_t *lr_hash;
+    const float *lr_val;
+    const uint32_t *lr_combo;
+    const uint32_t *ffm_off;   /* [B+1] (may be NULL when ffm_k == 0) */
+    const uint32_t *ffm_hash;
+    const float *ffm_val;
+    const uint32_t *ffm_field;
+} fwgpu_batch;
+
+typedef struct fwgpu_ctx fwgpu_ctx;
+typedef struct fwgpu_dataset fwgpu_dataset; /* records resident in HBM */
+
+/* ---- lifecycle ---------------------------------------------------------------------------- */
+
+/* Regressor::new = new_without_weights + allocate_and_init_weights (regressor.rs:153-165, 173-345):
+ * allocates the tables in HBM and initialises them like the reference (LR zeros block_lr.rs:97-105,
+ * FFM merand48 block_ffm.rs:784-829), builds the AdaGrad look-up tables (optimizer.rs:121-144). */
+fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **out);
+void fwgpu_destroy(fwgpu_ctx *ctx);
+const char *fwgpu_last_error(const fwgpu_ctx *ctx); /* ctx may be NULL: last create() failure */
+fwgpu_status fwgpu_sync(fwgpu_ctx *ctx);
+void *fwgpu_stream(fwgpu_ctx *ctx);            /* the ctx's cudaStream_t, for event timing by the caller */
+uint64_t fwgpu_launch_count(const fwgpu_ctx *ctx); /* kernels launched by this ctx so far */
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+
+/* Regressor::learn (regressor.rs:356-379) over a mini-batch: forward, prediction out, and when
+ * update != 0 (and importance != 0) backward + per-weight optimizer update, Hogwild-style with
+ * device atomics.  preds_out: host pointer, [n_examples], the probability before the update. */
+fwgpu_status fwgpu_learn_batch(fwgpu_ctx *ctx, const fwgpu_batch *batch, float *preds_out, int update);
+
+/* Regressor::predict (regressor.rs:381-395) over a mini-batch. */
+fwgpu_status fwgpu_predict_batch(fwgpu_ctx *ctx, const fwgpu_batch *batch, float *preds_out);
+
+/* FeatureBufferTranslator::translate + Regressor::learn, i.e. the body of the reference's train
+ * loop (main.rs:240-256) and of a Hogwild worker (hogwild.rs:93-100), on raw parser/cache records
+ * (parser.rs:57-74).  records: n_words u32 words holding n_examples records back to back;
+ * rec_off: [n_examples+1] word offsets of each record, or NULL when every record has the fixed
+ * length n_words / n_examples.  Translation runs on the device and is bit-exact with the reference. */
+fwgpu_status fwgpu_learn_records(fwgpu_ctx *ctx, const uint32_t *records, uint64_t n_words,
+                                 const uint32_t *rec_off, uint32_t n_examples, float *preds_out, int update);
+
+/* The translated form of a record batch, for bit-exact comparison with the reference's translate
+ * (feature_buffer.rs:178-338).  Fills caller arrays (host); capacities in entries; counts returned
+ * through lr_off/ffm_off [n_examples+1].  Synchronous. */
+fwgpu_status fwgpu_translate_records(fwgpu_ctx *ctx, const uint32_t *records, uint64_t n_words,
+                                     const uint32_t *rec_off, uint32_t n_examples,
+                                     float *labels, float *importance,
+                                     uint32_t *lr_off, uint32_t *lr_hash, float *lr_val, uint32_t *lr_combo, uint64_t lr_cap,
+                                     uint32_t *ffm_off, uint32_t *ffm_hash, float *ffm_val, uint32_t *ffm_field, uint64_t ffm_cap);
+
+/* Records kept resident in HBM (the input cache of cache.rs held on the device): upload once,
+ * then learn over [first, first+count) slices without host traffic.  preds_out may be NULL. */
+fwgpu_status fwgpu_dataset_upload(fwgpu_ctx *ctx, const uint32_t *records, uint64_t n_words,
+                                  const uint32_t *rec_off, uint64_t n_examples, fwgpu_dataset **out);
+fwgpu_status fwgpu_dataset_learn(fwgpu_ctx *ctx, fwgpu_dataset *ds, uint64_t first, uint64_t count,
+                                 float *preds_out, int update);
+void fwgpu_dataset_free(fwgpu_ctx *ctx, fwgpu_dataset *ds);
+
+/* ---- weights (regressor.rs:426-469 write_weights_to_buf / overwrite_weights_from_buf) ------ */
+
+/* BlockTrait::get_serialized_len (block_lr.rs:257-259, block_ffm.rs:831-833, block_neural.rs:414-416):
+ * number of weights of a block; bytes = what the reference writes for that block
+ * (LR: len * 8 {w,acc} or len * 4 for SGD; FFM/NN: len*4 weights then len*4 accumulators, SGD: weights only). */
+fwgpu_status fwgpu_block_len(const fwgpu_ctx *ctx, int block, uint64_t *n_weights, uint64_t *n_bytes);
+/* write_weights_to_buf for one block in the reference byte layout (block_helpers.rs:99-124). Synchronous. */
+fwgpu_status fwgpu_export_block(fwgpu_ctx *ctx, int block, void *dst, uint64_t dst_bytes);
+/* read_weights_from_buf (block_helpers.rs:43-60).  with_optimizer_state = 0 reads a weights-only
+ * payload (read_weights_from_buf_into_forward_only, block_lr.rs:277-292, block_ffm.rs:879-899). */
+fwgpu_status fwgpu_import_block(fwgpu_ctx *ctx, int block, const void *src, uint64_t src_bytes, int with_optimizer_state);
+/* the AdaGrad LUT of a block (which: 0 lr, 1 ffm, 2 nn), 2048 floats, for inspection */
+fwgpu_status fwgpu_get_lut(const fwgpu_ctx *ctx, int which, float *dst2048);
+
+/* ---- measurement helpers ------------------------------------------------------------------ */
+
+/* When enabled, every hot-path kernel launch is bracketed by CUDA events on the ctx stream;
+ * fwgpu_kernel_time returns the accumulated device time and launch count per kernel kind
+ * (0 = learn/predict kernel, 1 = translate kernels). */
+fwgpu_status fwgpu_set_profiling(fwgpu_ctx *ctx, int enabled);
+fwgpu_status fwgpu_kernel_time(fwgpu_ctx *ctx, int kind, double *total_ms, uint64_t *launches);
+
+/* pinned host memory for batch buffers (SURVEY.md section 8b "Batch layout") */
+fwgpu_status fwgpu_host_alloc(void **out, uint64_t bytes);
+void fwgpu_host_free(void *p);
+
+/* library identity: "fwgpu <version> sm_100a" */
+const char *fwgpu_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
