@@ -34,6 +34,7 @@ class ModelDesc(C.Structure):
         ("add_constant", C.c_uint32),
         ("field_off", u32p), ("field_ns", u32p),
         ("max_ffm_per_example", C.c_uint32), ("max_lr_per_example", C.c_uint32),
+        ("hogwild_ramp_div", C.c_uint32),
     ]
 
 
@@ -89,6 +90,9 @@ def lib():
     L.fwgpu_export_block.argtypes = [vp, C.c_int, vp, C.c_uint64]
     L.fwgpu_import_block.argtypes = [vp, C.c_int, vp, C.c_uint64, C.c_int]
     L.fwgpu_get_lut.argtypes = [vp, C.c_int, vp]
+    L.fwgpu_set_examples_seen.argtypes = [vp, C.c_uint64]
+    L.fwgpu_get_examples_seen.argtypes = [vp]
+    L.fwgpu_get_examples_seen.restype = C.c_uint64
     L.fwgpu_set_profiling.argtypes = [vp, C.c_int]
     L.fwgpu_kernel_time.argtypes = [vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.fwgpu_host_alloc.argtypes = [C.POINTER(vp), C.c_uint64]
@@ -97,7 +101,7 @@ def lib():
     for name in ("fwgpu_create", "fwgpu_sync", "fwgpu_learn_batch", "fwgpu_predict_batch", "fwgpu_learn_records",
                  "fwgpu_translate_records", "fwgpu_dataset_upload", "fwgpu_dataset_learn", "fwgpu_block_len",
                  "fwgpu_export_block", "fwgpu_import_block", "fwgpu_get_lut", "fwgpu_set_profiling",
-                 "fwgpu_kernel_time", "fwgpu_host_alloc"):
+                 "fwgpu_kernel_time", "fwgpu_host_alloc", "fwgpu_set_examples_seen"):
         getattr(L, name).restype = C.c_int32
     _lib = L
     return L
@@ -109,5 +113,6 @@ EXPORTED_SYMBOLS = [
     "fwgpu_learn_batch", "fwgpu_predict_batch", "fwgpu_learn_records", "fwgpu_translate_records",
     "fwgpu_dataset_upload", "fwgpu_dataset_learn", "fwgpu_dataset_free",
     "fwgpu_block_len", "fwgpu_export_block", "fwgpu_import_block", "fwgpu_get_lut",
+    "fwgpu_set_examples_seen", "fwgpu_get_examples_seen",
     "fwgpu_set_profiling", "fwgpu_kernel_time", "fwgpu_host_alloc", "fwgpu_host_free", "fwgpu_version",
 ]

@@ -95,6 +95,9 @@ struct fwgpu_ctx {
     size_t smem_optin = 0;
     int force_T = 0;
     uint64_t launches = 0;
+    uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
+    uint32_t ramp_div = 32;
+    bool ramp_finished = false;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[2];
     std::vector<cudaEvent_t> ev_pool;
@@ -279,6 +282,8 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     if ((st = upload_vec(c, c->field_off, &c->d_field_off))) return st;
     if ((st = upload_vec(c, c->field_ns, &c->d_field_ns))) return st;
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
+    c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 32;
+    if (const char *t = getenv("FWGPU_RAMP_DIV")) c->ramp_div = (uint32_t)strtoul(t, nullptr, 10);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return FWGPU_OK;
 }
@@ -371,7 +376,7 @@ extern "C" fwgpu_status fwgpu_kernel_time(fwgpu_ctx *c, int kind, double *total_
 }
 
 // ---- learn kernel launch ----------------------------------------------------------------------
-template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const LearnParams &p, size_t smem)
+template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
 {
     auto kern = k_learn<T, VEC>;
     static thread_local size_t configured = 0;
@@ -387,18 +392,20 @@ template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const
     constexpr int GROUPS = 256 / T;
     uint32_t need = (p.n_examples + GROUPS - 1) / GROUPS;
     uint32_t grid = std::min<uint32_t>(need, (uint32_t)(c->num_sms * per_sm));
+    if (p.max_groups) grid = std::min<uint32_t>(grid, (p.max_groups + GROUPS - 1) / GROUPS);
+    if (full_groups) *full_groups = (uint32_t)(c->num_sms * per_sm) * GROUPS;
     if (grid == 0) return cudaSuccess;
     kern<<<grid, 256, smem, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
 }
 
-template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnParams &p, size_t smem)
+template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
 {
     switch (c->VEC) {
-    case 4: return launch_learn_tv<T, 4>(c, p, smem);
-    case 2: return launch_learn_tv<T, 2>(c, p, smem);
-    default: return launch_learn_tv<T, 1>(c, p, smem);
+    case 4: return launch_learn_tv<T, 4>(c, p, smem, full_groups);
+    case 2: return launch_learn_tv<T, 2>(c, p, smem, full_groups);
+    default: return launch_learn_tv<T, 1>(c, p, smem, full_groups);
     }
 }
 
@@ -415,7 +422,7 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
     p.optimizer = c->optimizer;
     p.lr_lr = c->d.learning_rate; p.lr_mpt = -c->d.power_t; p.ffm_lr = c->d.ffm_learning_rate; p.ffm_mpt = -c->d.ffm_power_t;
     p.update = update; p.err_flag = c->err_flag;
-    size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 8;
+    size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 16;
     size_t group_bytes = ((words * 4 + 15) / 16) * 16;
     p.group_smem_bytes = (uint32_t)group_bytes;
     int T = 32;
@@ -428,15 +435,41 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
         c->set_error("example staging needs " + std::to_string(smem) + " B of shared memory (> " + std::to_string(c->smem_optin) + "): F*F*k or features per example too large");
         return FWGPU_ERR_TOO_LARGE;
     }
-    ProfScope ps(c, 0);
-    cudaError_t e;
-    switch (T) {
-    case 32: e = launch_learn_t<32>(c, p, smem); break;
-    case 64: e = launch_learn_t<64>(c, p, smem); break;
-    case 128: e = launch_learn_t<128>(c, p, smem); break;
-    default: e = launch_learn_t<256>(c, p, smem); break;
+    // Concurrency ramp (DESIGN.md "semantics"): a cold model is trained with examples_seen / ramp_div examples
+    // in flight; segments double until the whole machine is in use.  Predict-only launches are never limited.
+    uint32_t done = 0;
+    while (done < n_examples) {
+        uint32_t cnt = n_examples - done;
+        uint32_t cap = 0;
+        if (update && c->ramp_div != 0xffffffffu && !c->ramp_finished) {
+            const uint64_t seen = c->examples_seen;
+            cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(seen / c->ramp_div, 1), 1u << 30);
+            const uint64_t seg_end = std::max<uint64_t>(2 * seen, c->ramp_div);
+            cnt = (uint32_t)std::min<uint64_t>(cnt, seg_end - seen);
+        }
+        LearnParams q = p;
+        q.meta = p.meta + done;
+        q.preds = p.preds + done;
+        q.n_examples = cnt;
+        q.max_groups = cap;
+        uint32_t full_groups = 0;
+        cudaError_t e;
+        {
+            ProfScope ps(c, 0);
+            switch (T) {
+            case 32: e = launch_learn_t<32>(c, q, smem, &full_groups); break;
+            case 64: e = launch_learn_t<64>(c, q, smem, &full_groups); break;
+            case 128: e = launch_learn_t<128>(c, q, smem, &full_groups); break;
+            default: e = launch_learn_t<256>(c, q, smem, &full_groups); break;
+            }
+        }
+        if (e != cudaSuccess) { c->set_error(std::string("k_learn launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+        if (update) {
+            c->examples_seen += cnt;
+            if (cap && full_groups && cap >= full_groups) c->ramp_finished = true;
+        }
+        done += cnt;
     }
-    if (e != cudaSuccess) { c->set_error(std::string("k_learn launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
     return FWGPU_OK;
 }
 
@@ -794,6 +827,7 @@ extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *
     const bool with_acc = with_optimizer_state && !sgd;
     const uint64_t need = n * (with_acc ? 8 : 4);
     if (src_bytes < need) { c->set_error("import payload too small"); return FWGPU_ERR_INVALID; }
+    if (with_acc) { c->examples_seen = std::max<uint64_t>(c->examples_seen, 1ull << 40); c->ramp_finished = true; }
     if (block == FWGPU_BLOCK_LR) {
         if (with_acc) CUDA_TRY(c, cudaMemcpyAsync(c->lr, src, n * 8, cudaMemcpyHostToDevice, c->stream));
         else {
@@ -816,6 +850,15 @@ extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *
     }
     return fwgpu_sync(c);
 }
+
+extern "C" fwgpu_status fwgpu_set_examples_seen(fwgpu_ctx *c, uint64_t n)
+{
+    if (!c) return FWGPU_ERR_INVALID;
+    c->examples_seen = n;
+    c->ramp_finished = false;
+    return FWGPU_OK;
+}
+extern "C" uint64_t fwgpu_get_examples_seen(const fwgpu_ctx *c) { return c ? c->examples_seen : 0; }
 
 extern "C" fwgpu_status fwgpu_get_lut(const fwgpu_ctx *c, int which, float *dst)
 {

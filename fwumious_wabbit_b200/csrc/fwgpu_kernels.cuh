@@ -58,6 +58,7 @@ struct LearnParams {
     int update;
     uint32_t *err_flag;     // bit0: example exceeded n_cap
     uint32_t group_smem_bytes;
+    uint32_t max_groups;    // 0 = all resident groups; else cap on examples in flight (concurrency ramp)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -113,7 +114,7 @@ __device__ __forceinline__ float opt_step(uint32_t optimizer, float grad, float 
 // ---------------------------------------------------------------------------------------------
 // k_learn<T, VEC>: T threads per example, VEC floats per memory transaction.
 // Block = 256 threads = 256/T groups.  Dynamic smem = groups * p.group_smem_bytes.
-// Group smem layout (floats): C[F*Fk] | d[n_cap*k] | val[n_cap] | hash[n_cap] | field[n_cap] | fstart[F+1] | red[8]
+// Group smem layout (floats): C[F*Fk] | d[n_cap*k] | val[n_cap] | hash[n_cap] | field[n_cap] | fstart[F+1] | red[16]
 // ---------------------------------------------------------------------------------------------
 template <int T, int VEC>
 __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
@@ -137,7 +138,12 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
 
     const float *__restrict__ W = p.ffm_w;
 
-    for (uint32_t ex = blockIdx.x * GROUPS + gib; ex < p.n_examples; ex += gridDim.x * GROUPS) {
+    uint32_t n_groups = gridDim.x * GROUPS;
+    if (p.max_groups && p.max_groups < n_groups) n_groups = p.max_groups;
+    const uint32_t gid = blockIdx.x * GROUPS + gib;
+    if (gid >= n_groups) return; // whole groups leave; the named barriers below are per group
+
+    for (uint32_t ex = gid; ex < p.n_examples; ex += n_groups) {
         const ExMeta m = p.meta[ex];
         const uint32_t n = m.ffm_cnt, nlr = m.lr_cnt;
         const uint4 *__restrict__ fe = p.ffm_ent + m.ffm_begin;
@@ -147,6 +153,7 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
             continue;
         }
         float part = 0.0f;
+        bool overlap = false;
 
         if (F > 0) {
             // ---- stage the example's feature list ------------------------------------------------
@@ -211,6 +218,19 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
             }
             group_sync<T>(gib);
 
+            // Windows of two features of one example may overlap (the mask aligns rows to next_pow2(k) floats
+            // only, feature_buffer.rs:142-148, and equal hashes can meet across fields).  The reference then
+            // applies the per-slot accumulator updates in feature order (block_ffm.rs:269-287); remember
+            // whether this example needs that ordering.
+            if (p.update) {
+                for (uint32_t a = tg; a < n; a += T)
+                    for (uint32_t b = a + 1; b < n; b++) {
+                        const uint32_t ha = hash[a], hb = hash[b];
+                        const uint32_t diff = ha > hb ? ha - hb : hb - ha;
+                        if (diff < Fk) overlap = true;
+                    }
+            }
+
             // ---- forward: FFM outputs through the triangle (block_ffm.rs:219-261, block_misc.rs:862-884) ----
             // sum over z<f of 2*out[f][z] + out[f][f], with out[f][z] = 0.5*sum_k C[f][zk..]*C[z][fk..]
             const uint32_t FF = F * F;
@@ -230,7 +250,7 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
                             const float v = val[e];
                             for (uint32_t q = 0; q < k; q++) {
                                 float wq = d[e * k + q];
-                                float g_ = v * (cf[q] - wq * v); // block_ffm.rs:238-243
+                                float g_ = __fmul_rn(v, __fsub_rn(cf[q], __fmul_rn(wq, v))); // block_ffm.rs:238-243
                                 s = fmaf(wq, g_, s);
                             }
                         }
@@ -249,12 +269,14 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
 
         // ---- reduce over the group -----------------------------------------------------------------
         float wsum = warp_sum(part);
+        overlap = __any_sync(0xffffffffu, overlap);
         if (NW > 1) {
-            if (lane == 0) red[wg] = wsum;
+            if (lane == 0) { red[wg] = wsum; red[8 + wg] = overlap ? 1.0f : 0.0f; }
             group_sync<T>(gib);
             wsum = 0.0f;
+            overlap = false;
 #pragma unroll
-            for (int w_ = 0; w_ < NW; w_++) wsum += red[w_];
+            for (int w_ = 0; w_ < NW; w_++) { wsum += red[w_]; overlap = overlap || (red[8 + w_] != 0.0f); }
         }
 
         // ---- sigmoid + logloss gradient (block_loss_functions.rs:105-153) ---------------------------
@@ -270,9 +292,7 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
         if (do_update) {
             // ---- FFM update (block_ffm.rs:265-288): every d_out[f][z] equals g (triangle backward mirrors it) ----
             if (F > 0) {
-                const uint32_t total = n * cpr;
-                for (uint32_t idx = tg; idx < total; idx += T) {
-                    const uint32_t e = fdiv(idx, p.div_cpr), c = idx - e * cpr;
+                auto update_chunk = [&](uint32_t e, uint32_t c) {
                     const uint32_t f = field[e], h = hash[e], x0 = c * VEC;
                     const float v = val[e];
                     float grad[VEC], gg[VEC], old[VEC];
@@ -281,8 +301,11 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
                         const uint32_t x = x0 + j;
                         const uint32_t z = fdiv(x, p.div_k), q = x - z * k;
                         float cz = C[z * Fk + f * k + q];
-                        if (z == f) cz = cz - d[e * k + q] * v;
-                        grad[j] = g * (v * cz);
+                        // separate roundings, never an FMA: for a lone feature C[f][f-block] IS fl(w*v), so the
+                        // self-interaction must cancel to exactly 0 like the reference's (block_ffm.rs:238-240);
+                        // AdaGrad with a zero initial accumulator turns any residue into a full-size step.
+                        if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
+                        grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
                         gg[j] = grad[j] * grad[j];
                     }
                     float upd[VEC];
@@ -295,6 +318,20 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
                         for (int j = 0; j < VEC; j++) upd[j] = -opt_step(p.optimizer, grad[j], old[j] + gg[j], p.lut_ffm, p.ffm_lr, p.ffm_mpt);
                     }
                     red_add_vec<VEC>(p.ffm_w + h + x0, upd);
+                };
+                if (!overlap) {
+                    const uint32_t total = n * cpr;
+                    for (uint32_t idx = tg; idx < total; idx += T) {
+                        const uint32_t e = fdiv(idx, p.div_cpr);
+                        update_chunk(e, idx - e * cpr);
+                    }
+                } else {
+                    // ordered: a feature's accumulator atomics have returned (their results were consumed above)
+                    // before the next feature's are issued
+                    for (uint32_t e = 0; e < n; e++) {
+                        for (uint32_t c = tg; c < cpr; c += T) update_chunk(e, c);
+                        group_sync<T>(gib);
+                    }
                 }
             }
             // ---- LR update (block_lr.rs:135-151); duplicates of one hash inside an example are applied

@@ -53,6 +53,7 @@ class ModelInstance:
     ns_is_f32: Optional[List[int]] = None
     max_ffm_per_example: int = 0
     max_lr_per_example: int = 0
+    hogwild_ramp_div: int = 0  # 0 = default (32), 0xffffffff = no concurrency ramp
 
     @staticmethod
     def new_empty():
@@ -108,4 +109,5 @@ class ModelInstance:
         d.field_ns = field_ns.ctypes.data_as(_lib.u32p)
         d.max_ffm_per_example = self.max_ffm_per_example
         d.max_lr_per_example = self.max_lr_per_example
+        d.hogwild_ramp_div = self.hogwild_ramp_div
         return d, (is_f32, combo_off, combo_ns, combo_w, field_off, field_ns)

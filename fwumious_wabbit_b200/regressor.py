@@ -193,6 +193,12 @@ class Regressor:
         table = np.ascontiguousarray(table, dtype=np.float32)
         self.import_block(_lib.BLOCK_LR, table.reshape(-1), with_optimizer_state=(table.ndim == 2 and table.shape[1] == 2))
 
+    def set_examples_seen(self, n):
+        self._check(self.L.fwgpu_set_examples_seen(self.h, n))
+
+    def examples_seen(self):
+        return int(self.L.fwgpu_get_examples_seen(self.h))
+
     # ---- measurement ----
     def set_profiling(self, on=True):
         self._check(self.L.fwgpu_set_profiling(self.h, 1 if on else 0))

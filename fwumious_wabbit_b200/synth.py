@@ -76,7 +76,7 @@ class Workload:
         return 4 * F * F * mi.ffm_k + 4 * n_lr + inp + 4
 
 
-def _mi(n_ns, *, ffm_k, ffm_bits, bits, interactions=(), lr=0.1, ffm_lr=0.05, power_t=0.5):
+def _mi(n_ns, *, ffm_k, ffm_bits, bits, interactions=(), lr=0.1, ffm_lr=0.05, power_t=0.5, ffm_init_acc=0.0):
     mi = ModelInstance()
     mi.num_namespaces = n_ns
     mi.feature_combo_descs = [([j], 1.0) for j in range(n_ns)] + [(list(c), 1.0) for c in interactions]
@@ -87,7 +87,7 @@ def _mi(n_ns, *, ffm_k, ffm_bits, bits, interactions=(), lr=0.1, ffm_lr=0.05, po
     mi.ffm_fields = [[j] for j in range(n_ns)] if ffm_k else []
     mi.ffm_learning_rate, mi.ffm_power_t = ffm_lr, power_t
     mi.optimizer = Optimizer.AdagradLUT  # --adaptive with fastmath (model_instance.rs:481-492)
-    mi.init_acc_gradient, mi.ffm_init_acc_gradient = 1.0, 0.0
+    mi.init_acc_gradient, mi.ffm_init_acc_gradient = 1.0, ffm_init_acc
     return mi
 
 
@@ -105,7 +105,10 @@ def workload(name: str) -> Workload:
                         "FFM k=4, 8 fields (one namespace each, 1e5 Zipf ids), ffm_bit_precision=20, -b 18")
     if name in ("c3", "c4"):
         card = [100] * 13 + [10 ** (3 + (j % 5)) for j in range(26)]  # 13 binned numeric + 26 categorical 1e3..1e7
-        mi = _mi(39, ffm_k=8, ffm_bits=24 if name == "c3" else 28, bits=24)
+        # -l 0.05 --ffm_learning_rate 0.02 --ffm_init_acc_gradient 0.1: with 39 fields the reference's defaults
+        # (ffm_init_acc_gradient 0) make the sequential learner itself diverge on this stream (logloss above the prior)
+        mi = _mi(39, ffm_k=8, ffm_bits=24 if name == "c3" else 28, bits=24, lr=0.05, ffm_lr=0.02, ffm_init_acc=0.1)
         return Workload(name, mi, NS_LETTERS[:39], card,
-                        f"FFM k=8, 39 fields (Criteo shape: 13 low-card + 26 high-card), ffm_bit_precision={mi.ffm_bit_precision}, -b 24")
+                        f"FFM k=8, 39 fields (Criteo shape: 13 low-card + 26 high-card), ffm_bit_precision={mi.ffm_bit_precision}, -b 24, "
+                        "-l 0.05 --ffm_learning_rate 0.02 --ffm_init_acc_gradient 0.1")
     raise KeyError(name)

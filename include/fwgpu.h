@@ -81,6 +81,11 @@ typedef struct fwgpu_model_desc {
     const uint32_t *field_ns;     /* namespace_index of every namespace of every field         */
     uint32_t max_ffm_per_example; /* 0 = derive (one feature per field namespace); raise for multi-valued namespaces */
     uint32_t max_lr_per_example;  /* 0 = derive                                                */
+    /* Hogwild concurrency ramp: a freshly initialised model is trained with at most
+     * examples_seen / hogwild_ramp_div examples in flight, growing to the full machine; it keeps
+     * the cold-start of AdaGrad (accumulators at 0) from overshooting when thousands of examples
+     * hit the same weights at once.  0 = default (32); 0xffffffff = no ramp.  DESIGN.md "semantics". */
+    uint32_t hogwild_ramp_div;
 } fwgpu_model_desc;
 
 /*
@@ -164,6 +169,10 @@ fwgpu_status fwgpu_export_block(fwgpu_ctx *ctx, int block, void *dst, uint64_t d
 /* read_weights_from_buf (block_helpers.rs:43-60).  with_optimizer_state = 0 reads a weights-only
  * payload (read_weights_from_buf_into_forward_only, block_lr.rs:277-292, block_ffm.rs:879-899). */
 fwgpu_status fwgpu_import_block(fwgpu_ctx *ctx, int block, const void *src, uint64_t src_bytes, int with_optimizer_state);
+/* Number of examples this ctx has learned from (drives the concurrency ramp).  Importing weights
+ * with optimizer state marks the model as trained (no ramp); set it explicitly when needed. */
+fwgpu_status fwgpu_set_examples_seen(fwgpu_ctx *ctx, uint64_t n);
+uint64_t fwgpu_get_examples_seen(const fwgpu_ctx *ctx);
 /* the AdaGrad LUT of a block (which: 0 lr, 1 ffm, 2 nn), 2048 floats, for inspection */
 fwgpu_status fwgpu_get_lut(const fwgpu_ctx *ctx, int which, float *dst2048);
 

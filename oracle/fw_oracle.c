@@ -1063,3 +1063,153 @@ double fwo_hogwild_run(fwo_regressor *r, const fwo_translate_spec *spec, const u
     clock_gettime(CLOCK_MONOTONIC, &t1);
     return (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Wave emulation (analysis tool, no reference counterpart): what a device that keeps `wave`
+ * examples in flight computes.  All examples of a wave are scored against the same weight
+ * snapshot; their updates are then applied
+ *   mode 0: one after another, each slot's accumulator growing with every hit (what lock-free
+ *           per-example atomics do -- "Hogwild on device");
+ *   mode 1: aggregated per slot over the wave: G = sum g_i, acc += sum g_i^2, one step with G.
+ * Used on the CPU to choose the device semantics and the safe amount of concurrency; regressor
+ * graph without head only.
+ * ---------------------------------------------------------------------------------------- */
+void fwo_learn_records_wave(fwo_regressor *r, const fwo_translate_spec *spec, const uint32_t *records,
+                            const uint64_t *rec_off, uint64_t n_records, uint32_t wave, int mode, float *preds)
+{
+    /* mode bits: low 4 bits = update mode; bits 8.. = ramp divisor (0 = none): the wave grows as
+     * examples_seen / ramp_div, capped at `wave` (the concurrency ramp of the device path). */
+    const uint32_t ramp_div = (uint32_t)mode >> 8;
+    mode &= 15;
+    const uint32_t F = r->F, k = r->k, Fk = r->Fk;
+    const uint32_t cap = 4096;
+    fwo_lr_feat *lr = (fwo_lr_feat *)malloc(sizeof(fwo_lr_feat) * cap * (size_t)wave);
+    fwo_ffm_feat *ffm = (fwo_ffm_feat *)malloc(sizeof(fwo_ffm_feat) * cap * (size_t)wave);
+    uint32_t *n_lr = (uint32_t *)malloc(4 * (size_t)wave), *n_ffm = (uint32_t *)malloc(4 * (size_t)wave);
+    float *gs = (float *)malloc(4 * (size_t)wave);
+    size_t *loc_off = (size_t *)malloc(sizeof(size_t) * ((size_t)wave + 1));
+    size_t loc_cap = 0;
+    float *loc = NULL;
+    float *gsum_ffm = NULL, *g2_ffm = NULL, *gsum_lr = NULL, *g2_lr = NULL;
+    uint32_t *touched = NULL;
+    size_t touched_cap = 0;
+    if (mode == 1) {
+        gsum_ffm = (float *)calloc(r->ffm_len + 1, 4); g2_ffm = (float *)calloc(r->ffm_len + 1, 4);
+        gsum_lr = (float *)calloc(r->lr_len, 4); g2_lr = (float *)calloc(r->lr_len, 4);
+    }
+    uint32_t m = 0;
+    for (uint64_t a = 0; a < n_records; a += m) {
+        uint32_t wv = wave;
+        if (ramp_div) { uint64_t lim = a / ramp_div; if (lim < 1) lim = 1; if (lim < wv) wv = (uint32_t)lim; }
+        m = (uint32_t)((a + wv <= n_records) ? wv : n_records - a);
+        /* phase 1: forward of the whole wave on the snapshot */
+        size_t need = 0;
+        for (uint32_t i = 0; i < m; i++) {
+            fwo_feature_buffer fb;
+            fwo_lr_feat *l = lr + (size_t)i * cap; fwo_ffm_feat *f = ffm + (size_t)i * cap;
+            if (fwo_translate(spec, records + rec_off[a + i], l, cap, &n_lr[i], f, cap, &n_ffm[i], &fb.label, &fb.example_importance) != 0) { n_lr[i] = n_ffm[i] = 0; }
+            loc_off[i] = need; need += (size_t)n_ffm[i] * Fk;
+        }
+        loc_off[m] = need;
+        if (need > loc_cap) { free(loc); loc_cap = need * 2 + 16; loc = (float *)malloc(4 * loc_cap); }
+        for (uint32_t i = 0; i < m; i++) {
+            fwo_feature_buffer fb;
+            fb.label = (float)records[rec_off[a + i] + 1];
+            memcpy(&fb.example_importance, &records[rec_off[a + i] + 2], 4);
+            fb.example_number = a + i; fb.n_lr = n_lr[i]; fb.lr = lr + (size_t)i * cap; fb.n_ffm = n_ffm[i]; fb.ffm = ffm + (size_t)i * cap;
+            float p = fwo_forward_backward(r, &fb, 0); /* training-order forward, no update */
+            if (preds) preds[a + i] = p;
+            float g;
+            /* recompute g as the sigmoid block does */
+            if (p != p) g = 0.0f; else g = -(fb.label - p) * fb.example_importance;
+            /* clamp cases (|wsum| > 50) give g = 0 in the reference; p then equals logistic(+-50) */
+            if (p <= 1.0f / (1.0f + expf(50.0f)) || p >= 1.0f / (1.0f + expf(-50.0f))) g = 0.0f;
+            if (fb.example_importance == 0.0f) g = 0.0f;
+            gs[i] = g;
+            /* local gradients G_i (block_ffm.rs:219-261) were left in the thread-local scratch by forward_backward */
+            memcpy(loc + loc_off[i], tls_scratch.local, 4 * (size_t)n_ffm[i] * Fk);
+        }
+        /* phase 2: updates */
+        if (mode == 0) {
+            for (uint32_t i = 0; i < m; i++) {
+                float g = gs[i];
+                if (g == 0.0f) continue;
+                const float *G = loc + loc_off[i];
+                size_t li = 0;
+                for (uint32_t e = 0; e < n_ffm[i]; e++) {
+                    size_t fi = ffm[(size_t)i * cap + e].hash;
+                    for (uint32_t x = 0; x < Fk; x++) {
+                        float gradient = g * G[li++];
+                        float upd = opt_update(&r->opt_ffm, gradient, &r->ffm_acc[fi + x]);
+                        r->ffm_w[fi + x] -= upd;
+                    }
+                }
+                for (uint32_t e = 0; e < n_lr[i]; e++) {
+                    const fwo_lr_feat *f = &lr[(size_t)i * cap + e];
+                    float upd = opt_update(&r->opt_lr, g * f->value, &r->lr[f->hash].acc);
+                    r->lr[f->hash].w -= upd;
+                }
+            }
+        } else {
+            size_t nt = 0;
+            size_t max_touch = 0;
+            for (uint32_t i = 0; i < m; i++) max_touch += (size_t)n_ffm[i] * Fk + n_lr[i];
+            if (max_touch > touched_cap) { free(touched); touched_cap = max_touch * 2 + 16; touched = (uint32_t *)malloc(4 * touched_cap); }
+            for (uint32_t i = 0; i < m; i++) {
+                float g = gs[i];
+                if (g == 0.0f) continue;
+                const float *G = loc + loc_off[i];
+                size_t li = 0;
+                for (uint32_t e = 0; e < n_ffm[i]; e++) {
+                    size_t fi = ffm[(size_t)i * cap + e].hash;
+                    for (uint32_t x = 0; x < Fk; x++) {
+                        float gradient = g * G[li++];
+                        if (g2_ffm[fi + x] == 0.0f && gsum_ffm[fi + x] == 0.0f) touched[nt++] = (uint32_t)(fi + x);
+                        gsum_ffm[fi + x] += gradient; g2_ffm[fi + x] += gradient * gradient;
+                    }
+                }
+            }
+            for (size_t t = 0; t < nt; t++) {
+                uint32_t s = touched[t];
+                if (g2_ffm[s] == 0.0f && gsum_ffm[s] == 0.0f) continue;
+                float G = gsum_ffm[s], g2 = g2_ffm[s];
+                gsum_ffm[s] = 0.0f; g2_ffm[s] = 0.0f;
+                /* acc += sum g_i^2 ; step with the summed gradient */
+                float new_acc = r->ffm_acc[s] + g2;
+                r->ffm_acc[s] = new_acc;
+                float step;
+                if (r->opt_ffm.kind == FWO_OPT_ADAGRAD_LUT) step = G * r->opt_ffm.lut[f2bits(new_acc) >> 20];
+                else if (r->opt_ffm.kind == FWO_OPT_ADAGRAD_FLEX) step = G * r->opt_ffm.lr * powf(new_acc, r->opt_ffm.minus_power_t);
+                else step = G * r->opt_ffm.lr;
+                r->ffm_w[s] -= step;
+            }
+            nt = 0;
+            for (uint32_t i = 0; i < m; i++) {
+                float g = gs[i];
+                if (g == 0.0f) continue;
+                for (uint32_t e = 0; e < n_lr[i]; e++) {
+                    const fwo_lr_feat *f = &lr[(size_t)i * cap + e];
+                    float gradient = g * f->value;
+                    if (g2_lr[f->hash] == 0.0f && gsum_lr[f->hash] == 0.0f) touched[nt++] = f->hash;
+                    gsum_lr[f->hash] += gradient; g2_lr[f->hash] += gradient * gradient;
+                }
+            }
+            for (size_t t = 0; t < nt; t++) {
+                uint32_t s = touched[t];
+                if (g2_lr[s] == 0.0f && gsum_lr[s] == 0.0f) continue;
+                float G = gsum_lr[s], g2 = g2_lr[s];
+                gsum_lr[s] = 0.0f; g2_lr[s] = 0.0f;
+                float new_acc = r->lr[s].acc + g2;
+                r->lr[s].acc = new_acc;
+                float step;
+                if (r->opt_lr.kind == FWO_OPT_ADAGRAD_LUT) step = G * r->opt_lr.lut[f2bits(new_acc) >> 20];
+                else if (r->opt_lr.kind == FWO_OPT_ADAGRAD_FLEX) step = G * r->opt_lr.lr * powf(new_acc, r->opt_lr.minus_power_t);
+                else step = G * r->opt_lr.lr;
+                r->lr[s].w -= step;
+            }
+        }
+    }
+    free(lr); free(ffm); free(n_lr); free(n_ffm); free(gs); free(loc_off); free(loc);
+    free(gsum_ffm); free(g2_ffm); free(gsum_lr); free(g2_lr); free(touched);
+    (void)F; (void)k;
+}

@@ -177,6 +177,12 @@ void fwo_learn_batch_sequential(fwo_regressor *r, const fwo_batch *b, float *pre
 double fwo_hogwild_run(fwo_regressor *r, const fwo_translate_spec *spec, const uint32_t *records,
                        const uint64_t *rec_off, uint64_t n_records, uint32_t n_threads, float *preds);
 
+/* Analysis tool (no reference counterpart): emulates a device that keeps `wave` examples in flight
+ * (all scored on one weight snapshot, then updated; mode 0 = per-example updates in order,
+ * mode 1 = per-slot aggregated update).  See fw_oracle.c. */
+void fwo_learn_records_wave(fwo_regressor *r, const fwo_translate_spec *spec, const uint32_t *records,
+                            const uint64_t *rec_off, uint64_t n_records, uint32_t wave, int mode, float *preds);
+
 #ifdef __cplusplus
 }
 #endif

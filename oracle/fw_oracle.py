@@ -139,6 +139,9 @@ def lib():
     L.fwo_hogwild_run.restype = C.c_double
     L.fwo_hogwild_run.argtypes = [C.c_void_p, C.POINTER(TranslateSpec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                   C.c_uint64, C.c_uint32, C.POINTER(C.c_float)]
+    L.fwo_learn_records_wave.argtypes = [C.c_void_p, C.POINTER(TranslateSpec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                         C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
+    L.fwo_learn_records_wave.restype = None
     _lib = L
     return L
 
@@ -348,6 +351,16 @@ class Regressor:
                                                          _f32p(batch["ffm_val"]), _u32p(batch["ffm_field"]))
         preds = np.zeros(n, dtype=np.float32)
         lib().fwo_learn_batch_sequential(self.h, C.byref(b), _f32p(preds), 1 if update else 0)
+        return preds
+
+    def learn_wave(self, spec, records, rec_off, wave, mode):
+        """Analysis tool: emulate `wave` examples in flight (see fwo_learn_records_wave)."""
+        records = np.ascontiguousarray(records, dtype=np.uint32)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        n = rec_off.shape[0] - 1
+        preds = np.zeros(n, dtype=np.float32)
+        lib().fwo_learn_records_wave(self.h, C.byref(spec.c), _u32p(records), rec_off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                     n, wave, mode, _f32p(preds))
         return preds
 
     def hogwild(self, spec, records, rec_off, n_threads, want_preds=False):

@@ -347,6 +347,26 @@ def test_learn_large_batch_progressive_logloss():
     assert util.logloss(got[h:], labels[h:]) < util.logloss(np.full(n - h, labels.mean()), labels[h:])
 
 
+def test_concurrency_ramp_bookkeeping():
+    """The cold-start ramp: examples_seen advances with learned examples only, importing optimizer state
+    marks the model as trained, and a cold model trained in one big call still learns (no overshoot)."""
+    w = synth.workload("c2")
+    n = 300_000
+    recs = w.records(n)
+    re = fw.Regressor(w.mi)
+    assert re.examples_seen() == 0
+    re.learn_records(recs[:1000].reshape(-1), n_examples=1000, update=False)
+    assert re.examples_seen() == 0
+    p = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    assert re.examples_seen() == n
+    labels = recs[:, 1].astype(np.float32)
+    prior = util.logloss(np.full(n, labels.mean()), labels)
+    assert util.logloss(p, labels) < prior  # progressive logloss of a cold model beats the prior even in one call
+    re2 = fw.Regressor(w.mi)
+    re2.import_block(_lib.BLOCK_FFM, re.export_block(_lib.BLOCK_FFM), True)
+    assert re2.examples_seen() >= 1 << 40
+
+
 def test_records_path_equals_csr_path():
     """learn_records (device translate) and learn_batch (host CSR) are the same computation."""
     w = synth.workload("c2")
