@@ -452,6 +452,7 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
         q.preds = p.preds + done;
         q.n_examples = cnt;
         q.max_groups = cap;
+        q.exact_order = (cap == 1 || cnt == 1) ? 1 : 0; // a single example in flight: sum in the reference's order
         uint32_t full_groups = 0;
         cudaError_t e;
         {
@@ -848,6 +849,21 @@ extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *
             c->launches++;
         }
     }
+    return fwgpu_sync(c);
+}
+
+extern "C" fwgpu_status fwgpu_debug_logistic(fwgpu_ctx *c, const float *in, float *out, uint64_t n)
+{
+    if (!c || !in || !out) return FWGPU_ERR_INVALID;
+    if (n == 0) return FWGPU_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    fwgpu_status st;
+    if ((st = ensure(c, c->csr, n * 8))) return st;
+    float *din = (float *)c->csr.p, *dout = din + n;
+    CUDA_TRY(c, cudaMemcpyAsync(din, in, n * 4, cudaMemcpyHostToDevice, c->stream));
+    k_debug_logistic<<<c->num_sms * 4, 256, 0, c->stream>>>(din, dout, n);
+    c->launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, c->stream));
     return fwgpu_sync(c);
 }
 

@@ -59,6 +59,7 @@ struct LearnParams {
     uint32_t *err_flag;     // bit0: example exceeded n_cap
     uint32_t group_smem_bytes;
     uint32_t max_groups;    // 0 = all resident groups; else cap on examples in flight (concurrency ramp)
+    int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -96,6 +97,41 @@ __device__ __forceinline__ float warp_sum(float v)
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// expf exactly as glibc (>= 2.27, sysdeps/ieee754/flt-32/e_expf.c, the ARM optimized-routines algorithm) computes it:
+// the reference's logistic() (block_loss_functions.rs:15-17) is Rust's f32::exp = libm expf, and AdagradLUT turns a
+// 1-ulp difference in the gradient into a different table bucket sooner or later, so the device reproduces the same
+// double-precision evaluation instead of calling CUDA's expf (2 ulp).  Valid for |x| < 88 (the sigmoid clamps at 50).
+// tests/test_expf.py checks the host restatement of this routine against libm bit for bit.
+__device__ __constant__ uint64_t c_exp2f_tab[32] = {
+    0x3ff0000000000000ull, 0x3fefd9b0d3158574ull, 0x3fefb5586cf9890full, 0x3fef9301d0125b51ull,
+    0x3fef72b83c7d517bull, 0x3fef54873168b9aaull, 0x3fef387a6e756238ull, 0x3fef1e9df51fdee1ull,
+    0x3fef06fe0a31b715ull, 0x3feef1a7373aa9cbull, 0x3feedea64c123422ull, 0x3feece086061892dull,
+    0x3feebfdad5362a27ull, 0x3feeb42b569d4f82ull, 0x3feeab07dd485429ull, 0x3feea47eb03a5585ull,
+    0x3feea09e667f3bcdull, 0x3fee9f75e8ec5f74ull, 0x3feea11473eb0187ull, 0x3feea589994cce13ull,
+    0x3feeace5422aa0dbull, 0x3feeb737b0cdc5e5ull, 0x3feec49182a3f090ull, 0x3feed503b23e255dull,
+    0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
+    0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
+__device__ __forceinline__ float expf_libm(float x)
+{
+    const double InvLn2N = 0x1.71547652b82fep+0 * 32.0, SHIFT = 0x1.8p+52;
+    const double C0 = 0x1.c6af84b912394p-5 / 32.0 / 32.0 / 32.0, C1 = 0x1.ebfce50fac4f3p-3 / 32.0 / 32.0, C2 = 0x1.62e42ff0c52d6p-1 / 32.0;
+    const double z = __dmul_rn(InvLn2N, (double)x);
+    double kd = __dadd_rn(z, SHIFT);
+    const uint64_t ki = (uint64_t)__double_as_longlong(kd);
+    kd = __dsub_rn(kd, SHIFT);
+    const double r = __dsub_rn(z, kd);
+    const uint64_t t = c_exp2f_tab[ki & 31] + (ki << 47);
+    const double sc = __longlong_as_double((long long)t);
+    const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
+    const double r2 = __dmul_rn(r, r);
+    double y = __dadd_rn(__dmul_rn(C2, r), 1.0);
+    y = __dadd_rn(__dmul_rn(zz, r2), y);
+    y = __dmul_rn(y, sc);
+    return __double2float_rn(y);
+}
+// logistic(t) = (1.0 + (-t).exp()).recip()   (block_loss_functions.rs:15-17)
+__device__ __forceinline__ float logistic(float t) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_libm(-t))); }
 
 // optimizer.rs calculate_update given the accumulator value *after* adding g^2
 __device__ __forceinline__ float opt_step(uint32_t optimizer, float grad, float new_acc, const float *__restrict__ lut, float lr, float mpt)
@@ -237,9 +273,10 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
             for (uint32_t idx = tg; idx < FF; idx += T) {
                 const uint32_t f = fdiv(idx, p.div_F), z = idx - f * F;
                 if (z < f) {
+                    // 2 * out[f][z] = sum_q w_f[z][q] * (v * contra) with separate roundings (block_ffm.rs:246-257)
                     const float *a = C + f * Fk + z * k, *b = C + z * Fk + f * k;
                     float s = 0.0f;
-                    for (uint32_t q = 0; q < k; q++) s = fmaf(a[q], b[q], s);
+                    for (uint32_t q = 0; q < k; q++) s = __fadd_rn(s, __fmul_rn(a[q], b[q]));
                     part += s;
                 } else if (z == f) {
                     const uint32_t b0 = fstart[f], b1 = fstart[f + 1];
@@ -251,7 +288,7 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
                             for (uint32_t q = 0; q < k; q++) {
                                 float wq = d[e * k + q];
                                 float g_ = __fmul_rn(v, __fsub_rn(cf[q], __fmul_rn(wq, v))); // block_ffm.rs:238-243
-                                s = fmaf(wq, g_, s);
+                                s = __fadd_rn(s, __fmul_rn(wq, g_));
                             }
                         }
                         part += 0.5f * s;
@@ -264,7 +301,7 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
         for (uint32_t i = tg; i < nlr; i += T) {
             uint4 e = __ldg(le + i);
             float2 cell = __ldcg(p.lr + e.x);
-            part = fmaf(cell.x, __uint_as_float(e.y), part);
+            part += __fmul_rn(cell.x, __uint_as_float(e.y));
         }
 
         // ---- reduce over the group -----------------------------------------------------------------
@@ -279,12 +316,55 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
             for (int w_ = 0; w_ < NW; w_++) { wsum += red[w_]; overlap = overlap || (red[8 + w_] != 0.0f); }
         }
 
+        if (p.exact_order) {
+            // Parity mode (one example in flight): the sigmoid sums its inputs left to right over the tape
+            // [LR combo outputs..., triangle outputs...] (graph.rs:251-284, block_loss_functions.rs:116-120).
+            // One thread redoes the forward in exactly that order, so the prediction and the gradient are bit-exact with
+            // the reference; AdagradLUT (a step function of the accumulator's top bits) then never lands in another bucket.
+            if (tg == 0) {
+                float ws = 0.0f, comb = 0.0f;
+                uint32_t cur = 0xffffffffu;
+                for (uint32_t i = 0; i < nlr; i++) { // block_lr.rs:38-45: out[combo] += w * v, entries arrive in combo order
+                    const uint4 e = __ldg(le + i);
+                    if (e.z != cur) { if (cur != 0xffffffffu) ws = __fadd_rn(ws, comb); comb = 0.0f; cur = e.z; }
+                    comb = __fadd_rn(comb, __fmul_rn(__ldcg(p.lr + e.x).x, __uint_as_float(e.y)));
+                }
+                if (cur != 0xffffffffu) ws = __fadd_rn(ws, comb);
+                // FFM outputs through the triangle, term by term in tape order (block_misc.rs:871-881):
+                // for field f: 2*out[f][z] (z < f) then out[f][f], where out[f][z] accumulates, feature by feature of
+                // field f, 0.5 * sum_q w_e[z][q] * (v_e * (contra[f][z][q] - [z==f] w_e[f][q] v_e))  (block_ffm.rs:219-261).
+                // Raw weights come straight from the table, contra sums from shared memory: faithful for any example.
+                for (uint32_t f = 0; f < F; f++) {
+                    const uint32_t b0 = fstart[f], b1 = fstart[f + 1];
+                    for (uint32_t z = 0; z <= f; z++) {
+                        float o = 0.0f;
+                        for (uint32_t e = b0; e < b1; e++) {
+                            const float v = val[e];
+                            const float *wrow = W + hash[e] + z * k;
+                            float corr = 0.0f;
+                            for (uint32_t q = 0; q < k; q++) {
+                                const float wq = __ldcg(wrow + q);
+                                float cz = C[z * Fk + f * k + q];
+                                if (z == f) cz = __fsub_rn(cz, __fmul_rn(wq, v));
+                                corr = __fadd_rn(corr, __fmul_rn(wq, __fmul_rn(v, cz)));
+                            }
+                            o = __fadd_rn(o, __fmul_rn(corr, 0.5f));
+                        }
+                        ws = __fadd_rn(ws, z < f ? __fmul_rn(o, 2.0f) : o);
+                    }
+                }
+                red[0] = ws;
+            }
+            group_sync<T>(gib);
+            wsum = red[0];
+        }
+
         // ---- sigmoid + logloss gradient (block_loss_functions.rs:105-153) ---------------------------
         float pr, g;
-        if (isnan(wsum)) { pr = 0.5f; g = 0.0f; }
-        else if (wsum < -50.0f) { pr = 1.0f / (1.0f + expf(50.0f)); g = 0.0f; }
-        else if (wsum > 50.0f) { pr = 1.0f / (1.0f + expf(-50.0f)); g = 0.0f; }
-        else { pr = 1.0f / (1.0f + expf(-wsum)); g = -(m.label - pr) * m.importance; }
+        if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+        else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+        else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+        else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(m.label, pr), m.importance); }
         if (tg == 0) p.preds[ex] = pr;
 
         // regressor.rs:366-370: update && importance != 0; a zero gradient changes nothing
@@ -539,6 +619,7 @@ __global__ void k_fill(float *p, size_t n, float v)
 {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
+__global__ void k_debug_logistic(const float *in, float *out, size_t n) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = logistic(in[i]); }
 // LR export/import helpers: AoS {w,acc} <-> weights-only
 __global__ void k_lr_extract_w(const float2 *t, float *w, size_t n) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) w[i] = t[i].x; }
 __global__ void k_lr_set_w(float2 *t, const float *w, size_t n, float acc) { for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) t[i] = make_float2(w[i], acc); }

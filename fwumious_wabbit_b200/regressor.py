@@ -193,6 +193,12 @@ class Regressor:
         table = np.ascontiguousarray(table, dtype=np.float32)
         self.import_block(_lib.BLOCK_LR, table.reshape(-1), with_optimizer_state=(table.ndim == 2 and table.shape[1] == 2))
 
+    def debug_logistic(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        out = np.empty_like(x)
+        self._check(self.L.fwgpu_debug_logistic(self.h, _vp(x), _vp(out), x.size))
+        return out
+
     def set_examples_seen(self, n):
         self._check(self.L.fwgpu_set_examples_seen(self.h, n))
 

@@ -184,6 +184,10 @@ fwgpu_status fwgpu_get_lut(const fwgpu_ctx *ctx, int which, float *dst2048);
 fwgpu_status fwgpu_set_profiling(fwgpu_ctx *ctx, int enabled);
 fwgpu_status fwgpu_kernel_time(fwgpu_ctx *ctx, int kind, double *total_ms, uint64_t *launches);
 
+/* Debug/verification: out[i] = logistic(in[i]) computed by the device routine the kernels use
+ * (block_loss_functions.rs:15-17 with glibc-exact expf).  Host pointers, synchronous. */
+fwgpu_status fwgpu_debug_logistic(fwgpu_ctx *ctx, const float *in, float *out, uint64_t n);
+
 /* pinned host memory for batch buffers (SURVEY.md section 8b "Batch layout") */
 fwgpu_status fwgpu_host_alloc(void **out, uint64_t bytes);
 void fwgpu_host_free(void *p);

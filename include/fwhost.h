@@ -36,6 +36,11 @@ int fwhost_synth_records(uint32_t *out, uint64_t n_examples, uint64_t first_exam
 int fwhost_synth_line(char *dst, size_t cap, uint64_t example_index, uint32_t n_namespaces, const char *ns_names,
                       const uint32_t *cardinality, uint64_t seed);
 
+/* The expf the device kernels use (glibc's algorithm restated; csrc/fwgpu_kernels.cuh expf_libm), on the host,
+ * so that it can be compared with the C library's expf without a GPU.  Valid for |x| < 88. */
+float fwhost_expf_libm(float x);
+void fwhost_expf_libm_array(const float *in, float *out, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

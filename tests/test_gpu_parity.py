@@ -312,14 +312,52 @@ def test_learn_batch1_parity(name, opt):
     want = ora.learn_batch(d, update=True)
     batch = util.csr_from_dict(d)
     got = np.array([re.learn_batch(batch.slice(i, i + 1), True)[0] for i in range(n)], dtype=np.float32)
-    assert np.max(np.abs(got - want)) <= TOL, np.max(np.abs(got - want))
+    exact = opt != Optimizer.AdagradFlex  # Flex calls powf: CUDA's and glibc's differ in the last bits, everything else is bit-exact
+    if exact:
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.max(np.abs(got - want)))
+    else:
+        assert np.max(np.abs(got - want)) <= TOL, np.max(np.abs(got - want))
     t = re.get_lr_table()
-    np.testing.assert_allclose(t[:, 0], ora.lr_table[:, 0], rtol=0, atol=5e-6)
     if mi.ffm_k:
         w, acc = re.get_ffm()
-        np.testing.assert_allclose(w, ora.ffm_weights, rtol=0, atol=5e-6)
-        if acc is not None:
+    if exact:
+        assert np.array_equal(t[:, 0].view(np.uint32), ora.lr_table[:, 0].view(np.uint32))
+        if mi.ffm_k:
+            assert np.array_equal(w.view(np.uint32), ora.ffm_weights.view(np.uint32))
+            if acc is not None:
+                assert np.array_equal(acc.view(np.uint32), ora.ffm_acc.view(np.uint32))
+    else:
+        np.testing.assert_allclose(t[:, 0], ora.lr_table[:, 0], rtol=0, atol=5e-6)
+        if mi.ffm_k:
+            np.testing.assert_allclose(w, ora.ffm_weights, rtol=0, atol=5e-6)
             np.testing.assert_allclose(acc, ora.ffm_acc, rtol=1e-4, atol=1e-7)
+
+
+SEQUENTIAL = 0x7FFFFFFF  # hogwild_ramp_div so large that one example is in flight for the whole run
+
+
+@pytest.mark.parametrize("name,n", [("c2", 20_000), ("c3", 1_500), ("c1", 20_000)])
+def test_sequential_mode_bit_exact(name, n):
+    """One example in flight (the reference's default single-threaded loop, main.rs:213-258), a whole
+    stream in a single call: per-example predictions and the final tables are BIT-EXACT with the oracle on
+    the BASELINE shapes (single-valued namespaces, value 1.0), AdagradLUT included."""
+    w = synth.workload(name)
+    mi = w.mi
+    mi.hogwild_ramp_div = SEQUENTIAL
+    recs = w.records(n)
+    ora = util.oracle_regressor(mi)
+    spec = util.oracle_spec(mi)
+    rec_off = np.arange(n + 1, dtype=np.uint64) * w.record_len
+    # the training-order forward is what the reference returns from learn(update=true) (regressor.rs:356-379)
+    _, want = ora.hogwild(spec, recs.reshape(-1), rec_off, 1, want_preds=True)
+    re = fw.Regressor(mi)
+    got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), float(np.max(np.abs(got - want)))
+    assert np.array_equal(re.get_lr_table().view(np.uint32), ora.lr_table.view(np.uint32))
+    if mi.ffm_k:
+        wts, acc = re.get_ffm()
+        assert np.array_equal(wts.view(np.uint32), ora.ffm_weights.view(np.uint32))
+        assert np.array_equal(acc.view(np.uint32), ora.ffm_acc.view(np.uint32))
 
 
 def test_learn_large_batch_progressive_logloss():
