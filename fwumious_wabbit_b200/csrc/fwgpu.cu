@@ -88,12 +88,16 @@ struct fwgpu_ctx {
     cudaEvent_t ev_ready[2]{}, ev_free[2]{};
     bool ev_free_recorded[2] = {false, false};
     // staging
-    DevBuf rec[2], rec_off_dev[2], meta, lr_ent, ffm_ent, preds, csr;
+    DevBuf rec[2], rec_off_dev[2], meta, lr_ent, ffm_ent, preds, csr, leftover;
+    bool fast_ok = false;     // k_learn_fixed applies to this model (one namespace per field, k % 4 == 0, ...)
+    bool fast_enabled = true; // FWGPU_FAST=0 turns the fused kernel off (measurement / debugging)
+    uint32_t fast_nch = 1;
     uint32_t *err_flag = nullptr;
     uint32_t *err_host = nullptr; // pinned
     int num_sms = 0;
     size_t smem_optin = 0;
     int force_T = 0;
+    int minb = 3;
     uint64_t launches = 0;
     uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
     uint32_t ramp_div = 32;
@@ -153,7 +157,7 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     cudaFree(c->lr); cudaFree(c->ffm_w); cudaFree(c->ffm_acc); cudaFree(c->lut_dev);
     cudaFree(c->d_ns_is_f32); cudaFree(c->d_combo_off); cudaFree(c->d_combo_ns); cudaFree(c->d_field_off);
     cudaFree(c->d_field_ns); cudaFree(c->d_combo_weight);
-    for (DevBuf *b : {&c->rec[0], &c->rec[1], &c->rec_off_dev[0], &c->rec_off_dev[1], &c->meta, &c->lr_ent, &c->ffm_ent, &c->preds, &c->csr})
+    for (DevBuf *b : {&c->rec[0], &c->rec[1], &c->rec_off_dev[0], &c->rec_off_dev[1], &c->meta, &c->lr_ent, &c->ffm_ent, &c->preds, &c->csr, &c->leftover})
         if (b->p) cudaFree(b->p);
     cudaFree(c->err_flag);
     if (c->err_host) cudaFreeHost(c->err_host);
@@ -281,7 +285,17 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     if ((st = upload_vec(c, c->combo_weight, &c->d_combo_weight))) return st;
     if ((st = upload_vec(c, c->field_off, &c->d_field_off))) return st;
     if ((st = upload_vec(c, c->field_ns, &c->d_field_ns))) return st;
+    {
+        bool ok = (c->k % 4 == 0) && c->F <= 32 && c->n_field_refs == c->F && (c->d.n_combos + (c->d.add_constant ? 1u : 0u)) <= 64 && c->d.n_namespaces > 0;
+        for (uint32_t f = 0; ok && f < c->F; f++) ok = (c->field_off[f + 1] - c->field_off[f]) == 1;
+        const uint32_t n_chunks = c->F * (c->Fk / 4);
+        if (n_chunks > 128) ok = false;
+        c->fast_ok = ok;
+        c->fast_nch = n_chunks <= 32 ? 1 : n_chunks <= 64 ? 2 : n_chunks <= 96 ? 3 : 4;
+        if (const char *t = getenv("FWGPU_FAST")) c->fast_enabled = atoi(t) != 0;
+    }
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
+    if (const char *t = getenv("FWGPU_MINB")) c->minb = atoi(t);
     c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 32;
     if (const char *t = getenv("FWGPU_RAMP_DIV")) c->ramp_div = (uint32_t)strtoul(t, nullptr, 10);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -376,9 +390,9 @@ extern "C" fwgpu_status fwgpu_kernel_time(fwgpu_ctx *c, int kind, double *total_
 }
 
 // ---- learn kernel launch ----------------------------------------------------------------------
-template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
+template <int T, int VEC, int MINB> static cudaError_t launch_learn_tvm(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
 {
-    auto kern = k_learn<T, VEC>;
+    auto kern = k_learn<T, VEC, MINB>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -400,6 +414,19 @@ template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const
     return cudaGetLastError();
 }
 
+// registers per thread decide how many one-example blocks (T = 256) an SM holds: MINB trades ILP for occupancy
+template <int T, int VEC> static cudaError_t launch_learn_tv(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
+{
+    if (T == 256) {
+        switch (c->minb) {
+        case 2: return launch_learn_tvm<T, VEC, 2>(c, p, smem, full_groups);
+        case 4: return launch_learn_tvm<T, VEC, 4>(c, p, smem, full_groups);
+        default: return launch_learn_tvm<T, VEC, 3>(c, p, smem, full_groups);
+        }
+    }
+    return launch_learn_tvm<T, VEC, 1>(c, p, smem, full_groups);
+}
+
 template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
 {
     switch (c->VEC) {
@@ -409,7 +436,8 @@ template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnPara
     }
 }
 
-static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_cap, int update)
+static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_cap, int update, const uint32_t *n_examples_dev = nullptr,
+                                 bool count_seen = true)
 {
     if (n_examples == 0) return FWGPU_OK;
     LearnParams p{};
@@ -445,14 +473,15 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
             const uint64_t seen = c->examples_seen;
             cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(seen / c->ramp_div, 1), 1u << 30);
             const uint64_t seg_end = std::max<uint64_t>(2 * seen, c->ramp_div);
-            cnt = (uint32_t)std::min<uint64_t>(cnt, seg_end - seen);
+            if (!n_examples_dev) cnt = (uint32_t)std::min<uint64_t>(cnt, seg_end - seen);
         }
         LearnParams q = p;
-        q.meta = p.meta + done;
-        q.preds = p.preds + done;
+        q.meta = p.meta + done;   // ExMeta.out_index is absolute within the chunk, so preds is not offset
         q.n_examples = cnt;
+        q.n_examples_dev = n_examples_dev;
         q.max_groups = cap;
-        q.exact_order = (cap == 1 || cnt == 1) ? 1 : 0; // a single example in flight: sum in the reference's order
+        // parity mode: a strictly sequential run (ramp_div >= 2^31-1) or a single-example call sums in the reference's order
+        q.exact_order = ((cap == 1 && c->ramp_div >= 0x7fffffffu) || n_examples == 1) ? 1 : 0;
         uint32_t full_groups = 0;
         cudaError_t e;
         {
@@ -466,12 +495,29 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
         }
         if (e != cudaSuccess) { c->set_error(std::string("k_learn launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
         if (update) {
-            c->examples_seen += cnt;
+            if (count_seen) c->examples_seen += cnt;
             if (cap && full_groups && cap >= full_groups) c->ramp_finished = true;
         }
         done += cnt;
     }
     return FWGPU_OK;
+}
+
+// ---- fused fast path (k_learn_fixed) -----------------------------------------------------------
+template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+{
+    auto kern = k_learn_fixed<NCH>;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = std::min<uint32_t>((p.n_examples + 7) / 8, (uint32_t)(c->num_sms * per_sm));
+    if (p.max_groups) grid = std::min<uint32_t>(grid, (p.max_groups + 7) / 8);
+    *full_groups = (uint32_t)(c->num_sms * per_sm) * 8;
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, 256, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
 }
 
 // ---- CSR batch entry --------------------------------------------------------------------------
@@ -595,6 +641,53 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
     tp.ffm_k = c->d.ffm_k;
     tp.lr_stride = lr_stride; tp.ffm_stride = ffm_stride;
     tp.meta = (ExMeta *)c->meta.p; tp.lr_ent = (uint4 *)c->lr_ent.p; tp.ffm_ent = (uint4 *)c->ffm_ent.p; tp.err_flag = c->err_flag;
+    const bool use_fast = run_learn && c->fast_ok && c->fast_enabled && c->ramp_div < 0x7fffffffu;
+    if (use_fast) {
+        // fused kernel on the raw records; records it cannot take are listed and go through the general path below
+        if ((st = ensure(c, c->leftover, (size_t)(count + 4) * 4))) return st;
+        uint32_t *left_cnt = (uint32_t *)c->leftover.p, *left_idx = left_cnt + 4;
+        CUDA_TRY(c, cudaMemsetAsync(left_cnt, 0, 16, c->stream));
+        FixedParams fp{};
+        fp.lr = c->lr; fp.ffm_w = c->ffm_w; fp.ffm_acc = c->ffm_acc; fp.lut_lr = c->lut_dev; fp.lut_ffm = c->lut_dev + FWGPU_LUT_SIZE;
+        fp.records = rv.dev_records; fp.rec_off = rv.dev_rec_off; fp.off_base = rv.off_base; fp.fixed_len = rv.fixed_len;
+        fp.F = c->F; fp.k = c->k; fp.cpr = c->Fk / 4;
+        fp.div_cpr = make_fastdiv(std::max<uint32_t>(fp.cpr, 1)); fp.div_k4 = make_fastdiv(std::max<uint32_t>(c->k / 4, 1));
+        fp.field_ns = c->d_field_ns;
+        fp.n_combos = c->d.n_combos; fp.combo_off = c->d_combo_off; fp.combo_ns = c->d_combo_ns; fp.combo_weight = c->d_combo_weight;
+        fp.add_constant = c->d.add_constant; fp.lr_mask = tp.lr_mask; fp.ffm_mask = tp.ffm_mask;
+        fp.optimizer = c->optimizer; fp.lr_lr = c->d.learning_rate; fp.lr_mpt = -c->d.power_t; fp.ffm_lr = c->d.ffm_learning_rate; fp.ffm_mpt = -c->d.ffm_power_t;
+        fp.update = update; fp.preds = (float *)c->preds.p; fp.leftover_idx = left_idx; fp.leftover_cnt = left_cnt;
+        fp.warp_smem_floats = c->F * (fp.cpr + 1) * 4;
+        const size_t smem = (size_t)fp.warp_smem_floats * 4 * 8;
+        uint32_t done = 0;
+        while (done < count) {
+            uint32_t cnt = count - done, cap = 0;
+            if (update && c->ramp_div != 0xffffffffu && !c->ramp_finished) {
+                const uint64_t seen = c->examples_seen;
+                cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(seen / c->ramp_div, 1), 1u << 30);
+                cnt = (uint32_t)std::min<uint64_t>(cnt, std::max<uint64_t>(2 * seen, c->ramp_div) - seen);
+            }
+            fp.ex_begin = done; fp.n_examples = cnt; fp.max_groups = cap;
+            uint32_t full_groups = 0;
+            cudaError_t e;
+            {
+                ProfScope ps(c, 0);
+                switch (c->fast_nch) {
+                case 1: e = launch_fixed_n<1>(c, fp, smem, &full_groups); break;
+                case 2: e = launch_fixed_n<2>(c, fp, smem, &full_groups); break;
+                case 3: e = launch_fixed_n<3>(c, fp, smem, &full_groups); break;
+                default: e = launch_fixed_n<4>(c, fp, smem, &full_groups); break;
+                }
+            }
+            if (e != cudaSuccess) { c->set_error(std::string("k_learn_fixed launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+            if (update) {
+                c->examples_seen += cnt;
+                if (cap && full_groups && cap >= full_groups) c->ramp_finished = true;
+            }
+            done += cnt;
+        }
+        tp.ex_list = left_idx; tp.ex_count = left_cnt;
+    }
     {
         ProfScope ps(c, 1);
         k_translate<<<(count + 255) / 256, 256, 0, c->stream>>>(tp);
@@ -602,7 +695,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
     }
     CUDA_TRY(c, cudaGetLastError());
     if (!run_learn) return FWGPU_OK;
-    if ((st = launch_learn(c, count, ffm_stride, update))) return st;
+    if ((st = launch_learn(c, count, ffm_stride, update, use_fast ? tp.ex_count : nullptr, !use_fast))) return st;
     if (preds_host) CUDA_TRY(c, cudaMemcpyAsync(preds_host, c->preds.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream));
     return FWGPU_OK;
 }

@@ -31,7 +31,9 @@ __device__ __forceinline__ uint32_t fdiv(uint32_t n, const FastDiv &f) { return 
 struct __align__(16) ExMeta {
     float label, importance;
     uint32_t lr_begin, lr_cnt;
-    uint32_t ffm_begin, ffm_cnt, pad0, pad1;
+    uint32_t ffm_begin, ffm_cnt;
+    uint32_t out_index; // where the prediction goes (index into preds)
+    uint32_t pad1;
 };
 
 enum { OPT_SGD = 0, OPT_FLEX = 1, OPT_LUT = 2 };
@@ -59,6 +61,7 @@ struct LearnParams {
     uint32_t *err_flag;     // bit0: example exceeded n_cap
     uint32_t group_smem_bytes;
     uint32_t max_groups;    // 0 = all resident groups; else cap on examples in flight (concurrency ramp)
+    const uint32_t *n_examples_dev; // when set, the number of examples is read from device memory (leftover list)
     int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
 };
 
@@ -152,8 +155,8 @@ __device__ __forceinline__ float opt_step(uint32_t optimizer, float grad, float 
 // Block = 256 threads = 256/T groups.  Dynamic smem = groups * p.group_smem_bytes.
 // Group smem layout (floats): C[F*Fk] | d[n_cap*k] | val[n_cap] | hash[n_cap] | field[n_cap] | fstart[F+1] | red[16]
 // ---------------------------------------------------------------------------------------------
-template <int T, int VEC>
-__global__ void __launch_bounds__(256) k_learn(const LearnParams p)
+template <int T, int VEC, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int GROUPS = 256 / T;
@@ -179,13 +182,14 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
     const uint32_t gid = blockIdx.x * GROUPS + gib;
     if (gid >= n_groups) return; // whole groups leave; the named barriers below are per group
 
-    for (uint32_t ex = gid; ex < p.n_examples; ex += n_groups) {
+    const uint32_t n_total = p.n_examples_dev ? *p.n_examples_dev : p.n_examples;
+    for (uint32_t ex = gid; ex < n_total; ex += n_groups) {
         const ExMeta m = p.meta[ex];
         const uint32_t n = m.ffm_cnt, nlr = m.lr_cnt;
         const uint4 *__restrict__ fe = p.ffm_ent + m.ffm_begin;
         const uint4 *__restrict__ le = p.lr_ent + m.lr_begin;
         if (n > ncap) { // uniform over the group
-            if (tg == 0) { atomicOr(p.err_flag, 1u); p.preds[ex] = __int_as_float(0x7fc00000); }
+            if (tg == 0) { atomicOr(p.err_flag, 1u); p.preds[m.out_index] = __int_as_float(0x7fc00000); }
             continue;
         }
         float part = 0.0f;
@@ -365,7 +369,7 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
         else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
         else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
         else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(m.label, pr), m.importance); }
-        if (tg == 0) p.preds[ex] = pr;
+        if (tg == 0) p.preds[m.out_index] = pr;
 
         // regressor.rs:366-370: update && importance != 0; a zero gradient changes nothing
         const bool do_update = p.update && m.importance != 0.0f && g != 0.0f;
@@ -400,10 +404,60 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
                     red_add_vec<VEC>(p.ffm_w + h + x0, upd);
                 };
                 if (!overlap) {
+                    // UB independent chunks per thread and round: all accumulator atomics of a round are in flight
+                    // together (one L2 round trip per round instead of one per chunk), then the weight reductions.
+                    constexpr int UB = 4;
                     const uint32_t total = n * cpr;
-                    for (uint32_t idx = tg; idx < total; idx += T) {
-                        const uint32_t e = fdiv(idx, p.div_cpr);
-                        update_chunk(e, idx - e * cpr);
+                    // gradient of one chunk, recomputed from shared memory whenever needed (cheaper than holding it in
+                    // registers across the atomic round trip: registers decide how many examples an SM keeps in flight)
+                    auto chunk_grad = [&](uint32_t idx, float (&gr)[VEC], uint32_t &address) -> bool {
+                        const uint32_t e = fdiv(idx, p.div_cpr), c = idx - e * cpr;
+                        const uint32_t f = field[e], x0 = c * VEC;
+                        const float v = val[e];
+                        address = hash[e] + x0;
+                        bool any = false;
+#pragma unroll
+                        for (int j = 0; j < VEC; j++) {
+                            const uint32_t x = x0 + j;
+                            const uint32_t z = fdiv(x, p.div_k), q = x - z * k;
+                            float cz = C[z * Fk + f * k + q];
+                            if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
+                            gr[j] = __fmul_rn(g, __fmul_rn(v, cz));
+                            any = any || (gr[j] != 0.0f);
+                        }
+                        return any; // an all-zero gradient (own block of a lone feature, absent field) changes nothing
+                    };
+                    for (uint32_t idx0 = tg; idx0 < total; idx0 += UB * T) {
+                        float old[UB][VEC];
+                        bool on[UB];
+#pragma unroll
+                        for (int u = 0; u < UB; u++) {
+                            const uint32_t idx = idx0 + u * T;
+                            on[u] = false;
+                            if (idx >= total) continue;
+                            float gr[VEC];
+                            uint32_t address;
+                            on[u] = chunk_grad(idx, gr, address);
+                            if (on[u] && p.optimizer != OPT_SGD) {
+                                float gg[VEC];
+#pragma unroll
+                                for (int j = 0; j < VEC; j++) gg[j] = gr[j] * gr[j];
+                                atom_add_vec<VEC>(p.ffm_acc + address, gg, old[u]);
+                            }
+                        }
+#pragma unroll
+                        for (int u = 0; u < UB; u++) {
+                            if (!on[u]) continue;
+                            float gr[VEC], upd[VEC];
+                            uint32_t address;
+                            chunk_grad(idx0 + u * T, gr, address);
+#pragma unroll
+                            for (int j = 0; j < VEC; j++) {
+                                if (p.optimizer == OPT_SGD) upd[j] = -(gr[j] * p.ffm_lr);
+                                else upd[j] = -opt_step(p.optimizer, gr[j], old[u][j] + gr[j] * gr[j], p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                            }
+                            red_add_vec<VEC>(p.ffm_w + address, upd);
+                        }
                     }
                 } else {
                     // ordered: a feature's accumulator atomics have returned (their results were consumed above)
@@ -441,6 +495,176 @@ __global__ void __launch_bounds__(256) k_learn(const LearnParams p)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_learn_fixed<NCH>: the fused fast path for the cache's in-place encoding.
+//
+// The parser stores a namespace with one feature of weight 1.0 directly in its header slot
+// (parser.rs:396-404) -- the case the reference itself special-cases ("value == 1.0", block_ffm.rs:978,
+// SPEED.md).  When every field is one namespace and k % 4 == 0, one WARP takes one raw record and does
+// translate + forward + backward + update with the latent rows in registers:
+//   lane j (+32t) owns the 16-byte chunk c of row e:  W[h_e + 4c .. 4c+4)  = w_e towards field z = 4c/k
+//   its partner chunk  w_z towards field e  is fetched through a padded shared-memory transpose,
+//   dot(mine, partner) is both the forward term and (times g) the gradient of my chunk,
+//   so a lane issues one LDG.128, one ATOMG.128 and one REDG.128 per chunk and nothing else touches HBM.
+// Records that do not fit (a referenced namespace holds several features or weights) are appended to
+// a leftover list and go through k_translate + k_learn afterwards.
+// ---------------------------------------------------------------------------------------------
+struct FixedParams {
+    float2 *lr; float *ffm_w; float *ffm_acc; const float *lut_lr; const float *lut_ffm;
+    const uint32_t *records; const uint32_t *rec_off; uint32_t off_base, fixed_len;
+    uint32_t ex_begin, n_examples; // this launch handles records [ex_begin, ex_begin + n_examples)
+    uint32_t F, k, cpr;            // cpr = F*k/4 chunks per row
+    FastDiv div_cpr, div_k4;       // by cpr, by k/4
+    const uint32_t *field_ns;      // [F] the namespace of each field
+    uint32_t n_combos; const uint32_t *combo_off, *combo_ns; const float *combo_weight; uint32_t add_constant;
+    uint32_t lr_mask, ffm_mask;
+    uint32_t optimizer; float lr_lr, lr_mpt, ffm_lr, ffm_mpt;
+    int update;
+    float *preds;
+    uint32_t *leftover_idx, *leftover_cnt;
+    uint32_t max_groups;
+    uint32_t warp_smem_floats;     // F * (cpr + 1) * 4
+};
+
+template <int NCH>
+__global__ void __launch_bounds__(256) k_learn_fixed(const FixedParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float4 *S = reinterpret_cast<float4 *>(smem_raw) + (size_t)wib * (p.warp_smem_floats / 4);
+    const uint32_t F = p.F, k = p.k, cpr = p.cpr, row_stride = cpr + 1, k4 = k >> 2;
+    const uint32_t n_chunks = F * cpr;
+    uint32_t n_warps = gridDim.x * 8;
+    if (p.max_groups && p.max_groups < n_warps) n_warps = p.max_groups;
+    const uint32_t wid = blockIdx.x * 8 + wib;
+    if (wid >= n_warps) return;
+    const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u);
+
+    // static per-lane geometry: which chunk(s) I own and where my partner lives
+    uint32_t my_e[NCH], my_c[NCH], part_off[NCH], my_off[NCH];
+    bool act[NCH], diag[NCH];
+#pragma unroll
+    for (int t = 0; t < NCH; t++) {
+        const uint32_t j = lane + 32 * t;
+        act[t] = j < n_chunks;
+        const uint32_t e = act[t] ? fdiv(j, p.div_cpr) : 0, c = act[t] ? j - e * cpr : 0;
+        const uint32_t z = fdiv(c, p.div_k4), q4 = c - z * k4; // chunk c = quarter q4 of the block towards field z
+        my_e[t] = e; my_c[t] = c;
+        my_off[t] = e * row_stride + c;
+        part_off[t] = z * row_stride + e * k4 + q4;              // row z, its block towards field e, same quarter
+        diag[t] = (z == e);
+    }
+    const uint32_t my_field_ns = lane < F ? __ldg(p.field_ns + lane) : 0;
+
+    for (uint32_t ex = p.ex_begin + wid; ex < p.ex_begin + p.n_examples; ex += n_warps) {
+        const uint32_t *rec = p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len);
+        // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
+        const uint32_t slot = lane < F ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
+        bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
+        // LR entries: one per lane (two rounds when there are more than 32)
+        uint32_t lr_h[2]; float lr_v[2]; bool lr_ok[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const uint32_t i = lane + 32 * r;
+            lr_ok[r] = false; lr_h[r] = 0; lr_v[r] = 0.0f;
+            if (i < p.n_combos) {
+                const uint32_t o0 = __ldg(p.combo_off + i), o1 = __ldg(p.combo_off + i + 1);
+                uint32_t h = 0; bool ok = true;
+                for (uint32_t o = o0; o < o1; o++) {
+                    const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
+                    if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
+                    h = (o == o0) ? sl : ((h * 16777619u) ^ sl); // feature_buffer.rs:239-251
+                }
+                lr_ok[r] = ok; lr_h[r] = h & p.lr_mask; lr_v[r] = __ldg(p.combo_weight + i); // value 1.0 * combo weight
+            } else if (i == p.n_combos && p.add_constant) {
+                lr_ok[r] = true; lr_h[r] = 11650396u & p.lr_mask; lr_v[r] = 1.0f;       // feature_buffer.rs:270-276
+            }
+        }
+        if (__any_sync(0xffffffffu, bad)) {
+            if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+            continue;
+        }
+        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
+
+        // ---- gather: one 128-bit load per chunk ----
+        float4 v[NCH];
+        uint32_t hbase[NCH]; bool pres[NCH];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) {
+            const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
+            pres[t] = act[t] && sl != 0x80000000u;
+            hbase[t] = (sl & p.ffm_mask) + 4 * my_c[t];
+            v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp(); // previous example's partner reads are done
+#pragma unroll
+        for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
+        __syncwarp();
+
+        // ---- forward ----
+        float part = 0.0f;
+        float4 pv[NCH];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) {
+            pv[t] = act[t] ? S[part_off[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act[t] && !diag[t]) {
+                float sd = __fmul_rn(v[t].x, pv[t].x);
+                sd = __fadd_rn(sd, __fmul_rn(v[t].y, pv[t].y));
+                sd = __fadd_rn(sd, __fmul_rn(v[t].z, pv[t].z));
+                sd = __fadd_rn(sd, __fmul_rn(v[t].w, pv[t].w));
+                part += sd;
+            }
+        }
+        part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
+#pragma unroll
+        for (int r = 0; r < 2; r++) if (lr_ok[r]) part += __fmul_rn(__ldcg(p.lr + lr_h[r]).x, lr_v[r]);
+        const float wsum = warp_sum(part);
+
+        float pr, g;
+        if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+        else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+        else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+        else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
+        if (lane == 0) p.preds[ex] = pr;
+        if (!(p.update && importance != 0.0f && g != 0.0f)) continue;
+
+        // ---- update: grad of my chunk = g * partner chunk (values are 1.0); diagonal chunks get exactly 0 ----
+#pragma unroll
+        for (int t = 0; t < NCH; t++) {
+            if (!pres[t] || diag[t]) continue;
+            const float gx = __fmul_rn(g, pv[t].x), gy = __fmul_rn(g, pv[t].y), gz = __fmul_rn(g, pv[t].z), gw = __fmul_rn(g, pv[t].w);
+            if (gx == 0.0f && gy == 0.0f && gz == 0.0f && gw == 0.0f) continue; // partner field absent
+            float4 upd;
+            if (p.optimizer == OPT_SGD) {
+                upd = make_float4(-(gx * p.ffm_lr), -(gy * p.ffm_lr), -(gz * p.ffm_lr), -(gw * p.ffm_lr));
+            } else {
+                const float4 gg = make_float4(gx * gx, gy * gy, gz * gz, gw * gw);
+                const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
+                upd.x = -opt_step(p.optimizer, gx, old.x + gg.x, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                upd.y = -opt_step(p.optimizer, gy, old.y + gg.y, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                upd.z = -opt_step(p.optimizer, gz, old.z + gg.z, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                upd.w = -opt_step(p.optimizer, gw, old.w + gg.w, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+            }
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + hbase[t]), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+        }
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            if (!lr_ok[r]) continue;
+            float *cell = reinterpret_cast<float *>(p.lr + lr_h[r]);
+            const float grad = __fmul_rn(g, lr_v[r]);
+            float upd;
+            if (p.optimizer == OPT_SGD) upd = grad * p.lr_lr;
+            else {
+                const float gg = grad * grad;
+                const float old = atomicAdd(cell + 1, gg);
+                upd = opt_step(p.optimizer, grad, old + gg, p.lut_lr, p.lr_lr, p.lr_mpt);
+            }
+            atomicAdd(cell, -upd);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Translate: raw record -> AoS feature lists (feature_buffer.rs:178-338), one thread per example.
 // ---------------------------------------------------------------------------------------------
@@ -463,6 +687,8 @@ struct TranslateParams {
     ExMeta *meta;
     uint4 *lr_ent, *ffm_ent;
     uint32_t *err_flag; // bit1: slab overflow
+    const uint32_t *ex_list;  // optional: translate only these examples (the fast kernel's leftovers) ...
+    const uint32_t *ex_count; // ... their number, in device memory
 };
 
 // feature_reader! (feature_buffer.rs:48-108) for a primitive namespace: number of features and accessors
@@ -488,15 +714,17 @@ __device__ __forceinline__ float ns_val(const NsView &v, uint32_t i) { return (v
 #define FWGPU_MAX_COMBO_NS 8
 __global__ void __launch_bounds__(256) k_translate(const TranslateParams p)
 {
-    const uint32_t ex = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ex >= p.n_examples) return;
+    const uint32_t slot_i = blockIdx.x * blockDim.x + threadIdx.x; // position in the output arrays
+    if (slot_i >= (p.ex_count ? *p.ex_count : p.n_examples)) return;
+    const uint32_t ex = p.ex_list ? p.ex_list[slot_i] : slot_i;     // which record
     const uint32_t *rec = p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len);
     ExMeta m;
     m.label = (float)rec[1];                 // feature_buffer.rs:190
     m.importance = __uint_as_float(rec[2]);  // :191-192
-    m.lr_begin = ex * p.lr_stride;
-    m.ffm_begin = ex * p.ffm_stride;
-    m.pad0 = m.pad1 = 0;
+    m.lr_begin = slot_i * p.lr_stride;
+    m.ffm_begin = slot_i * p.ffm_stride;
+    m.out_index = ex;
+    m.pad1 = 0;
     uint4 *lr = p.lr_ent + (size_t)m.lr_begin;
     uint4 *ffm = p.ffm_ent + (size_t)m.ffm_begin;
     uint32_t nlr = 0, nffm = 0;
@@ -556,7 +784,7 @@ __global__ void __launch_bounds__(256) k_translate(const TranslateParams p)
         if (nlr > p.lr_stride) m.lr_cnt = p.lr_stride;
         // an over-long ffm list keeps its true count so k_learn flags and skips the example
     }
-    p.meta[ex] = m;
+    p.meta[slot_i] = m;
 }
 
 // CSR (host layout of fwgpu_batch) -> AoS
@@ -576,7 +804,8 @@ __global__ void __launch_bounds__(256) k_pack(const PackParams p)
         m.label = p.labels[i]; m.importance = p.importance[i];
         m.lr_begin = p.lr_off[i]; m.lr_cnt = p.lr_off[i + 1] - p.lr_off[i];
         m.ffm_begin = p.ffm_off ? p.ffm_off[i] : 0; m.ffm_cnt = p.ffm_off ? p.ffm_off[i + 1] - p.ffm_off[i] : 0;
-        m.pad0 = m.pad1 = 0;
+        m.out_index = i;
+        m.pad1 = 0;
         p.meta[i] = m;
     }
     if (i < p.n_lr) p.lr_ent[i] = make_uint4(p.lr_hash[i], __float_as_uint(p.lr_val[i]), p.lr_combo[i], 0);

@@ -412,9 +412,44 @@ def test_records_path_equals_csr_path():
     recs = w.records(n)
     d = util.oracle_translate_batch(util.oracle_spec(w.mi), recs, fixed_len=w.record_len)
     r1, r2 = fw.Regressor(w.mi), fw.Regressor(w.mi)
-    p1 = r1.learn_records(recs.reshape(-1), n_examples=n, update=False)
-    p2 = r2.predict_batch(util.csr_from_dict(d))
-    assert np.array_equal(p1, p2)
+    p1 = r1.learn_records(recs.reshape(-1), n_examples=n, update=False)  # fused fast kernel (warp per record)
+    p2 = r2.predict_batch(util.csr_from_dict(d))                           # general kernel on translated features
+    assert np.max(np.abs(p1 - p2)) <= 1e-6
+    want = util.oracle_regressor(w.mi).learn_batch(d, update=False)
+    assert np.max(np.abs(p1 - want)) <= TOL and np.max(np.abs(p2 - want)) <= TOL
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_fast_path_with_leftovers(k):
+    """Records whose namespaces hold several features / weights do not fit the fused kernel: they are listed
+    and go through translate + the general kernel.  Every prediction still matches the oracle, and training on
+    the mixed stream moves the same weights."""
+    rng = np.random.default_rng(5 + k)
+    n_ns = 6
+    mi = new_mi(learning_rate=0.1, power_t=0.5, ffm_learning_rate=0.05, ffm_power_t=0.5, bit_precision=18, ffm_k=k,
+                ffm_bit_precision=18, optimizer=Optimizer.AdagradLUT,
+                feature_combo_descs=[([j], 1.0) for j in range(n_ns)] + [([0, 1], 1.0), ([2, 3, 4], 0.5)],
+                ffm_fields=[[j] for j in range(n_ns)], num_namespaces=n_ns, max_ffm_per_example=32, max_lr_per_example=64)
+    recs, offs = _random_records(rng, 3000, n_ns, multi=True)
+    ora = util.oracle_regressor(mi)
+    ora.lr_table[:, 0] = rng.normal(0, 0.2, ora.lr_table.shape[0]).astype(np.float32)
+    ora.ffm_weights[:] = rng.normal(0, 0.3, ora.ffm_weights.shape[0]).astype(np.float32)
+    re = fw.Regressor(mi)
+    util.sync_tables_from_oracle(re, ora)
+    re.set_examples_seen(0)
+    d = util.oracle_translate_batch(util.oracle_spec(mi), recs, rec_off=offs.astype(np.uint64))
+    want = ora.learn_batch(d, update=False)
+    got = re.learn_records(recs, rec_off=offs, update=False)
+    assert np.max(np.abs(got - want)) <= TOL
+    # now learn on it: every example must have been processed exactly once (LR accumulators count the hits)
+    re.learn_records(recs, rec_off=offs, update=True)
+    acc = re.get_lr_table()[:, 1]
+    const_cell = 11650396 & ((1 << 18) - 1)
+    ora.learn_batch(d, update=True)
+    assert acc[const_cell] > 0
+    touched_gpu = np.flatnonzero(re.get_lr_table()[:, 1] != ora.lr_table[:, 1] * 0)
+    touched_ora = np.flatnonzero(ora.lr_table[:, 1] != 0)
+    assert np.array_equal(touched_gpu, touched_ora)
 
 
 def test_dataset_resident_path_and_determinism_of_predict():
