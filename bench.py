@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="examples in the cpu_baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--uniform-ids", action="store_true", help="diagnostic: uniform feature ids instead of Zipf (no hot rows)")
     return ap.parse_args()
 
 
@@ -186,7 +187,7 @@ def run_ours(args):
     hp = C.c_void_p()
     assert L.fwgpu_host_alloc(C.byref(hp), nbytes) == 0
     recs = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n, w.record_len))
-    w.records(n, first=rank * n, seed=1, out=recs)
+    w.records(n, first=rank * n, seed=1, out=recs, uniform=args.uniform_ids)
     pp = C.c_void_p()
     assert L.fwgpu_host_alloc(C.byref(pp), n * 4) == 0
     preds = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(n,))
@@ -284,7 +285,7 @@ def run_ours(args):
             "metric": "examples/sec FFM training", "value": value, "unit": "examples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{w.name}: {w.description}", "examples_per_step_per_gpu": n,
+            "config": {"workload": f"{w.name}: {w.description}" + (" [DIAGNOSTIC: uniform ids]" if args.uniform_ids else ""), "examples_per_step_per_gpu": n,
                        "parallelism": f"replicas x{world} (independent models, disjoint example shards)" if world > 1 else "single GPU",
                        "l2_policy": f"inputs larger than L2: {nbytes >> 20} MiB of records per step; table ({(w.mi.ffm_k and ((1 << w.mi.ffm_bit_precision) * 8 >> 20))} MiB w+acc) is L2-resident by nature for c2",
                        "optimizer": "AdagradLUT", "semantics": "Hogwild on device, chunked launches"},

@@ -97,7 +97,7 @@ struct fwgpu_ctx {
     int num_sms = 0;
     size_t smem_optin = 0;
     int force_T = 0;
-    int minb = 3;
+    int minb = 4;
     uint64_t launches = 0;
     uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
     uint32_t ramp_div = 32;
@@ -450,6 +450,8 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
     p.optimizer = c->optimizer;
     p.lr_lr = c->d.learning_rate; p.lr_mpt = -c->d.power_t; p.ffm_lr = c->d.ffm_learning_rate; p.ffm_mpt = -c->d.ffm_power_t;
     p.update = update; p.err_flag = c->err_flag;
+    p.simple_update = 1; // measured on B200 (c3): one chunk at a time with 4 blocks/SM beats rounds of four with 3
+    if (const char *t = getenv("FWGPU_SIMPLE_UPDATE")) p.simple_update = atoi(t);
     size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 16;
     size_t group_bytes = ((words * 4 + 15) / 16) * 16;
     p.group_smem_bytes = (uint32_t)group_bytes;
@@ -507,15 +509,22 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
 template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
 {
     auto kern = k_learn_fixed<NCH>;
+    constexpr int NW = FIXED_WARPS;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e0 != cudaSuccess) return e0;
+        configured = smem;
+    }
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    uint32_t grid = std::min<uint32_t>((p.n_examples + 7) / 8, (uint32_t)(c->num_sms * per_sm));
-    if (p.max_groups) grid = std::min<uint32_t>(grid, (p.max_groups + 7) / 8);
-    *full_groups = (uint32_t)(c->num_sms * per_sm) * 8;
+    uint32_t grid = std::min<uint32_t>((p.n_examples + NW - 1) / NW, (uint32_t)(c->num_sms * per_sm));
+    if (p.max_groups) grid = std::min<uint32_t>(grid, (p.max_groups + NW - 1) / NW);
+    *full_groups = (uint32_t)(c->num_sms * per_sm) * NW;
     if (grid == 0) return cudaSuccess;
-    kern<<<grid, 256, smem, c->stream>>>(p);
+    kern<<<grid, NW * 32, smem, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
 }
@@ -658,7 +667,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
         fp.optimizer = c->optimizer; fp.lr_lr = c->d.learning_rate; fp.lr_mpt = -c->d.power_t; fp.ffm_lr = c->d.ffm_learning_rate; fp.ffm_mpt = -c->d.ffm_power_t;
         fp.update = update; fp.preds = (float *)c->preds.p; fp.leftover_idx = left_idx; fp.leftover_cnt = left_cnt;
         fp.warp_smem_floats = c->F * (fp.cpr + 1) * 4;
-        const size_t smem = (size_t)fp.warp_smem_floats * 4 * 8;
+        const size_t smem = (size_t)fp.warp_smem_floats * 4 * FIXED_WARPS + (size_t)2 * FIXED_WARPS * FIXED_LR_MAX * 8;
         uint32_t done = 0;
         while (done < count) {
             uint32_t cnt = count - done, cap = 0;

@@ -62,6 +62,7 @@ struct LearnParams {
     uint32_t group_smem_bytes;
     uint32_t max_groups;    // 0 = all resident groups; else cap on examples in flight (concurrency ramp)
     const uint32_t *n_examples_dev; // when set, the number of examples is read from device memory (leftover list)
+    int simple_update;      // debug knob: one chunk at a time (ATOMG -> REDG) instead of rounds of four
     int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
 };
 
@@ -136,18 +137,22 @@ __device__ __forceinline__ float expf_libm(float x)
 // logistic(t) = (1.0 + (-t).exp()).recip()   (block_loss_functions.rs:15-17)
 __device__ __forceinline__ float logistic(float t) { return __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_libm(-t))); }
 
+// new accumulator = old + g*g with two roundings (optimizer.rs:77-79, 148-151).  Never an FMA: the LUT is a step function
+// of this sum's top bits, and a fused g*g+old lands in the neighbouring bucket once in ~2^20 updates.
+__device__ __forceinline__ float acc_after(float old, float grad) { return __fadd_rn(old, __fmul_rn(grad, grad)); }
+
 // optimizer.rs calculate_update given the accumulator value *after* adding g^2
 __device__ __forceinline__ float opt_step(uint32_t optimizer, float grad, float new_acc, const float *__restrict__ lut, float lr, float mpt)
 {
     if (optimizer == OPT_LUT) { // optimizer.rs:147-156
         uint32_t key = __float_as_uint(new_acc) >> 20;
-        return grad * __ldg(lut + key);
+        return __fmul_rn(grad, __ldg(lut + key));
     }
     if (optimizer == OPT_FLEX) { // optimizer.rs:76-89
-        float u = grad * lr * powf(new_acc, mpt);
+        float u = __fmul_rn(__fmul_rn(grad, lr), powf(new_acc, mpt));
         return (isnan(u) || isinf(u)) ? 0.0f : u;
     }
-    return grad * lr; // optimizer.rs:35-37
+    return __fmul_rn(grad, lr); // optimizer.rs:35-37
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -390,7 +395,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                         // AdaGrad with a zero initial accumulator turns any residue into a full-size step.
                         if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
                         grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
-                        gg[j] = grad[j] * grad[j];
+                        gg[j] = __fmul_rn(grad[j], grad[j]);
                     }
                     float upd[VEC];
                     if (p.optimizer == OPT_SGD) {
@@ -399,11 +404,17 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                     } else {
                         atom_add_vec<VEC>(p.ffm_acc + h + x0, gg, old);
 #pragma unroll
-                        for (int j = 0; j < VEC; j++) upd[j] = -opt_step(p.optimizer, grad[j], old[j] + gg[j], p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                        for (int j = 0; j < VEC; j++) upd[j] = -opt_step(p.optimizer, grad[j], acc_after(old[j], grad[j]), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
                     }
                     red_add_vec<VEC>(p.ffm_w + h + x0, upd);
                 };
-                if (!overlap) {
+                if (!overlap && p.simple_update) {
+                    const uint32_t total = n * cpr;
+                    for (uint32_t idx = tg; idx < total; idx += T) {
+                        const uint32_t e = fdiv(idx, p.div_cpr);
+                        update_chunk(e, idx - e * cpr);
+                    }
+                } else if (!overlap) {
                     // UB independent chunks per thread and round: all accumulator atomics of a round are in flight
                     // together (one L2 round trip per round instead of one per chunk), then the weight reductions.
                     constexpr int UB = 4;
@@ -441,7 +452,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                             if (on[u] && p.optimizer != OPT_SGD) {
                                 float gg[VEC];
 #pragma unroll
-                                for (int j = 0; j < VEC; j++) gg[j] = gr[j] * gr[j];
+                                for (int j = 0; j < VEC; j++) gg[j] = __fmul_rn(gr[j], gr[j]);
                                 atom_add_vec<VEC>(p.ffm_acc + address, gg, old[u]);
                             }
                         }
@@ -454,7 +465,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
 #pragma unroll
                             for (int j = 0; j < VEC; j++) {
                                 if (p.optimizer == OPT_SGD) upd[j] = -(gr[j] * p.ffm_lr);
-                                else upd[j] = -opt_step(p.optimizer, gr[j], old[u][j] + gr[j] * gr[j], p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                                else upd[j] = -opt_step(p.optimizer, gr[j], acc_after(old[u][j], gr[j]), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
                             }
                             red_add_vec<VEC>(p.ffm_w + address, upd);
                         }
@@ -483,14 +494,17 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                     float upd;
                     if (p.optimizer == OPT_SGD) upd = grad * p.lr_lr;
                     else {
-                        const float gg = grad * grad;
+                        const float gg = __fmul_rn(grad, grad);
                         const float old = atomicAdd(cell + 1, gg);
-                        upd = opt_step(p.optimizer, grad, old + gg, p.lut_lr, p.lr_lr, p.lr_mpt);
+                        upd = opt_step(p.optimizer, grad, acc_after(old, grad), p.lut_lr, p.lr_lr, p.lr_mpt);
                     }
                     atomicAdd(cell, -upd);
                 }
             }
         }
+        // Parity mode: the next example must see this one's weight reductions (REDG is fire-and-forget; without the
+        // fence its gather can overtake them).  Hogwild mode tolerates that staleness by design.
+        if (p.exact_order) __threadfence();
         group_sync<T>(gib); // C / meta are reused by the next example
     }
 }
@@ -527,19 +541,33 @@ struct FixedParams {
     uint32_t warp_smem_floats;     // F * (cpr + 1) * 4
 };
 
+// Block = FIXED_WARPS warps working in lock-step rounds (one record per warp and round).  After every round the
+// block combines its LR updates in shared memory: records that hit the same LR cell -- above all the constant
+// feature, which EVERY record hits (feature_buffer.rs:270-276) -- issue one accumulator atomic and one weight
+// reduction for the block instead of one per record.  Same-address atomics serialise in L2 (~4 ns each on B200,
+// tools/hotrow_microbench.cu), which capped the per-record version at ~180 M records/s.
+// The combined update is  acc += sum g_i^2 ;  w -= (sum g_i) * LUT[acc]  over the records of the round.
+constexpr int FIXED_WARPS = 16;
+constexpr int FIXED_LR_MAX = 64; // LR entries per record the fast path supports (two per lane)
+
 template <int NCH>
-__global__ void __launch_bounds__(256) k_learn_fixed(const FixedParams p)
+__global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const FixedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NW = FIXED_WARPS;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4 *S = reinterpret_cast<float4 *>(smem_raw) + (size_t)wib * (p.warp_smem_floats / 4);
+    // LR exchange area, double-buffered by round parity: [2][NW][FIXED_LR_MAX] hashes then gradients
+    uint32_t *x_hash = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NW * p.warp_smem_floats * 4);
+    float *x_grad = reinterpret_cast<float *>(x_hash + 2 * NW * FIXED_LR_MAX);
     const uint32_t F = p.F, k = p.k, cpr = p.cpr, row_stride = cpr + 1, k4 = k >> 2;
     const uint32_t n_chunks = F * cpr;
-    uint32_t n_warps = gridDim.x * 8;
+    uint32_t n_warps = gridDim.x * NW;
     if (p.max_groups && p.max_groups < n_warps) n_warps = p.max_groups;
-    const uint32_t wid = blockIdx.x * 8 + wib;
-    if (wid >= n_warps) return;
-    const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u);
+    const uint32_t n_blocks = (n_warps + NW - 1) / NW;
+    if (blockIdx.x >= n_blocks) return;
+    const uint32_t gw = blockIdx.x * NW + wib; // global warp index
+    const bool warp_on = gw < n_warps;          // the ramp may leave the last block partly idle
 
     // static per-lane geometry: which chunk(s) I own and where my partner lives
     uint32_t my_e[NCH], my_c[NCH], part_off[NCH], my_off[NCH];
@@ -557,110 +585,144 @@ __global__ void __launch_bounds__(256) k_learn_fixed(const FixedParams p)
     }
     const uint32_t my_field_ns = lane < F ? __ldg(p.field_ns + lane) : 0;
 
-    for (uint32_t ex = p.ex_begin + wid; ex < p.ex_begin + p.n_examples; ex += n_warps) {
-        const uint32_t *rec = p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len);
-        // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
-        const uint32_t slot = lane < F ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
-        bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
-        // LR entries: one per lane (two rounds when there are more than 32)
-        uint32_t lr_h[2]; float lr_v[2]; bool lr_ok[2];
+    for (uint32_t round = 0;; round++) {
+        const uint32_t base = round * n_warps; // round r handles records [r * n_warps, (r+1) * n_warps), one per active warp
+        if (base >= p.n_examples) break;       // uniform over the grid
+        const uint32_t ex = p.ex_begin + base + gw;
+        bool live = warp_on && base + gw < p.n_examples;
+        uint32_t *xh = x_hash + ((round & 1) * NW + wib) * FIXED_LR_MAX;
+        float *xg = x_grad + ((round & 1) * NW + wib) * FIXED_LR_MAX;
+        uint32_t lr_h[2] = {0, 0};
+        float lr_g[2] = {0.0f, 0.0f}; // this record's LR gradients (0 = nothing to apply)
+
+        if (live) {
+            const uint32_t *rec = p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len);
+            // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
+            const uint32_t slot = lane < F ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
+            bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
+            float lr_v[2]; bool lr_ok[2];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const uint32_t i = lane + 32 * r;
-            lr_ok[r] = false; lr_h[r] = 0; lr_v[r] = 0.0f;
-            if (i < p.n_combos) {
-                const uint32_t o0 = __ldg(p.combo_off + i), o1 = __ldg(p.combo_off + i + 1);
-                uint32_t h = 0; bool ok = true;
-                for (uint32_t o = o0; o < o1; o++) {
-                    const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
-                    if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
-                    h = (o == o0) ? sl : ((h * 16777619u) ^ sl); // feature_buffer.rs:239-251
+            for (int r = 0; r < 2; r++) {
+                const uint32_t i = lane + 32 * r;
+                lr_ok[r] = false; lr_v[r] = 0.0f;
+                if (i < p.n_combos) {
+                    const uint32_t o0 = __ldg(p.combo_off + i), o1 = __ldg(p.combo_off + i + 1);
+                    uint32_t h = 0; bool ok = true;
+                    for (uint32_t o = o0; o < o1; o++) {
+                        const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
+                        if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
+                        h = (o == o0) ? sl : ((h * 16777619u) ^ sl); // feature_buffer.rs:239-251
+                    }
+                    lr_ok[r] = ok; lr_h[r] = h & p.lr_mask; lr_v[r] = __ldg(p.combo_weight + i); // value 1.0 * combo weight
+                } else if (i == p.n_combos && p.add_constant) {
+                    lr_ok[r] = true; lr_h[r] = 11650396u & p.lr_mask; lr_v[r] = 1.0f;       // feature_buffer.rs:270-276
                 }
-                lr_ok[r] = ok; lr_h[r] = h & p.lr_mask; lr_v[r] = __ldg(p.combo_weight + i); // value 1.0 * combo weight
-            } else if (i == p.n_combos && p.add_constant) {
-                lr_ok[r] = true; lr_h[r] = 11650396u & p.lr_mask; lr_v[r] = 1.0f;       // feature_buffer.rs:270-276
             }
-        }
-        if (__any_sync(0xffffffffu, bad)) {
-            if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
-            continue;
-        }
-        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
-
-        // ---- gather: one 128-bit load per chunk ----
-        float4 v[NCH];
-        uint32_t hbase[NCH]; bool pres[NCH];
-#pragma unroll
-        for (int t = 0; t < NCH; t++) {
-            const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
-            pres[t] = act[t] && sl != 0x80000000u;
-            hbase[t] = (sl & p.ffm_mask) + 4 * my_c[t];
-            v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        __syncwarp(); // previous example's partner reads are done
-#pragma unroll
-        for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
-        __syncwarp();
-
-        // ---- forward ----
-        float part = 0.0f;
-        float4 pv[NCH];
-#pragma unroll
-        for (int t = 0; t < NCH; t++) {
-            pv[t] = act[t] ? S[part_off[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (act[t] && !diag[t]) {
-                float sd = __fmul_rn(v[t].x, pv[t].x);
-                sd = __fadd_rn(sd, __fmul_rn(v[t].y, pv[t].y));
-                sd = __fadd_rn(sd, __fmul_rn(v[t].z, pv[t].z));
-                sd = __fadd_rn(sd, __fmul_rn(v[t].w, pv[t].w));
-                part += sd;
-            }
-        }
-        part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
-#pragma unroll
-        for (int r = 0; r < 2; r++) if (lr_ok[r]) part += __fmul_rn(__ldcg(p.lr + lr_h[r]).x, lr_v[r]);
-        const float wsum = warp_sum(part);
-
-        float pr, g;
-        if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
-        else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
-        else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
-        else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
-        if (lane == 0) p.preds[ex] = pr;
-        if (!(p.update && importance != 0.0f && g != 0.0f)) continue;
-
-        // ---- update: grad of my chunk = g * partner chunk (values are 1.0); diagonal chunks get exactly 0 ----
-#pragma unroll
-        for (int t = 0; t < NCH; t++) {
-            if (!pres[t] || diag[t]) continue;
-            const float gx = __fmul_rn(g, pv[t].x), gy = __fmul_rn(g, pv[t].y), gz = __fmul_rn(g, pv[t].z), gw = __fmul_rn(g, pv[t].w);
-            if (gx == 0.0f && gy == 0.0f && gz == 0.0f && gw == 0.0f) continue; // partner field absent
-            float4 upd;
-            if (p.optimizer == OPT_SGD) {
-                upd = make_float4(-(gx * p.ffm_lr), -(gy * p.ffm_lr), -(gz * p.ffm_lr), -(gw * p.ffm_lr));
+            if (__any_sync(0xffffffffu, bad)) {
+                if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+                live = false;
             } else {
-                const float4 gg = make_float4(gx * gx, gy * gy, gz * gz, gw * gw);
-                const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
-                upd.x = -opt_step(p.optimizer, gx, old.x + gg.x, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                upd.y = -opt_step(p.optimizer, gy, old.y + gg.y, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                upd.z = -opt_step(p.optimizer, gz, old.z + gg.z, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                upd.w = -opt_step(p.optimizer, gw, old.w + gg.w, p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-            }
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + hbase[t]), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
-        }
+                const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
+
+                // ---- gather: one 128-bit load per chunk ----
+                float4 v[NCH];
+                uint32_t hbase[NCH]; bool pres[NCH];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            if (!lr_ok[r]) continue;
-            float *cell = reinterpret_cast<float *>(p.lr + lr_h[r]);
-            const float grad = __fmul_rn(g, lr_v[r]);
-            float upd;
-            if (p.optimizer == OPT_SGD) upd = grad * p.lr_lr;
-            else {
-                const float gg = grad * grad;
-                const float old = atomicAdd(cell + 1, gg);
-                upd = opt_step(p.optimizer, grad, old + gg, p.lut_lr, p.lr_lr, p.lr_mpt);
+                for (int t = 0; t < NCH; t++) {
+                    const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
+                    pres[t] = act[t] && sl != 0x80000000u;
+                    hbase[t] = (sl & p.ffm_mask) + 4 * my_c[t];
+                    v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float lrw[2];
+#pragma unroll
+                for (int r = 0; r < 2; r++) lrw[r] = lr_ok[r] ? __ldcg(p.lr + lr_h[r]).x : 0.0f;
+                __syncwarp(); // the previous round's partner reads are done
+#pragma unroll
+                for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
+                __syncwarp();
+
+                // ---- forward ----
+                float part = 0.0f;
+                float4 pv[NCH];
+#pragma unroll
+                for (int t = 0; t < NCH; t++) {
+                    pv[t] = act[t] ? S[part_off[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (act[t] && !diag[t]) {
+                        float sd = __fmul_rn(v[t].x, pv[t].x);
+                        sd = __fadd_rn(sd, __fmul_rn(v[t].y, pv[t].y));
+                        sd = __fadd_rn(sd, __fmul_rn(v[t].z, pv[t].z));
+                        sd = __fadd_rn(sd, __fmul_rn(v[t].w, pv[t].w));
+                        part += sd;
+                    }
+                }
+                part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
+#pragma unroll
+                for (int r = 0; r < 2; r++) if (lr_ok[r]) part += __fmul_rn(lrw[r], lr_v[r]);
+                const float wsum = warp_sum(part);
+
+                float pr, g;
+                if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+                else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+                else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+                else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
+                if (lane == 0) p.preds[ex] = pr;
+
+                if (p.update && importance != 0.0f && g != 0.0f) {
+                    // ---- FFM update: grad of my chunk = g * partner chunk (values are 1.0); diagonal chunks get exactly 0 ----
+#pragma unroll
+                    for (int t = 0; t < NCH; t++) {
+                        if (!pres[t] || diag[t]) continue;
+                        const float gx = __fmul_rn(g, pv[t].x), gy = __fmul_rn(g, pv[t].y), gz = __fmul_rn(g, pv[t].z), gw = __fmul_rn(g, pv[t].w);
+                        if (gx == 0.0f && gy == 0.0f && gz == 0.0f && gw == 0.0f) continue; // partner field absent
+                        float4 upd;
+                        if (p.optimizer == OPT_SGD) {
+                            upd = make_float4(-__fmul_rn(gx, p.ffm_lr), -__fmul_rn(gy, p.ffm_lr), -__fmul_rn(gz, p.ffm_lr), -__fmul_rn(gw, p.ffm_lr));
+                        } else {
+                            const float4 gg = make_float4(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz), __fmul_rn(gw, gw));
+                            const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
+                            upd.x = -opt_step(p.optimizer, gx, acc_after(old.x, gx), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                            upd.y = -opt_step(p.optimizer, gy, acc_after(old.y, gy), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                            upd.z = -opt_step(p.optimizer, gz, acc_after(old.z, gz), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                            upd.w = -opt_step(p.optimizer, gw, acc_after(old.w, gw), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                        }
+                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + hbase[t]), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+                    }
+#pragma unroll
+                    for (int r = 0; r < 2; r++) if (lr_ok[r]) lr_g[r] = __fmul_rn(g, lr_v[r]);
+                }
             }
-            atomicAdd(cell, -upd);
+        }
+
+        // ---- LR update, combined over the block's records of this round (block_lr.rs:135-151) ----
+        if (p.update) {
+#pragma unroll
+            for (int r = 0; r < 2; r++) { xh[lane + 32 * r] = lr_h[r]; xg[lane + 32 * r] = lr_g[r]; }
+            __syncthreads();
+            const uint32_t *bh = x_hash + (round & 1) * NW * FIXED_LR_MAX;
+            const float *bg = x_grad + (round & 1) * NW * FIXED_LR_MAX;
+#pragma unroll
+            for (int r = 0; r < 2; r++) {
+                if (lr_g[r] == 0.0f) continue;
+                const uint32_t i = lane + 32 * r;
+                bool first = true;
+                for (int w2 = 0; w2 < wib; w2++)
+                    if (bg[w2 * FIXED_LR_MAX + i] != 0.0f && bh[w2 * FIXED_LR_MAX + i] == lr_h[r]) { first = false; break; }
+                if (!first) continue; // an earlier warp of the block applies this cell for all of us
+                float G = lr_g[r], G2 = __fmul_rn(lr_g[r], lr_g[r]);
+                for (int w2 = wib + 1; w2 < NW; w2++) {
+                    const float g2 = bg[w2 * FIXED_LR_MAX + i];
+                    if (g2 != 0.0f && bh[w2 * FIXED_LR_MAX + i] == lr_h[r]) { G += g2; G2 += g2 * g2; }
+                }
+                float *cell = reinterpret_cast<float *>(p.lr + lr_h[r]);
+                float upd;
+                if (p.optimizer == OPT_SGD) upd = __fmul_rn(G, p.lr_lr);
+                else {
+                    const float old = atomicAdd(cell + 1, G2);
+                    upd = opt_step(p.optimizer, G, __fadd_rn(old, G2), p.lut_lr, p.lr_lr, p.lr_mpt);
+                }
+                atomicAdd(cell, -upd);
+            }
         }
     }
 }

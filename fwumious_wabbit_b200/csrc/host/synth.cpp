@@ -46,12 +46,14 @@ inline double planted_pair(uint64_t seed, uint32_t j, uint32_t a, uint32_t b)
 
 struct Sample { uint32_t id; };
 
+// bit 63 of the seed selects uniform ids instead of the log-uniform (Zipf ~ 1) law: a diagnostic stream without hot rows
 inline void draw_ids(uint64_t seed, uint64_t i, uint32_t n_ns, const uint32_t *card, uint32_t *ids, uint32_t *label)
 {
     double score = -0.4;
+    const bool uniform = (seed >> 63) != 0;
     for (uint32_t j = 0; j < n_ns; j++) {
         uint64_t h = splitmix64(seed ^ splitmix64(i * 0x9e3779b97f4a7c15ULL + j));
-        ids[j] = zipf_id(h, card[j]);
+        ids[j] = uniform ? (uint32_t)(h % card[j]) : zipf_id(h, card[j]);
         score += planted(seed, j, ids[j]) / std::sqrt((double)n_ns / 4.0);
     }
     for (uint32_t j = 0; j + 1 < n_ns; j += 2) score += planted_pair(seed, j, ids[j] % 64, ids[j + 1] % 64);

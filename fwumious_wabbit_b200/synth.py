@@ -46,8 +46,11 @@ class Workload:
     def record_len(self):
         return 3 + self.n_namespaces
 
-    def records(self, n_examples, first=0, seed=1, out=None, threads=0):
-        """(n_examples, 3 + N) uint32 array of fixed-width records."""
+    def records(self, n_examples, first=0, seed=1, out=None, threads=0, uniform=False):
+        """(n_examples, 3 + N) uint32 array of fixed-width records.  uniform=True draws ids uniformly instead of
+        Zipf-like (a diagnostic stream without hot rows)."""
+        if uniform:
+            seed |= 1 << 63
         if out is None:
             out = np.empty((n_examples, self.record_len), dtype=np.uint32)
         assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= n_examples * self.record_len

@@ -521,18 +521,21 @@ def test_edge_cases():
 
 
 def test_too_many_features_is_reported():
-    mi = cfg_mi("k4_f8")
-    mi.max_ffm_per_example = 8
+    """An example with more FFM features than max_ffm_per_example cannot be staged: the call reports
+    FWGPU_ERR_TOO_LARGE at sync (its prediction is NaN, nothing is learned from it) instead of corrupting memory."""
+    rng = np.random.default_rng(9)
+    n_ns = 6
+    mi = new_mi(bit_precision=18, ffm_k=4, ffm_bit_precision=18, optimizer=Optimizer.AdagradLUT,
+                feature_combo_descs=[([j], 1.0) for j in range(n_ns)], ffm_fields=[[j] for j in range(n_ns)],
+                num_namespaces=n_ns, max_ffm_per_example=6, max_lr_per_example=64)
+    recs, offs = _random_records(rng, 200, n_ns, multi=True)  # multi-valued namespaces: up to 18 features per example
     re = fw.Regressor(mi)
-    w = synth.workload("c2")
-    # records path with a stride of 8 but fields referencing 8 namespaces is fine; shrink to force overflow
-    mi2 = cfg_mi("k4_f8")
-    mi2.max_ffm_per_example = 4
-    re2 = fw.Regressor(mi2)
-    recs = w.records(16)
     with pytest.raises(_lib.FwgpuError) as ei:
-        re2.learn_records(recs.reshape(-1), n_examples=16, update=True)
+        re.learn_records(recs, rec_off=offs, update=True)
     assert ei.value.status == _lib.ERR_TOO_LARGE
+    # the ctx stays usable afterwards
+    simple = np.array([3 + n_ns, 1, 0x3F800000] + [7 * (j + 1) for j in range(n_ns)], dtype=np.uint32)
+    assert re.learn_records(simple, n_examples=1, update=False).shape == (1,)
 
 
 @pytest.mark.parametrize("name", ["c2", "c3"])

@@ -1,0 +1,11 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_exp3.txt 2>&1); grep -E "^FAILED|passed|failed" gpurun_out/pytest_gpu_exp3.txt | head
+summ() { python -c "
+import sys,json
+d=json.loads(open(sys.argv[1]).read()); r=d['roofline']
+print(sys.argv[2], 'value %.1fM ex/s'%(d['value']/1e6), ('e2e %.1fM'%(d['e2e']['value']/1e6)) if d.get('e2e') else '', 'frac %.3f'%r['frac'], 'launch ms %.3f'%r['avg_launch_ms'], 'll', d['e2e']['last_step_logloss'] if d.get('e2e') else None)
+" $1 "$2" 2>&1 | tail -1; }
+timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/exp3_c2.json 2> gpurun_out/exp3_c2.err; summ gpurun_out/exp3_c2.json "c2 zipf"; tail -2 gpurun_out/exp3_c2.err
+timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e --uniform-ids > gpurun_out/exp3_c2u.json 2> gpurun_out/exp3_c2u.err; summ gpurun_out/exp3_c2u.json "c2 uniform"
+timeout 300 python bench.py --workload c1 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/exp3_c1.json 2> gpurun_out/exp3_c1.err; summ gpurun_out/exp3_c1.json "c1"; tail -2 gpurun_out/exp3_c1.err
