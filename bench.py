@@ -98,18 +98,9 @@ class ClockSampler(threading.Thread):
 
 
 def dist_setup(n_gpus):
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist_mod
+    from fwumious_wabbit_b200 import dist_util
 
-        torch.cuda.set_device(local_rank)
-        dist_mod.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
-        dist = dist_mod
-    return world, rank, local_rank, dist
+    return dist_util.init("nccl")
 
 
 def cpu_baseline(w, n_sample, threads, seed=1):
@@ -187,7 +178,10 @@ def run_ours(args):
     hp = C.c_void_p()
     assert L.fwgpu_host_alloc(C.byref(hp), nbytes) == 0
     recs = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n, w.record_len))
-    w.records(n, first=rank * n, seed=1, out=recs, uniform=args.uniform_ids)
+    from fwumious_wabbit_b200 import dist_util
+
+    first, _ = dist_util.shard(rank, world, n)
+    w.records(n, first=first, seed=1, out=recs, uniform=args.uniform_ids)
     pp = C.c_void_p()
     assert L.fwgpu_host_alloc(C.byref(pp), n * 4) == 0
     preds = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(n,))
@@ -200,11 +194,7 @@ def run_ours(args):
         re.sync()
 
     def max_over_ranks(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return dist_util.max_over_ranks(x, dist, device="cuda")
 
     # ---------------- value: records resident in HBM ----------------
     for _ in range(args.warmup):
@@ -229,7 +219,7 @@ def run_ours(args):
     t_ms, t_n = re.kernel_time(1)
     re.set_profiling(False)
     sampler.join(timeout=2)
-    value = world * n * args.steps / (ms_total * 1e-3)
+    value = dist_util.whole_job_rate(n, args.steps, world, ms_total)
 
     # ---------------- e2e: host buffers through the C ABI ----------------
     e2e = None

@@ -437,7 +437,7 @@ template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnPara
 }
 
 static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_cap, int update, const uint32_t *n_examples_dev = nullptr,
-                                 bool count_seen = true)
+                                 bool count_seen = true, uint32_t lr_cap = 0)
 {
     if (n_examples == 0) return FWGPU_OK;
     LearnParams p{};
@@ -452,7 +452,9 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
     p.update = update; p.err_flag = c->err_flag;
     p.simple_update = 1; // measured on B200 (c3): one chunk at a time with 4 blocks/SM beats rounds of four with 3
     if (const char *t = getenv("FWGPU_SIMPLE_UPDATE")) p.simple_update = atoi(t);
-    size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 16;
+    p.kv = (c->k == 0 || c->k % std::max<uint32_t>(c->VEC, 1) == 0) ? 1 : 0;
+    p.lr_cap = std::min<uint32_t>(lr_cap, 1024);
+    size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 16 + p.lr_cap;
     size_t group_bytes = ((words * 4 + 15) / 16) * 16;
     p.group_smem_bytes = (uint32_t)group_bytes;
     int T = 32;
@@ -585,7 +587,9 @@ static fwgpu_status learn_batch_impl(fwgpu_ctx *c, const fwgpu_batch *b, float *
     }
     CUDA_TRY(c, cudaGetLastError());
     uint32_t n_cap = std::max(max_ffm, c->n_field_refs);
-    if ((st = launch_learn(c, n, n_cap, update))) return st;
+    uint32_t max_lr = 0;
+    for (uint32_t i = 0; i < n; i++) max_lr = std::max(max_lr, b->lr_off[i + 1] - b->lr_off[i]);
+    if ((st = launch_learn(c, n, n_cap, update, nullptr, true, max_lr))) return st;
     if (preds_out) CUDA_TRY(c, cudaMemcpyAsync(preds_out, c->preds.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
     return FWGPU_OK;
 }
@@ -704,7 +708,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
     }
     CUDA_TRY(c, cudaGetLastError());
     if (!run_learn) return FWGPU_OK;
-    if ((st = launch_learn(c, count, ffm_stride, update, use_fast ? tp.ex_count : nullptr, !use_fast))) return st;
+    if ((st = launch_learn(c, count, ffm_stride, update, use_fast ? tp.ex_count : nullptr, !use_fast, lr_stride))) return st;
     if (preds_host) CUDA_TRY(c, cudaMemcpyAsync(preds_host, c->preds.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream));
     return FWGPU_OK;
 }

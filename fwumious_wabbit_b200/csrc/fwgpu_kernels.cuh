@@ -62,6 +62,8 @@ struct LearnParams {
     uint32_t group_smem_bytes;
     uint32_t max_groups;    // 0 = all resident groups; else cap on examples in flight (concurrency ramp)
     const uint32_t *n_examples_dev; // when set, the number of examples is read from device memory (leftover list)
+    int kv;                 // k % VEC == 0: a 16-byte chunk never straddles two field blocks (all BASELINE shapes)
+    uint32_t lr_cap;        // LR hashes staged in shared memory for the duplicate check (0 = read them from global)
     int simple_update;      // debug knob: one chunk at a time (ATOMG -> REDG) instead of rounds of four
     int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
 };
@@ -158,7 +160,7 @@ __device__ __forceinline__ float opt_step(uint32_t optimizer, float grad, float 
 // ---------------------------------------------------------------------------------------------
 // k_learn<T, VEC>: T threads per example, VEC floats per memory transaction.
 // Block = 256 threads = 256/T groups.  Dynamic smem = groups * p.group_smem_bytes.
-// Group smem layout (floats): C[F*Fk] | d[n_cap*k] | val[n_cap] | hash[n_cap] | field[n_cap] | fstart[F+1] | red[16]
+// Group smem layout (floats): C[F*Fk] | d[n_cap*k] | val[n_cap] | hash[n_cap] | field[n_cap] | fstart[F+1] | red[16] | lrh[lr_cap]
 // ---------------------------------------------------------------------------------------------
 template <int T, int VEC, int MINB>
 __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
     uint32_t *field = hash + ncap;
     uint32_t *fstart = field + ncap;
     float *red = reinterpret_cast<float *>(fstart + F + 1);
+    uint32_t *lrh = reinterpret_cast<uint32_t *>(red + 16);
 
     const float *__restrict__ W = p.ffm_w;
 
@@ -200,6 +203,8 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
         float part = 0.0f;
         bool overlap = false;
 
+        const bool lr_staged = nlr <= p.lr_cap;
+        if (lr_staged) for (uint32_t i = tg; i < nlr; i += T) lrh[i] = __ldg(&le[i].x); // visible after the next group_sync
         if (F > 0) {
             // ---- stage the example's feature list ------------------------------------------------
             for (uint32_t i = tg; i < n; i += T) {
@@ -248,13 +253,14 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                             ldcg_vec<VEC>(W + hash[e] + x0, wv);
                         }
                         const float v = val[e];
+                        const bool own_chunk = p.kv && x0 >= z * k && x0 < z * k + k;
 #pragma unroll
                         for (int j = 0; j < VEC; j++) {
                             // first feature assigns w*v, the rest accumulate (separate roundings as in the reference)
                             float t = __fmul_rn(wv[j], v);
                             acc[j] = (e == e0[u]) ? t : __fadd_rn(acc[j], t);
-                            uint32_t x = x0 + j;
-                            if (x >= z * k && x < z * k + k) d[e * k + (x - z * k)] = wv[j]; // own-field block of feature e
+                            if (p.kv) { if (own_chunk) d[e * k + (x0 - z * k) + j] = wv[j]; }
+                            else { uint32_t x = x0 + j; if (x >= z * k && x < z * k + k) d[e * k + (x - z * k)] = wv[j]; } // own-field block of feature e
                         }
                     }
 #pragma unroll
@@ -385,17 +391,36 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                     const uint32_t f = field[e], h = hash[e], x0 = c * VEC;
                     const float v = val[e];
                     float grad[VEC], gg[VEC], old[VEC];
+                    if (p.kv) {
+                        // the whole chunk lies in the block towards one field zc
+                        const uint32_t zc = fdiv(x0, p.div_k), q0 = x0 - zc * k;
+                        const bool own = (zc == f);
+                        // a lone feature's own-field block: the gradient is exactly 0, the reference's update a no-op
+                        if (own && fstart[f + 1] - fstart[f] == 1) return;
+                        const float *cp = C + zc * Fk + f * k + q0;
+                        bool any = false;
 #pragma unroll
-                    for (int j = 0; j < VEC; j++) {
-                        const uint32_t x = x0 + j;
-                        const uint32_t z = fdiv(x, p.div_k), q = x - z * k;
-                        float cz = C[z * Fk + f * k + q];
-                        // separate roundings, never an FMA: for a lone feature C[f][f-block] IS fl(w*v), so the
-                        // self-interaction must cancel to exactly 0 like the reference's (block_ffm.rs:238-240);
-                        // AdaGrad with a zero initial accumulator turns any residue into a full-size step.
-                        if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
-                        grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
-                        gg[j] = __fmul_rn(grad[j], grad[j]);
+                        for (int j = 0; j < VEC; j++) {
+                            float cz = cp[j];
+                            if (own) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q0 + j], v));
+                            grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
+                            gg[j] = __fmul_rn(grad[j], grad[j]);
+                            any = any || grad[j] != 0.0f;
+                        }
+                        if (!any) return; // partner field absent
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < VEC; j++) {
+                            const uint32_t x = x0 + j;
+                            const uint32_t z = fdiv(x, p.div_k), q = x - z * k;
+                            float cz = C[z * Fk + f * k + q];
+                            // separate roundings, never an FMA: for a lone feature C[f][f-block] IS fl(w*v), so the
+                            // self-interaction must cancel to exactly 0 like the reference's (block_ffm.rs:238-240);
+                            // AdaGrad with a zero initial accumulator turns any residue into a full-size step.
+                            if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
+                            grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
+                            gg[j] = __fmul_rn(grad[j], grad[j]);
+                        }
                     }
                     float upd[VEC];
                     if (p.optimizer == OPT_SGD) {
@@ -484,10 +509,12 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
             for (uint32_t i = tg; i < nlr; i += T) {
                 const uint4 e = __ldg(le + i);
                 bool owner = true;
-                for (uint32_t j = 0; j < i; j++) if (__ldg(&le[j].x) == e.x) { owner = false; break; }
+                if (lr_staged) { for (uint32_t j = 0; j < i; j++) if (lrh[j] == e.x) { owner = false; break; } }
+                else { for (uint32_t j = 0; j < i; j++) if (__ldg(&le[j].x) == e.x) { owner = false; break; } }
                 if (!owner) continue;
                 float *cell = reinterpret_cast<float *>(p.lr + e.x);
                 for (uint32_t j = i; j < nlr; j++) {
+                    if (lr_staged && j != i && lrh[j] != e.x) continue;
                     const uint4 ej = (j == i) ? e : __ldg(le + j);
                     if (ej.x != e.x) continue;
                     const float grad = g * __uint_as_float(ej.y);
