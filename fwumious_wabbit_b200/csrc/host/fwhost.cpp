@@ -1,0 +1,552 @@
+// Host-side pieces either side of the GPU hot path (include/fwhost.h): VW text parser (parser.rs),
+// .fwcache reader/writer (cache.rs), regressor file (persistence.rs), command-line -> ModelInstance
+// (model_instance.rs:296-495).  CPU code, C ABI outside; nothing here calls oracle/.
+#include "../../../include/fwhost.h"
+#include "model.hpp"
+#include "murmur3.hpp"
+
+#include <atomic>
+#include <cerrno>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+using namespace fwhost;
+
+namespace {
+
+void set_err(char *err, size_t cap, const std::string &m) { if (err && cap) { snprintf(err, cap, "%s", m.c_str()); } }
+char *dup_string(const std::string &s) { char *p = (char *)malloc(s.size() + 1); memcpy(p, s.data(), s.size()); p[s.size()] = 0; return p; }
+
+constexpr uint32_t HEADER_LEN = 3, LABEL_OFFSET = 1, IMPORTANCE_OFFSET = 2;
+constexpr uint32_t IS_NOT_SINGLE_MASK = 1u << 31, MASK31 = ~IS_NOT_SINGLE_MASK, NO_FEATURES = IS_NOT_SINGLE_MASK, NO_LABEL = 0xff, FLOAT32_ONE = 1065353216u;
+
+// ---------------------------------------------------------------- parser (parser.rs:214-461)
+struct NsInfo { uint32_t index; uint32_t seed; bool f32; };
+struct Parser {
+    VwMap vw;
+    std::unordered_map<std::string, NsInfo> by_name; // the reference uses a radix tree (radix_tree.rs); any exact map is equivalent
+    uint32_t n_ns = 0;
+};
+
+bool rust_parse_f32(const char *s, size_t a, size_t b, float *out)
+{
+    // parse_float_or_error (parser.rs:110-139): "NONE" -> NaN, otherwise Rust's str::parse::<f32>()
+    if (b - a == 4 && !memcmp(s + a, "NONE", 4)) { *out = NAN; return true; }
+    if (b <= a || b - a > 63) return false;
+    char tmp[64];
+    memcpy(tmp, s + a, b - a);
+    tmp[b - a] = 0;
+    for (size_t i = 0; i < b - a; i++) {
+        char c = tmp[i];
+        bool ok = (c >= '0' && c <= '9') || c == '.' || c == '-' || c == '+' || c == 'e' || c == 'E' || strchr("infatyINFATY", c);
+        if (!ok) return false;
+    }
+    char *end = nullptr;
+    float v = strtof(tmp, &end);
+    if (end == tmp || *end) return false;
+    *out = v;
+    return true;
+}
+
+// returns record length in words; 0 = empty; -1 error; -2 flush; -3 hogwild_load
+int parse_line(const Parser &P, const char *p, size_t size, uint32_t *out, size_t cap, std::string &err)
+{
+    if (size == 0) return 0;
+    const size_t bufpos = P.n_ns + HEADER_LEN;
+    if (cap < bufpos) { err = "record buffer too small"; return -1; }
+    size_t olen = bufpos;
+    for (size_t i = 0; i < bufpos; i++) out[i] = NO_FEATURES;
+    size_t i_start, i_end = 0;
+    switch ((unsigned char)p[0]) {
+    case 0x31: out[LABEL_OFFSET] = 1; break;
+    case 0x2d: out[LABEL_OFFSET] = 0; break;
+    case 0x7c: out[LABEL_OFFSET] = NO_LABEL; break;
+    default: {
+        if (size >= 5 && !memcmp(p, "flush", 5)) return -2;
+        if (size >= strlen("hogwild_load ")) {
+            size_t ntok = 0, i = 0, first_len = 0;
+            while (i < size) {
+                size_t s0 = i;
+                while (i < size && p[i] != 0x20) i++;
+                if (ntok == 0) first_len = i - s0;
+                ntok++;
+                while (i < size && p[i] == 0x20) i++;
+            }
+            if (ntok == 2 && first_len == 12 && !memcmp(p, "hogwild_load", 12)) return -3;
+        }
+        err = "Cannot parse an example";
+        return -1;
+    }
+    }
+    const size_t rowlen = size - 1; // ignore last newline byte (parser.rs:270)
+    if (out[LABEL_OFFSET] == NO_LABEL) out[IMPORTANCE_OFFSET] = FLOAT32_ONE;
+    else {
+        while (p[i_end] != 0x20 && i_end < rowlen) i_end++;
+        while (p[i_end] == 0x20 && i_end < rowlen) i_end++;
+        if (p[i_end] == 0x7c) out[IMPORTANCE_OFFSET] = FLOAT32_ONE;
+        else {
+            i_start = i_end;
+            while (p[i_end] != 0x20 && i_end < rowlen) i_end++;
+            float imp;
+            if (!rust_parse_f32(p, i_start, i_end, &imp)) { err = "Failed parsing example importance: " + std::string(p + i_start, i_end - i_start); return -1; }
+            if (imp < 0.0f) { char b[96]; snprintf(b, sizeof(b), "Example importance cannot be negative: %g! ", imp); err = b; return -1; }
+            memcpy(&out[IMPORTANCE_OFFSET], &imp, 4);
+        }
+    }
+    while (p[i_end] != 0x7c && i_end < rowlen) i_end++;
+    uint32_t cur_seed = 0;
+    size_t cur_off = HEADER_LEN, ns_start = 0;
+    bool cur_f32 = false;
+    float cur_w = 1.0f;
+    uint32_t cur_n = 0;
+    while (i_end < rowlen) {
+        while (p[i_end] == 0x20 && i_end < rowlen) i_end++;
+        i_start = i_end;
+        while (p[i_end] != 0x20 && p[i_end] != 0x3a && i_end < rowlen) i_end++;
+        const size_t first_end = i_end;
+        while (p[i_end] != 0x20 && i_end < rowlen) i_end++;
+        if (p[i_start] == 0x7c) {
+            i_start++;
+            if (first_end != i_end) {
+                if (!rust_parse_f32(p, first_end + 1, i_end, &cur_w)) { err = "Failed parsing namespace weight: " + std::string(p + first_end + 1, i_end - first_end - 1); return -1; }
+            } else cur_w = 1.0f;
+            auto it = P.by_name.find(std::string(p + i_start, first_end - i_start));
+            if (it == P.by_name.end()) { err = "Feature name was not predeclared in vw_namespace_map.csv: " + std::string(p + i_start, first_end - i_start); return -1; }
+            cur_seed = it->second.seed;
+            cur_off = it->second.index + HEADER_LEN;
+            cur_f32 = it->second.f32;
+            cur_n = 0;
+            ns_start = olen;
+        } else {
+            const uint32_t h = murmur3_32(p + i_start, first_end - i_start, cur_seed) & MASK31;
+            float fw = 1.0f;
+            if (first_end != i_end && !rust_parse_f32(p, first_end + 1, i_end, &fw)) { err = "Failed parsing feature weight: " + std::string(p + first_end + 1, i_end - first_end - 1); return -1; }
+            if (cur_n == 0 && !cur_f32 && cur_w == 1.0f && fw == 1.0f) out[cur_off] = h;
+            else {
+                if (olen + 4 > cap) { err = "record too long"; return -1; }
+                const uint32_t prev = out[cur_off];
+                if (cur_n == 1 && (prev & IS_NOT_SINGLE_MASK) == 0) { out[olen++] = prev; out[olen++] = FLOAT32_ONE; }
+                out[olen++] = h;
+                if (cur_f32) {
+                    const size_t fs = i_start + P.vw.namespace_skip_prefix;
+                    float fv = NAN;
+                    if (first_end != fs) {
+                        if (fs > first_end || !rust_parse_f32(p, fs, first_end, &fv)) { err = "Failed parsing feature value to float (for float namespace): " + std::string(p + i_start, first_end - i_start); return -1; }
+                    }
+                    memcpy(&out[olen++], &fv, 4);
+                    if (cur_w * fw != 1.0f) { err = "Namespaces that are f32 can not have weight attached neither to namespace nor to a single feature (basically they can' use :weight syntax"; return -1; }
+                } else {
+                    const float v = cur_w * fw;
+                    memcpy(&out[olen++], &v, 4);
+                }
+                out[cur_off] = IS_NOT_SINGLE_MASK | (uint32_t)((ns_start << 16) + olen);
+            }
+            cur_n++;
+        }
+        i_end++;
+    }
+    out[0] = (uint32_t)olen;
+    return (int)olen;
+}
+
+// ---------------------------------------------------------------- files
+constexpr uint32_t CACHE_VERSION = 11, REGRESSOR_VERSION = 6; // cache.rs:12-13, persistence.rs:17-18
+
+struct RegReader { FILE *f = nullptr; std::string vwmap_json, mi_json; uint64_t weights_len = 0; };
+
+bool read_exact(FILE *f, void *dst, size_t n) { return fread(dst, 1, n, f) == n; }
+bool read_blob(FILE *f, std::string &out)
+{
+    uint64_t len = 0;
+    if (!read_exact(f, &len, 8) || len > (1ull << 32)) return false;
+    out.resize(len);
+    return len == 0 || read_exact(f, &out[0], len);
+}
+
+// ---------------------------------------------------------------- cmdline (cmdline.rs, model_instance.rs:296-495)
+struct Args {
+    std::map<std::string, std::vector<std::string>> multi;
+    bool has(const std::string &k) const { return multi.count(k) > 0; }
+    const std::string *one(const std::string &k) const { auto it = multi.find(k); return it == multi.end() || it->second.empty() ? nullptr : &it->second.back(); }
+};
+// flags that take a value / flags that do not (subset of cmdline.rs:9-322)
+const char *VALUE_FLAGS[] = {"data", "predictions", "final_regressor", "initial_regressor", "keep", "interactions", "linear", "ffm_field", "ffm_field_verbose",
+                             "ffm_k", "ffm_bit_precision", "bit_precision", "learning_rate", "ffm_learning_rate", "nn_learning_rate", "power_t", "ffm_power_t", "nn_power_t",
+                             "init_acc_gradient", "ffm_init_acc_gradient", "nn_init_acc_gradient", "ffm_init_center", "ffm_init_width", "ffm_init_zero_band",
+                             "ffm_initialization_type", "minimum_learning_rate", "link", "loss_function", "l2", "hash", "nn_layers", "nn_topology", "nn",
+                             "predictions_after", "holdout_after", "hogwild_threads", "convert_inference_regressor", "transform", "prediction_model_delay",
+                             "batch_size", "device", nullptr};
+const char *BOOL_FLAGS[] = {"cache", "testonly", "save_resume", "adaptive", "sgd", "noconstant", "vwcompat", "hogwild_training", "quiet", "predictions_stdout",
+                            "build_cache_without_training", "sequential", "invariant", "normalized", nullptr};
+const std::pair<const char *, const char *> SHORT_FLAGS[] = {{"d", "data"}, {"p", "predictions"}, {"f", "final_regressor"}, {"i", "initial_regressor"}, {"b", "bit_precision"},
+                                                             {"l", "learning_rate"}, {"c", "cache"}, {"t", "testonly"}, {"q", "interactions"}};
+
+bool in_list(const char **l, const std::string &s) { for (; *l; l++) if (s == *l) return true; return false; }
+
+Args parse_args(int argc, const char *const *argv)
+{
+    Args a;
+    for (int i = 0; i < argc; i++) {
+        std::string t = argv[i], name;
+        if (t.rfind("--", 0) == 0) name = t.substr(2);
+        else if (t.size() == 2 && t[0] == '-') { for (auto &sf : SHORT_FLAGS) if (t[1] == sf.first[0]) name = sf.second; if (name.empty()) throw std::runtime_error("Found argument '" + t + "' which wasn't expected"); }
+        else throw std::runtime_error("Found argument '" + t + "' which wasn't expected, or isn't valid in this context");
+        std::string inline_val;
+        size_t eq = name.find('=');
+        if (eq != std::string::npos) { inline_val = name.substr(eq + 1); name = name.substr(0, eq); }
+        if (in_list(BOOL_FLAGS, name)) a.multi[name];
+        else if (in_list(VALUE_FLAGS, name)) {
+            if (eq != std::string::npos) a.multi[name].push_back(inline_val);
+            else { if (i + 1 >= argc) throw std::runtime_error("The argument '--" + name + "' requires a value but none was supplied"); a.multi[name].push_back(argv[++i]); }
+        } else throw std::runtime_error("Found argument '--" + name + "' which wasn't expected, or isn't valid in this context");
+    }
+    return a;
+}
+
+NsDesc ns_by_char(const VwMap &vw, char c)
+{
+    const VwEntry *e = vw.by_vwname(std::string(1, c));
+    if (!e) throw std::runtime_error(std::string("Unknown namespace char in command line: ") + c);
+    return NsDesc{e->index, e->f32};
+}
+NsDesc ns_by_verbose(const VwMap &vw, const std::string &s)
+{
+    const VwEntry *e = vw.by_verbose(s);
+    if (!e) throw std::runtime_error("Unknown verbose namespace in command line: " + s);
+    return NsDesc{e->index, e->f32};
+}
+float parse_float(const Args &a, const char *k, float dflt) { const std::string *v = a.one(k); return v ? strtof(v->c_str(), nullptr) : dflt; }
+
+ModelInstanceH mi_from_args(const Args &a, const VwMap &vw)
+{
+    ModelInstanceH mi;
+    const bool vwcompat = a.has("vwcompat");
+    if (vwcompat) {
+        mi.fastmath = false;
+        mi.init_acc_gradient = 0.0f;
+        if (!a.has("keep")) throw std::runtime_error("--vwcompat requires at least one --keep parameter, we do not implicitly take all features available");
+        const std::string *h = a.one("hash");
+        if (!h || *h != "all") throw std::runtime_error("--vwcompat requires use of --hash all");
+        if (!a.has("sgd")) throw std::runtime_error("--vwcompat requires use of --sgd");
+    }
+    if (a.has("transform")) throw std::runtime_error("--transform namespaces are out of scope for the GPU path (feature_transform_*.rs)");
+    auto combo_from_chars = [&](const std::string &s) {
+        ComboDesc c;
+        std::string names = s;
+        size_t colon = s.find(':');
+        if (colon != std::string::npos) {
+            if (s.find(':', colon + 1) != std::string::npos) throw std::runtime_error("only one value parameter allowed (denoted with \":\"): \"" + s + "\"");
+            c.weight = strtof(s.substr(colon + 1).c_str(), nullptr);
+            names = s.substr(0, colon);
+        }
+        for (char ch : names) c.ns.push_back(ns_by_char(vw, ch));
+        return c;
+    };
+    if (a.has("keep")) for (auto &s : a.multi.at("keep")) mi.feature_combo_descs.push_back(combo_from_chars(s));
+    if (a.has("interactions")) for (auto &s : a.multi.at("interactions")) mi.feature_combo_descs.push_back(combo_from_chars(s));
+    if (a.has("linear")) for (auto &s : a.multi.at("linear")) {
+        ComboDesc c;
+        std::string names = s;
+        size_t colon = s.find(':');
+        if (colon != std::string::npos) {
+            if (s.find(':', colon + 1) != std::string::npos) throw std::runtime_error("Verbose features cannot have \":\" as part of their names: \"" + s + "\"");
+            c.weight = strtof(s.substr(colon + 1).c_str(), nullptr);
+            names = s.substr(0, colon);
+        }
+        size_t p0 = 0;
+        for (;;) { size_t cm = names.find(',', p0); c.ns.push_back(ns_by_verbose(vw, names.substr(p0, cm == std::string::npos ? std::string::npos : cm - p0))); if (cm == std::string::npos) break; p0 = cm + 1; }
+        mi.feature_combo_descs.push_back(c);
+    }
+    if (const std::string *v = a.one("ffm_k")) { mi.ffm_k = (uint32_t)strtoul(v->c_str(), nullptr, 10); if (mi.ffm_k > 128) throw std::runtime_error("Maximum ffm_k is: 128, passed: " + *v); }
+    if (const std::string *v = a.one("ffm_initialization_type")) mi.ffm_initialization_type = *v;
+    mi.ffm_init_center = parse_float(a, "ffm_init_center", mi.ffm_init_center);
+    mi.ffm_init_width = parse_float(a, "ffm_init_width", mi.ffm_init_width);
+    mi.ffm_init_zero_band = parse_float(a, "ffm_init_zero_band", mi.ffm_init_zero_band);
+    if (a.has("ffm_field")) for (auto &s : a.multi.at("ffm_field")) { std::vector<NsDesc> f; for (char ch : s) f.push_back(ns_by_char(vw, ch)); mi.ffm_fields.push_back(f); }
+    if (a.has("ffm_field_verbose")) for (auto &s : a.multi.at("ffm_field_verbose")) {
+        if (s.find(':') != std::string::npos) throw std::runtime_error("Fields currently do not support passing a value via : \"" + s + "\"");
+        std::vector<NsDesc> f;
+        size_t p0 = 0;
+        for (;;) { size_t cm = s.find(',', p0); f.push_back(ns_by_verbose(vw, s.substr(p0, cm == std::string::npos ? std::string::npos : cm - p0))); if (cm == std::string::npos) break; p0 = cm + 1; }
+        mi.ffm_fields.push_back(f);
+    }
+    if (const std::string *v = a.one("ffm_bit_precision")) mi.ffm_bit_precision = (uint32_t)strtoul(v->c_str(), nullptr, 10);
+    if (const std::string *v = a.one("bit_precision")) mi.bit_precision = (uint32_t)strtoul(v->c_str(), nullptr, 10);
+    mi.learning_rate = parse_float(a, "learning_rate", mi.learning_rate);
+    mi.init_acc_gradient = parse_float(a, "init_acc_gradient", mi.init_acc_gradient);
+    mi.power_t = parse_float(a, "power_t", mi.power_t);
+    mi.ffm_learning_rate = parse_float(a, "ffm_learning_rate", mi.learning_rate);         // defaults chain like model_instance.rs:418-428
+    mi.ffm_init_acc_gradient = parse_float(a, "ffm_init_acc_gradient", mi.init_acc_gradient);
+    mi.ffm_power_t = parse_float(a, "ffm_power_t", mi.power_t);
+    mi.nn_learning_rate = parse_float(a, "nn_learning_rate", mi.ffm_learning_rate);
+    mi.nn_init_acc_gradient = parse_float(a, "nn_init_acc_gradient", mi.ffm_init_acc_gradient);
+    mi.nn_power_t = parse_float(a, "nn_power_t", mi.ffm_power_t);
+    if (const std::string *v = a.one("nn_layers")) mi.nn_layers.resize(strtoul(v->c_str(), nullptr, 10));
+    if (const std::string *v = a.one("nn_topology")) mi.nn_topology = *v;
+    if (a.has("nn")) for (auto &s : a.multi.at("nn")) {
+        size_t c1 = s.find(':'), c2 = c1 == std::string::npos ? c1 : s.find(':', c1 + 1);
+        if (c1 == std::string::npos || c2 == std::string::npos || s.find(':', c2 + 1) != std::string::npos) throw std::runtime_error("--nn parameters have to be of form layer:parameter_name:parameter_value: " + s);
+        size_t layer = strtoul(s.substr(0, c1).c_str(), nullptr, 10);
+        if (layer >= mi.nn_layers.size()) throw std::runtime_error("--nn parameter addressing layer " + std::to_string(layer) + ", but we have only " + std::to_string(mi.nn_layers.size()) + " layers");
+        mi.nn_layers[layer].emplace_back(s.substr(c1 + 1, c2 - c1 - 1), s.substr(c2 + 1));
+    }
+    if (const std::string *v = a.one("minimum_learning_rate")) mi.minimum_learning_rate = strtof(v->c_str(), nullptr);
+    if (const std::string *v = a.one("link")) if (*v != "logistic") throw std::runtime_error("--link only supports 'logistic'");
+    if (const std::string *v = a.one("loss_function")) if (*v != "logistic") throw std::runtime_error("--loss_function only supports 'logistic'");
+    if (const std::string *v = a.one("l2")) if (std::fabs(strtof(v->c_str(), nullptr)) > 0.00000001f) throw std::runtime_error("--l2 can only be 0.0");
+    if (a.has("noconstant")) mi.add_constant_feature = false;
+    if (a.has("sgd")) mi.optimizer = FWGPU_OPT_SGD;
+    if (a.has("adaptive")) mi.optimizer = FWGPU_OPT_ADAGRAD_FLEX;
+    if (mi.optimizer == FWGPU_OPT_ADAGRAD_FLEX && mi.fastmath) mi.optimizer = FWGPU_OPT_ADAGRAD_LUT;
+    return mi;
+}
+
+} // namespace
+
+// ================================================================ C ABI
+extern "C" {
+
+void fwhost_free(void *p) { free(p); }
+
+char *fwhost_vwmap_csv_to_json(const char *csv, char *err, size_t errcap)
+{
+    try { return dup_string(json_to_string(vwmap_to_json(vwmap_from_csv(csv)))); }
+    catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+
+char *fwhost_model_instance_from_cmdline(int argc, const char *const *argv, const char *vwmap_json, char *err, size_t errcap)
+{
+    try {
+        VwMap vw = vwmap_from_json(json_parse(vwmap_json));
+        return dup_string(json_to_string(mi_to_json(mi_from_args(parse_args(argc, argv), vw))));
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+
+char *fwhost_model_instance_normalize(const char *mi_json, char *err, size_t errcap)
+{
+    try { return dup_string(json_to_string(mi_to_json(mi_from_json(json_parse(mi_json))))); }
+    catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+
+// update_hyperparameters_from_cmd (model_instance.rs:497-550): -l / --ffm_learning_rate / --power_t / --ffm_power_t override a loaded model
+char *fwhost_model_instance_update_from_cmdline(const char *mi_json, int argc, const char *const *argv, char *err, size_t errcap)
+{
+    try {
+        ModelInstanceH mi = mi_from_json(json_parse(mi_json));
+        Args a = parse_args(argc, argv);
+        if (const std::string *v = a.one("learning_rate")) mi.learning_rate = strtof(v->c_str(), nullptr);
+        if (const std::string *v = a.one("ffm_learning_rate")) mi.ffm_learning_rate = strtof(v->c_str(), nullptr);
+        if (const std::string *v = a.one("power_t")) mi.power_t = strtof(v->c_str(), nullptr);
+        if (const std::string *v = a.one("ffm_power_t")) mi.ffm_power_t = strtof(v->c_str(), nullptr);
+        return dup_string(json_to_string(mi_to_json(mi)));
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+
+// ---- parser
+void *fwhost_parser_new(const char *vwmap_json, char *err, size_t errcap)
+{
+    try {
+        Parser *P = new Parser();
+        P->vw = vwmap_from_json(json_parse(vwmap_json));
+        P->n_ns = P->vw.num_namespaces;
+        for (auto &e : P->vw.entries) P->by_name[e.vwname] = NsInfo{e.index, murmur3_32(e.vwname.data(), e.vwname.size(), 0), e.f32}; // parser.rs:82-83
+        return P;
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
+}
+void fwhost_parser_free(void *p) { delete (Parser *)p; }
+
+int fwhost_parser_parse_line(void *parser, const char *line, size_t len, uint32_t *out, size_t cap, char *err, size_t errcap)
+{
+    std::string e;
+    int n = parse_line(*(Parser *)parser, line, len, out, cap, e);
+    if (n == -1) set_err(err, errcap, e);
+    return n;
+}
+
+// Whole buffer -> records back to back + offsets.  Lines are split first, then parsed by n_threads workers into
+// per-thread slabs that are concatenated in order (the reference parses on one thread, main.rs:213-239).
+int64_t fwhost_parser_parse_text(void *parser, const char *text, size_t len, uint32_t *out, uint64_t cap_words, uint32_t *rec_off, uint64_t cap_examples,
+                                 int n_threads, uint64_t *n_words_out, char *err, size_t errcap)
+{
+    const Parser &P = *(Parser *)parser;
+    std::vector<std::pair<size_t, size_t>> lines;
+    for (size_t pos = 0; pos < len;) {
+        const char *nl = (const char *)memchr(text + pos, '\n', len - pos);
+        size_t end = nl ? (size_t)(nl - text) + 1 : len;
+        lines.emplace_back(pos, end - pos);
+        pos = end;
+    }
+    if (lines.size() > cap_examples) { set_err(err, errcap, "rec_off capacity too small"); return -1; }
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = n_threads > 0 ? n_threads : (int)(hw ? hw : 1);
+    nt = (int)std::min<size_t>((size_t)nt, std::max<size_t>(1, lines.size() / 1024));
+    std::vector<std::vector<uint32_t>> slabs(nt), lens(nt);
+    std::vector<std::string> errs(nt);
+    std::vector<int64_t> bad(nt, -1);
+    size_t per = (lines.size() + nt - 1) / nt;
+    auto work = [&](int t) {
+        size_t a = std::min(lines.size(), (size_t)t * per), b = std::min(lines.size(), a + per);
+        std::vector<uint32_t> tmp(1 << 16);
+        for (size_t i = a; i < b; i++) {
+            const char *lp = text + lines[i].first;
+            size_t ll = lines[i].second;
+            std::string e;
+            // a last line without '\n' is parsed as the reference would see it after read_until(): pad a newline
+            std::string padded;
+            if (lp[ll - 1] != '\n') { padded.assign(lp, ll); padded.push_back('\n'); lp = padded.data(); ll = padded.size(); }
+            int n = parse_line(P, lp, ll, tmp.data(), tmp.size(), e);
+            if (n < 0) { bad[t] = (int64_t)i; errs[t] = n == -2 ? "flush command inside a data file" : n == -3 ? "hogwild_load command inside a data file" : e; return; }
+            if (n == 0) continue;
+            slabs[t].insert(slabs[t].end(), tmp.begin(), tmp.begin() + n);
+            lens[t].push_back((uint32_t)n);
+        }
+    };
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+    for (int t = 0; t < nt; t++) if (bad[t] >= 0) { set_err(err, errcap, errs[t] + " (line " + std::to_string(bad[t] + 1) + ")"); return -1; }
+    uint64_t words = 0, n = 0;
+    for (int t = 0; t < nt; t++) {
+        if (words + slabs[t].size() > cap_words) { set_err(err, errcap, "record buffer too small"); return -1; }
+        if (!slabs[t].empty()) memcpy(out + words, slabs[t].data(), slabs[t].size() * 4);
+        uint64_t w = words;
+        for (uint32_t l : lens[t]) { rec_off[n++] = (uint32_t)w; w += l; }
+        words += slabs[t].size();
+    }
+    rec_off[n] = (uint32_t)words;
+    if (n_words_out) *n_words_out = words;
+    return (int64_t)n;
+}
+
+// ---- .fwcache (cache.rs:12-26, 133-161, 187-232); uncompressed variant only (LZ4 applies to *.gz inputs, cache.rs:71)
+int fwhost_cache_write(const char *path, const char *vwmap_json, const uint32_t *records, uint64_t n_words, char *err, size_t errcap)
+{
+    try {
+        std::string blob = json_to_string(vwmap_to_json(vwmap_from_json(json_parse(vwmap_json))));
+        std::string tmp = std::string(path) + ".writing"; // cache.rs:69-70, 147-153: write then rename
+        FILE *f = fopen(tmp.c_str(), "wb");
+        if (!f) throw std::runtime_error("cannot create " + tmp);
+        uint64_t len = blob.size();
+        bool ok = fwrite("FWCA", 1, 4, f) == 4 && fwrite(&CACHE_VERSION, 4, 1, f) == 1 && fwrite(&len, 8, 1, f) == 1 && fwrite(blob.data(), 1, len, f) == len &&
+                  (n_words == 0 || fwrite(records, 4, n_words, f) == n_words);
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) throw std::runtime_error("write failed");
+        if (rename(tmp.c_str(), path)) throw std::runtime_error("rename failed");
+        return 0;
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+int64_t fwhost_cache_read(const char *path, const char *expect_vwmap_json, uint32_t **records_out, uint64_t *n_words_out, uint32_t **rec_off_out,
+                          char **vwmap_json_out, char *err, size_t errcap)
+{
+    FILE *f = nullptr;
+    try {
+        f = fopen(path, "rb");
+        if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+        char magic[4];
+        uint32_t version = 0;
+        if (!read_exact(f, magic, 4) || memcmp(magic, "FWCA", 4)) throw std::runtime_error("Cache header does not begin with magic bytes FWFW"); // sic, cache.rs:167
+        if (!read_exact(f, &version, 4) || version != CACHE_VERSION) throw std::runtime_error("Cache file version of this binary: 11, version of the cache file: " + std::to_string(version));
+        std::string blob;
+        if (!read_blob(f, blob)) throw std::runtime_error("truncated cache header");
+        VwMap in_file = vwmap_from_json(json_parse(blob));
+        if (expect_vwmap_json && !(in_file == vwmap_from_json(json_parse(expect_vwmap_json)))) throw std::runtime_error("vw_namespace_map.csv and the one from cache file differ");
+        long start = ftell(f);
+        fseek(f, 0, SEEK_END);
+        long end = ftell(f);
+        fseek(f, start, SEEK_SET);
+        uint64_t n_words = (uint64_t)(end - start) / 4;
+        uint32_t *recs = (uint32_t *)malloc(std::max<uint64_t>(n_words, 1) * 4);
+        if (n_words && !read_exact(f, recs, n_words * 4)) { free(recs); throw std::runtime_error("short read"); }
+        fclose(f);
+        f = nullptr;
+        std::vector<uint32_t> offs;
+        uint64_t w = 0;
+        while (w < n_words) {
+            uint32_t l = recs[w];
+            if (l < HEADER_LEN || w + l > n_words) { free(recs); throw std::runtime_error("corrupt record length in cache"); }
+            offs.push_back((uint32_t)w);
+            w += l;
+        }
+        offs.push_back((uint32_t)w);
+        uint32_t *ro = (uint32_t *)malloc(offs.size() * 4);
+        memcpy(ro, offs.data(), offs.size() * 4);
+        *records_out = recs; *n_words_out = n_words; *rec_off_out = ro;
+        if (vwmap_json_out) *vwmap_json_out = dup_string(blob);
+        return (int64_t)offs.size() - 1;
+    } catch (const std::exception &e) {
+        if (f) fclose(f);
+        set_err(err, errcap, e.what());
+        return -1;
+    }
+}
+
+// ---- regressor file (persistence.rs:55-97; regressor.rs:426-442)
+int fwhost_regressor_write(const char *path, const char *vwmap_json, const char *mi_json, uint64_t total_weights, const void *const *blocks,
+                           const uint64_t *block_bytes, uint32_t n_blocks, char *err, size_t errcap)
+{
+    try {
+        std::string vb = json_to_string(vwmap_to_json(vwmap_from_json(json_parse(vwmap_json))));
+        std::string mb = json_to_string(mi_to_json(mi_from_json(json_parse(mi_json))));
+        FILE *f = fopen(path, "wb");
+        if (!f) throw std::runtime_error(std::string("Cannot open ") + path + " to save regressor to");
+        uint64_t l1 = vb.size(), l2 = mb.size();
+        bool ok = fwrite("FWRE", 1, 4, f) == 4 && fwrite(&REGRESSOR_VERSION, 4, 1, f) == 1 && fwrite(&l1, 8, 1, f) == 1 && fwrite(vb.data(), 1, l1, f) == l1 &&
+                  fwrite(&l2, 8, 1, f) == 1 && fwrite(mb.data(), 1, l2, f) == l2 && fwrite(&total_weights, 8, 1, f) == 1;
+        for (uint32_t i = 0; ok && i < n_blocks; i++) ok = block_bytes[i] == 0 || fwrite(blocks[i], 1, block_bytes[i], f) == block_bytes[i];
+        ok = (fclose(f) == 0) && ok;
+        if (!ok) throw std::runtime_error("write failed");
+        return 0;
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return -1; }
+}
+
+void *fwhost_regressor_open(const char *path, char *err, size_t errcap)
+{
+    RegReader *r = new RegReader();
+    try {
+        r->f = fopen(path, "rb");
+        if (!r->f) throw std::runtime_error(std::string("cannot open ") + path);
+        char magic[4];
+        uint32_t version = 0;
+        if (!read_exact(r->f, magic, 4) || memcmp(magic, "FWRE", 4)) throw std::runtime_error("Regressor header error: does not begin with magic bytes FWRE");
+        if (!read_exact(r->f, &version, 4) || version != REGRESSOR_VERSION) throw std::runtime_error("Regressor file version of this binary: 6, version of the regressor file: " + std::to_string(version));
+        if (!read_blob(r->f, r->vwmap_json) || !read_blob(r->f, r->mi_json) || !read_exact(r->f, &r->weights_len, 8)) throw std::runtime_error("truncated regressor header");
+        json_parse(r->vwmap_json);
+        json_parse(r->mi_json);
+        return r;
+    } catch (const std::exception &e) {
+        if (r->f) fclose(r->f);
+        delete r;
+        set_err(err, errcap, e.what());
+        return nullptr;
+    }
+}
+const char *fwhost_regressor_vwmap_json(void *r) { return ((RegReader *)r)->vwmap_json.c_str(); }
+const char *fwhost_regressor_mi_json(void *r) { return ((RegReader *)r)->mi_json.c_str(); }
+uint64_t fwhost_regressor_weights_len(void *r) { return ((RegReader *)r)->weights_len; }
+int fwhost_regressor_read(void *r, void *dst, uint64_t bytes) { return read_exact(((RegReader *)r)->f, dst, bytes) ? 0 : -1; }
+int fwhost_regressor_skip(void *r, uint64_t bytes) { return fseek(((RegReader *)r)->f, (long)bytes, SEEK_CUR) == 0 ? 0 : -1; }
+void fwhost_regressor_close(void *r) { RegReader *rr = (RegReader *)r; if (rr) { if (rr->f) fclose(rr->f); delete rr; } }
+
+// ModelInstance + vwmap JSON -> fwgpu_model_desc.  keep must be released with fwhost_model_desc_free.
+int fwhost_model_desc_from_json(const char *mi_json, const char *vwmap_json, int immutable, void *out_v, void **keep, char *err, size_t errcap)
+{
+    fwgpu_model_desc *out = (fwgpu_model_desc *)out_v;
+    try {
+        ModelInstanceH mi = mi_from_json(json_parse(mi_json));
+        VwMap vw = vwmap_from_json(json_parse(vwmap_json));
+        FlatDesc *f = new FlatDesc();
+        mi_to_desc(mi, vw, immutable != 0, *f);
+        *out = f->d;
+        *keep = f;
+        return 0;
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return -1; }
+}
+void fwhost_model_desc_free(void *keep) { delete (FlatDesc *)keep; }
+
+} // extern "C"

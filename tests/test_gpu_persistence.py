@@ -1,0 +1,108 @@
+"""Regressor files on the GPU path: the reference's save/load tests (persistence.rs:250-421) through
+host.save_regressor_to_filename / new_regressor_from_filename, and interchange with the oracle's tables."""
+import json
+
+import numpy as np
+import pytest
+
+import fwumious_wabbit_b200 as fw
+from fwumious_wabbit_b200 import FeatureBuffer, HashAndValue, HashAndValueAndSeq, ModelInstance, Optimizer, _lib, host, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def close(a, b, tol=1e-5):
+    assert abs(float(a) - float(b)) <= tol, (float(a), float(b))
+
+
+VW = "A,featureA\nB,featureB\n"
+
+
+def test_save_load_and_test_mode_lr(tmp_path):  # persistence.rs:250-313
+    vw = host.VwNamespaceMap.new(VW)
+    mi = ModelInstance.new_empty()
+    mi.learning_rate, mi.power_t, mi.bit_precision, mi.optimizer, mi.init_acc_gradient = 0.1, 0.5, 18, Optimizer.AdagradFlex, 0.0
+    mi.num_namespaces = 2
+    re = fw.Regressor(mi)
+    fbuf = FeatureBuffer(label=0.0, lr_buffer=[HashAndValue(1, 1.0, 0), HashAndValue(2, 1.0, 0)])
+    close(re.learn(fbuf, True), 0.5)
+    close(re.learn(fbuf, True), 0.45016602)
+    close(re.learn(fbuf, False), 0.41731137)
+    path = str(tmp_path / "test_regressor2.fw")
+    host.save_regressor_to_filename(path, mi, vw, re)
+    mi2, vw2, re2 = host.new_regressor_from_filename(path, immutable=False)
+    assert mi2.optimizer == Optimizer.AdagradFlex and vw2.source == vw.source
+    close(re2.learn(fbuf, False), 0.41731137)
+    close(re2.predict(fbuf), 0.41731137)
+    assert np.array_equal(re2.get_lr_table(), re.get_lr_table())       # weights AND accumulators came back
+    close(re2.learn(fbuf, True), 0.41731137)                           # training resumes from the saved state (--save_resume)
+    mi3, _, re3 = host.new_regressor_from_filename(path, immutable=True)
+    assert re3.get_name() == 'Regressor with optimizer "SGD"'
+    close(re3.predict(fbuf), 0.41731137)
+    with pytest.raises(_lib.FwgpuError):
+        re3.learn(fbuf, True)
+    # -l / --power_t on the command line override the stored hyper-parameters (model_instance.rs:497-550)
+    mi4, _, _ = host.new_regressor_from_filename(path, immutable=False, cmd_arguments=["-l", "0.25", "--ffm_power_t", "0.3"])
+    assert mi4.learning_rate == 0.25 and abs(mi4.ffm_power_t - 0.3) < 1e-7 and abs(mi4.power_t - 0.5) < 1e-7
+
+
+def test_save_load_and_test_mode_ffm_and_inference_file(tmp_path):  # persistence.rs:341-421 + main.rs:136-149
+    vw = host.VwNamespaceMap.new(VW)
+    mi = ModelInstance.new_empty()
+    mi.learning_rate, mi.power_t, mi.bit_precision = 0.1, 0.0, 18
+    mi.ffm_k, mi.ffm_bit_precision, mi.ffm_power_t, mi.ffm_learning_rate = 1, 18, 0.0, 0.1
+    mi.ffm_fields, mi.optimizer, mi.num_namespaces = [[], []], Optimizer.AdagradFlex, 2
+    re = fw.Regressor(mi)
+    n, _ = re.block_len(_lib.BLOCK_FFM)
+    re.set_ffm(np.ones(n, np.float32), np.zeros(n, np.float32))
+    fbuf = FeatureBuffer(label=0.0, ffm_buffer=[HashAndValueAndSeq(1, 1.0, 0), HashAndValueAndSeq(3000, 1.0, 0), HashAndValueAndSeq(100, 2.0, 1)])
+    close(re.learn(fbuf, True), 0.9933072)
+    close(re.learn(fbuf, False), 0.9395168)
+    path = str(tmp_path / "m.fw")
+    host.save_regressor_to_filename(path, mi, vw, re)
+    _, _, re2 = host.new_regressor_from_filename(path, False)
+    assert re2.get_name() == 'Regressor with optimizer "AdagradFlex"'
+    close(re2.learn(fbuf, False), 0.9395168)
+    close(re2.predict(fbuf), 0.9395168)
+    _, _, re3 = host.new_regressor_from_filename(path, True)
+    assert re3.get_name() == 'Regressor with optimizer "SGD"'
+    close(re3.predict(fbuf), 0.9395168)
+    # --convert_inference_regressor: write the immutable regressor (weights only), reload, same predictions
+    # (the assertion of examples/ffm/run_fw_with_prediction_tests.sh:130-137)
+    inf = str(tmp_path / "inference.fw")
+    host.save_regressor_to_filename(inf, mi, vw, re3)
+    full_size, inf_size = (tmp_path / "m.fw").stat().st_size, (tmp_path / "inference.fw").stat().st_size
+    assert inf_size < full_size * 0.6
+    mi5, _, re5 = host.new_regressor_from_filename(inf, True)
+    assert mi5.optimizer == Optimizer.SGD
+    close(re5.predict(fbuf), 0.9395168)
+
+
+def test_file_interchange_with_oracle_tables(tmp_path):
+    """A model trained on the GPU, saved, and its payload loaded into the CPU oracle predicts the same (and the other
+    way round): the block byte layouts are the reference's (block_helpers.rs:23-28, block_ffm.rs:835-848)."""
+    w = synth.workload("c2")
+    vw = host.VwNamespaceMap.new("".join(f"{c},feature{c}\n" for c in w.ns_names))
+    recs = w.records(50_000)
+    re = fw.Regressor(w.mi)
+    re.learn_records(recs.reshape(-1), n_examples=50_000, update=True)
+    path = str(tmp_path / "c2.fw")
+    host.save_regressor_to_filename(path, w.mi, vw, re)
+    raw = open(path, "rb").read()
+    l1 = int.from_bytes(raw[8:16], "little")
+    l2 = int.from_bytes(raw[16 + l1:24 + l1], "little")
+    body = 24 + l1 + l2
+    assert int.from_bytes(raw[body:body + 8], "little") == (1 << 18) + (1 << 20) + 32
+    payload = np.frombuffer(raw, dtype=np.float32, offset=body + 8)
+    ora = util.oracle_regressor(w.mi)
+    n_lr, n_f = 1 << 18, (1 << 20) + 32
+    ora.lr_table[:] = payload[: 2 * n_lr].reshape(n_lr, 2)
+    ora.ffm_weights[:] = payload[2 * n_lr: 2 * n_lr + n_f]
+    ora.ffm_acc[:] = payload[2 * n_lr + n_f: 2 * n_lr + 2 * n_f]
+    m = 3000
+    d = util.oracle_translate_batch(util.oracle_spec(w.mi), recs[:m], fixed_len=w.record_len)
+    want = ora.learn_batch(d, update=False)
+    _, _, re2 = host.new_regressor_from_filename(path, True)
+    got = re2.learn_records(recs[:m].reshape(-1), n_examples=m, update=False)
+    assert np.max(np.abs(got - want)) <= 1e-5

@@ -1,0 +1,12 @@
+#!/bin/bash
+mkdir -p gpurun_out
+(timeout 600 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_exp4.txt 2>&1); grep -E "^FAILED|passed|failed" gpurun_out/pytest_gpu_exp4.txt | head
+summ() { python -c "
+import sys,json
+d=json.loads(open(sys.argv[1]).read()); r=d['roofline']
+print(sys.argv[2], 'value %.1fM ex/s'%(d['value']/1e6), ('e2e %.1fM'%(d['e2e']['value']/1e6)) if d.get('e2e') else '', 'frac %.3f'%r['frac'], 'launch ms %.3f'%r['avg_launch_ms'], 'll', d['e2e']['last_step_logloss'] if d.get('e2e') else None)
+" $1 "$2" 2>&1 | tail -1; }
+timeout 300 python bench.py --workload c3 --steps 3 --warmup 2 --no-cpu-baseline > gpurun_out/exp4_c3.json 2> gpurun_out/exp4_c3.err; summ gpurun_out/exp4_c3.json "c3"; tail -2 gpurun_out/exp4_c3.err
+FWGPU_MINB=3 timeout 300 python bench.py --workload c3 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/exp4_c3m3.json 2> gpurun_out/exp4_c3.err; summ gpurun_out/exp4_c3m3.json "c3 minb3"
+FWGPU_SIMPLE_UPDATE=0 timeout 300 python bench.py --workload c3 --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/exp4_c3b.json 2> gpurun_out/exp4_c3.err; summ gpurun_out/exp4_c3b.json "c3 batched"
+FWGPU_FAST=0 timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu-baseline --no-e2e > gpurun_out/exp4_c2g.json 2> gpurun_out/exp4_c2g.err; summ gpurun_out/exp4_c2g.json "c2 general kernel"
