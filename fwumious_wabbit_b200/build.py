@@ -7,6 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfwgpu.so")
+CLI_SRC = os.path.join(HERE, "cli", "fwgpu_main.cpp")
+CLI_OUT = os.path.join(HERE, "fwgpu")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -31,11 +33,13 @@ def deps():
     for root, _, files in os.walk(CSRC):
         out += [os.path.join(root, f) for f in files]
     out.append(os.path.join(os.path.dirname(HERE), "include", "fwgpu.h"))
+    out.append(os.path.join(os.path.dirname(HERE), "include", "fwhost.h"))
+    out.append(CLI_SRC)
     return out
 
 
 def up_to_date():
-    if not os.path.exists(OUT):
+    if not os.path.exists(OUT) or not os.path.exists(CLI_OUT):
         return False
     t = os.path.getmtime(OUT)
     return all(os.path.getmtime(d) <= t for d in deps())
@@ -55,6 +59,14 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
+    # the command-line front end (fwgpu): plain C++ against the two C ABIs, finds the library next to itself
+    cmd2 = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI_OUT, CLI_SRC, "-L" + HERE, "-lfwgpu", "-Wl,-rpath,$ORIGIN"]
+    res2 = subprocess.run(cmd2, capture_output=True, text=True)
+    with open(os.path.join(HERE, "build.log"), "a") as f:
+        f.write(" ".join(cmd2) + "\n" + res2.stdout + res2.stderr)
+    if res2.returncode != 0:
+        sys.stderr.write(res2.stdout + res2.stderr)
+        raise RuntimeError("building the fwgpu command-line front end failed")
     if verbose:
         print(log)
     return OUT

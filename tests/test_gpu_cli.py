@@ -1,0 +1,93 @@
+"""The reference's CI integration test (examples/ffm/run_fw_with_prediction_tests.sh) against the `fwgpu`
+command-line front end: same flags, same assertions -- inference-weights predictions equal full-weights predictions
+line by line, predictions are not constant, balanced accuracy on the unseen-combination ("hard") set > 0.80 --
+plus the cache path (-c) and --sequential."""
+import os
+import random
+import subprocess
+
+import numpy as np
+import pytest
+
+from fwumious_wabbit_b200 import build
+
+pytestmark = pytest.mark.gpu
+FW = os.path.join(os.path.dirname(build.OUT), "fwgpu")
+
+
+def get_score(a, b):  # examples/ffm/generate.py:12-20
+    return 1 if (a == "Herbivore" and b == "Plant") or (a == "Carnivore" and b == "Meat") else -1
+
+
+def generate(d, n_train=30000, n_eval=3000, num_animals=300, num_foods=200, block_beyond=100, seed=1):
+    """examples/ffm/generate.py:31-92: train / easy / hard (ids unseen together during training) sets."""
+    rnd = random.Random(seed)
+    open(os.path.join(d, "vw_namespace_map.csv"), "w").write("A,animal\nB,food\n")
+
+    def ex(person, movie):
+        a, b = rnd.choice(["Herbivore", "Carnivore"]), rnd.choice(["Plant", "Meat"])
+        return f"{get_score(a, b)} |A {a}-{person} |B {b}-{movie}\n"
+
+    with open(os.path.join(d, "train.vw"), "w") as f:
+        for _ in range(n_train):
+            if rnd.randint(0, 1):
+                f.write(ex(rnd.randint(0, num_animals), rnd.randint(0, block_beyond)))
+            else:
+                f.write(ex(rnd.randint(0, block_beyond), rnd.randint(0, num_foods)))
+    with open(os.path.join(d, "test-hard.vw"), "w") as f:
+        for _ in range(n_eval):
+            f.write(ex(rnd.randint(block_beyond + 1, num_animals), rnd.randint(block_beyond + 1, num_foods)))
+
+
+def run(args):
+    r = subprocess.run([FW] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    return r
+
+
+def labels_of(path):
+    return np.array([1.0 if l.split()[0] == "1" else 0.0 for l in open(path)])
+
+
+def balanced_accuracy(p, y, thr=0.5):
+    pred = p > thr
+    tpr = np.mean(pred[y == 1]) if np.any(y == 1) else 0.0
+    tnr = np.mean(~pred[y == 0]) if np.any(y == 0) else 0.0
+    return 0.5 * (tpr + tnr)
+
+
+@pytest.mark.parametrize("mode", ["hogwild", "sequential"])
+def test_reference_ffm_integration_script(tmp_path, mode):
+    d = str(tmp_path)
+    generate(d)
+    ns = "--keep A --keep B --interactions AB --ffm_k 10 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 -b 25 -c --sgd --loss_function logistic --link logistic --power_t 0.0 --l2 0.0 --hash all --noconstant".split()
+    extra = ["--sequential"] if mode == "sequential" else []
+    tr, full, inf = f"{d}/train.vw", f"{d}/full.fw", f"{d}/inference.fw"
+    run(ns + rest + extra + ["--data", tr, "-p", f"{d}/training.txt", "-f", full, "--save_resume"])
+    assert os.path.exists(tr + ".fwcache")                                   # -c wrote the cache (cache.rs:69-70)
+    run(ns + rest + ["-i", full, "--convert_inference_regressor", inf])
+    assert os.path.getsize(inf) < os.path.getsize(full)
+    run(ns + rest + ["-i", full, "--data", tr, "-p", f"{d}/eval_full.txt", "-t"])      # reads the cache this time
+    run(ns + rest + ["-i", inf, "-d", tr, "-t", "-p", f"{d}/eval_inf.txt"])
+    run(ns + rest + ["-i", inf, "-d", f"{d}/test-hard.vw", "-t", "-p", f"{d}/hard.txt"])
+    y = labels_of(tr)
+    p_train = np.loadtxt(f"{d}/training.txt")
+    p_full, p_inf = np.loadtxt(f"{d}/eval_full.txt"), np.loadtxt(f"{d}/eval_inf.txt")
+    assert len(p_train) == len(p_full) == len(p_inf) == len(y) == 30000
+    assert open(f"{d}/eval_full.txt").read() == open(f"{d}/eval_inf.txt").read()   # run_fw_with_prediction_tests.sh:130-137
+    assert len(np.unique(p_inf)) > 100                                             # :143-160 predictions are not constant
+    assert balanced_accuracy(p_full, y) > 0.95
+    hard = np.loadtxt(f"{d}/hard.txt")
+    assert balanced_accuracy(hard, labels_of(f"{d}/test-hard.vw")) > 0.80            # :56, :247-252
+
+
+def test_cli_flag_errors(tmp_path):
+    d = str(tmp_path)
+    generate(d, n_train=10, n_eval=2)
+    r = subprocess.run([FW, "--data", f"{d}/train.vw", "--keep", "A", "-f", f"{d}/m.fw"], capture_output=True, text=True)
+    assert r.returncode != 0 and "You need to use --save_resume with --final_regressor" in r.stderr   # main.rs:112-115
+    r = subprocess.run([FW, "--data", f"{d}/train.vw", "--keep", "Z"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Unknown namespace" in r.stderr
+    r = subprocess.run([FW, "--data", f"{d}/nothere/train.vw", "--keep", "A"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Could not find vw_namespace_map.csv" in r.stderr
