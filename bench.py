@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="examples in the cpu_baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--predict-only", action="store_true", help="diagnostic: time the forward pass only (update = 0)")
     ap.add_argument("--uniform-ids", action="store_true", help="diagnostic: uniform feature ids instead of Zipf (no hot rows)")
     return ap.parse_args()
 
@@ -197,6 +198,7 @@ def run_ours(args):
         return dist_util.max_over_ranks(x, dist, device="cuda")
 
     # ---------------- value: records resident in HBM ----------------
+    upd = not args.predict_only
     for _ in range(args.warmup):
         re.learn_dataset(ds, 0, n, update=True, sync=False)
     barrier()
@@ -209,7 +211,7 @@ def run_ours(args):
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        re.learn_dataset(ds, 0, n, update=True, sync=False)
+        re.learn_dataset(ds, 0, n, update=upd, sync=False)
     ev1.record(stream)
     barrier()
     sampler.stop_flag = True
@@ -275,7 +277,7 @@ def run_ours(args):
             "metric": "examples/sec FFM training", "value": value, "unit": "examples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{w.name}: {w.description}" + (" [DIAGNOSTIC: uniform ids]" if args.uniform_ids else ""), "examples_per_step_per_gpu": n,
+            "config": {"workload": f"{w.name}: {w.description}" + (" [DIAGNOSTIC: uniform ids]" if args.uniform_ids else "") + (" [DIAGNOSTIC: predict only]" if args.predict_only else ""), "examples_per_step_per_gpu": n,
                        "parallelism": f"replicas x{world} (independent models, disjoint example shards)" if world > 1 else "single GPU",
                        "l2_policy": f"inputs larger than L2: {nbytes >> 20} MiB of records per step; table ({(w.mi.ffm_k and ((1 << w.mi.ffm_bit_precision) * 8 >> 20))} MiB w+acc) is L2-resident by nature for c2",
                        "optimizer": "AdagradLUT", "semantics": "Hogwild on device, chunked launches"},

@@ -34,7 +34,7 @@ class ModelDesc(C.Structure):
         ("add_constant", C.c_uint32),
         ("field_off", u32p), ("field_ns", u32p),
         ("max_ffm_per_example", C.c_uint32), ("max_lr_per_example", C.c_uint32),
-        ("hogwild_ramp_div", C.c_uint32),
+        ("hogwild_ramp_div", C.c_uint32), ("hogwild_max_inflight", C.c_uint32),
     ]
 
 

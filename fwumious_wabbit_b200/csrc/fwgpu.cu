@@ -101,6 +101,7 @@ struct fwgpu_ctx {
     uint64_t launches = 0;
     uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
     uint32_t ramp_div = 32;
+    uint32_t max_inflight = 0; // 0 = unlimited
     bool ramp_finished = false;
     bool profiling = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[2];
@@ -298,6 +299,11 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     if (const char *t = getenv("FWGPU_MINB")) c->minb = atoi(t);
     c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 32;
     if (const char *t = getenv("FWGPU_RAMP_DIV")) c->ramp_div = (uint32_t)strtoul(t, nullptr, 10);
+    {
+        const bool constant_step = c->optimizer == FWGPU_OPT_SGD || d.power_t == 0.0f || (d.ffm_k > 0 && d.ffm_power_t == 0.0f);
+        c->max_inflight = d.hogwild_max_inflight ? d.hogwild_max_inflight : (constant_step ? 16u : 0u);
+        if (const char *t = getenv("FWGPU_MAX_INFLIGHT")) c->max_inflight = (uint32_t)strtoul(t, nullptr, 10);
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return FWGPU_OK;
 }
@@ -479,6 +485,7 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
             const uint64_t seg_end = std::max<uint64_t>(2 * seen, c->ramp_div);
             if (!n_examples_dev) cnt = (uint32_t)std::min<uint64_t>(cnt, seg_end - seen);
         }
+        if (update && c->max_inflight && (cap == 0 || cap > c->max_inflight)) cap = c->max_inflight;
         LearnParams q = p;
         q.meta = p.meta + done;   // ExMeta.out_index is absolute within the chunk, so preds is not offset
         q.n_examples = cnt;
@@ -680,6 +687,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(seen / c->ramp_div, 1), 1u << 30);
                 cnt = (uint32_t)std::min<uint64_t>(cnt, std::max<uint64_t>(2 * seen, c->ramp_div) - seen);
             }
+            if (update && c->max_inflight && (cap == 0 || cap > c->max_inflight)) cap = c->max_inflight;
             fp.ex_begin = done; fp.n_examples = cnt; fp.max_groups = cap;
             uint32_t full_groups = 0;
             cudaError_t e;

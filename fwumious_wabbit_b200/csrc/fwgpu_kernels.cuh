@@ -385,31 +385,6 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
         // regressor.rs:366-370: update && importance != 0; a zero gradient changes nothing
         const bool do_update = p.update && m.importance != 0.0f && g != 0.0f;
         if (do_update) {
-            // ---- LR update (block_lr.rs:135-151), first half: when every entry has its own thread and its hash is unique in
-            //      the example (the usual case) the accumulator atomic is issued now and consumed after the FFM loop, so
-            //      its L2 round trip hides behind the FFM atomics.  Anything else takes the ordered loop afterwards. ----
-            bool lr_pending = false, lr_slow = nlr > T;
-            float lr_old = 0.0f, lr_grad = 0.0f;
-            float *lr_cell = nullptr;
-            if (nlr <= T) {
-                bool dup = false;
-                uint4 e = make_uint4(0, 0, 0, 0);
-                if (tg < nlr) {
-                    e = __ldg(le + tg);
-                    if (lr_staged) { for (uint32_t j = 0; j < nlr; j++) if (j != tg && lrh[j] == e.x) { dup = true; break; } }
-                    else { for (uint32_t j = 0; j < nlr; j++) if (j != tg && __ldg(&le[j].x) == e.x) { dup = true; break; } }
-                    if (!dup) {
-                        lr_cell = reinterpret_cast<float *>(p.lr + e.x);
-                        lr_grad = __fmul_rn(g, __uint_as_float(e.y));
-                        if (p.optimizer == OPT_SGD) atomicAdd(lr_cell, -__fmul_rn(lr_grad, p.lr_lr));
-                        else { lr_old = atomicAdd(lr_cell + 1, __fmul_rn(lr_grad, lr_grad)); lr_pending = true; }
-                    }
-                }
-                // any duplicate anywhere in the group -> the ordered loop runs (group-uniform decision not needed: it only
-                // handles entries that are duplicates)
-                lr_slow = dup;
-                lr_slow = __any_sync(0xffffffffu, lr_slow);
-            }
             // ---- FFM update (block_ffm.rs:265-288): every d_out[f][z] equals g (triangle backward mirrors it) ----
             if (F > 0) {
                 auto update_chunk = [&](uint32_t e, uint32_t c) {
@@ -529,34 +504,28 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                     }
                 }
             }
-            // ---- LR update, second half: finish the accumulator atomics issued before the FFM loop; entries whose hash
-            //      occurs more than once in this example are applied in buffer order by the first occurrence's thread
-            //      (pinned by regressor.rs:629-656) ----
-            if (lr_pending) {
-                const float upd = opt_step(p.optimizer, lr_grad, acc_after(lr_old, lr_grad), p.lut_lr, p.lr_lr, p.lr_mpt);
-                atomicAdd(lr_cell, -upd);
-            }
-            if (lr_slow) {
-                for (uint32_t i = tg; i < nlr; i += T) {
-                    const uint4 e = __ldg(le + i);
-                    bool owner = true, dup = false;
-                    if (lr_staged) { for (uint32_t j = 0; j < nlr; j++) if (j != i && lrh[j] == e.x) { dup = true; if (j < i) owner = false; } }
-                    else { for (uint32_t j = 0; j < nlr; j++) if (j != i && __ldg(&le[j].x) == e.x) { dup = true; if (j < i) owner = false; } }
-                    if (!owner || (!dup && nlr <= T)) continue; // singles were handled by the fast half when every entry has its own thread
-                    float *cell = reinterpret_cast<float *>(p.lr + e.x);
-                    for (uint32_t j = i; j < nlr; j++) {
-                        const uint4 ej = (j == i) ? e : __ldg(le + j);
-                        if (ej.x != e.x) continue;
-                        const float grad = __fmul_rn(g, __uint_as_float(ej.y));
-                        float upd;
-                        if (p.optimizer == OPT_SGD) upd = __fmul_rn(grad, p.lr_lr);
-                        else {
-                            const float gg = __fmul_rn(grad, grad);
-                            const float old = atomicAdd(cell + 1, gg);
-                            upd = opt_step(p.optimizer, grad, acc_after(old, grad), p.lut_lr, p.lr_lr, p.lr_mpt);
-                        }
-                        atomicAdd(cell, -upd);
+            // ---- LR update (block_lr.rs:135-151); duplicates of one hash inside an example are applied
+            //      in buffer order by the first occurrence's thread (pinned by regressor.rs:629-656) ----
+            for (uint32_t i = tg; i < nlr; i += T) {
+                const uint4 e = __ldg(le + i);
+                bool owner = true;
+                if (lr_staged) { for (uint32_t j = 0; j < i; j++) if (lrh[j] == e.x) { owner = false; break; } }
+                else { for (uint32_t j = 0; j < i; j++) if (__ldg(&le[j].x) == e.x) { owner = false; break; } }
+                if (!owner) continue;
+                float *cell = reinterpret_cast<float *>(p.lr + e.x);
+                for (uint32_t j = i; j < nlr; j++) {
+                    if (lr_staged && j != i && lrh[j] != e.x) continue;
+                    const uint4 ej = (j == i) ? e : __ldg(le + j);
+                    if (ej.x != e.x) continue;
+                    const float grad = g * __uint_as_float(ej.y);
+                    float upd;
+                    if (p.optimizer == OPT_SGD) upd = grad * p.lr_lr;
+                    else {
+                        const float gg = __fmul_rn(grad, grad);
+                        const float old = atomicAdd(cell + 1, gg);
+                        upd = opt_step(p.optimizer, grad, acc_after(old, grad), p.lut_lr, p.lr_lr, p.lr_mpt);
                     }
+                    atomicAdd(cell, -upd);
                 }
             }
         }

@@ -54,6 +54,7 @@ class ModelInstance:
     max_ffm_per_example: int = 0
     max_lr_per_example: int = 0
     hogwild_ramp_div: int = 0  # 0 = default (32), 0xffffffff = no concurrency ramp
+    hogwild_max_inflight: int = 0  # 0 = automatic (16 for constant-step models, unlimited otherwise)
 
     @staticmethod
     def new_empty():
@@ -110,4 +111,5 @@ class ModelInstance:
         d.max_ffm_per_example = self.max_ffm_per_example
         d.max_lr_per_example = self.max_lr_per_example
         d.hogwild_ramp_div = self.hogwild_ramp_div
+        d.hogwild_max_inflight = self.hogwild_max_inflight
         return d, (is_f32, combo_off, combo_ns, combo_w, field_off, field_ns)

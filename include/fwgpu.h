@@ -86,6 +86,11 @@ typedef struct fwgpu_model_desc {
      * the cold-start of AdaGrad (accumulators at 0) from overshooting when thousands of examples
      * hit the same weights at once.  0 = default (32); 0xffffffff = no ramp.  DESIGN.md "semantics". */
     uint32_t hogwild_ramp_div;
+    /* Hard cap on examples in flight.  0 = automatic: unlimited for AdaGrad with power_t > 0 (the accumulators damp
+     * concurrent steps on a hot weight), 16 for constant-step models (SGD, or power_t == 0) -- the width of the
+     * reference's own Hogwild default (--hogwild_threads 16, main.rs:187-198): with a constant step, m examples in
+     * flight multiply the effective learning rate of a hot weight by m. */
+    uint32_t hogwild_max_inflight;
 } fwgpu_model_desc;
 
 /*

@@ -19,8 +19,9 @@ def get_score(a, b):  # examples/ffm/generate.py:12-20
     return 1 if (a == "Herbivore" and b == "Plant") or (a == "Carnivore" and b == "Meat") else -1
 
 
-def generate(d, n_train=30000, n_eval=3000, num_animals=300, num_foods=200, block_beyond=100, seed=1):
-    """examples/ffm/generate.py:31-92: train / easy / hard (ids unseen together during training) sets."""
+def generate(d, n_train=30000, n_eval=3000, num_animals=300, num_foods=200, block_beyond=3, seed=1):
+    """examples/ffm/generate.py:31-92 with the arguments of run_fw_with_prediction_tests.sh:48 (block_beyond keeps its default 3):
+    train pairs always involve one of the few "bridge" ids; the hard set pairs ids never seen together."""
     rnd = random.Random(seed)
     open(os.path.join(d, "vw_namespace_map.csv"), "w").write("A,animal\nB,food\n")
 
@@ -67,7 +68,7 @@ def test_reference_ffm_integration_script(tmp_path, mode):
     run(ns + rest + extra + ["--data", tr, "-p", f"{d}/training.txt", "-f", full, "--save_resume"])
     assert os.path.exists(tr + ".fwcache")                                   # -c wrote the cache (cache.rs:69-70)
     run(ns + rest + ["-i", full, "--convert_inference_regressor", inf])
-    assert os.path.getsize(inf) < os.path.getsize(full)
+    assert os.path.getsize(inf) <= os.path.getsize(full)  # equal here: --sgd models carry no accumulators
     run(ns + rest + ["-i", full, "--data", tr, "-p", f"{d}/eval_full.txt", "-t"])      # reads the cache this time
     run(ns + rest + ["-i", inf, "-d", tr, "-t", "-p", f"{d}/eval_inf.txt"])
     run(ns + rest + ["-i", inf, "-d", f"{d}/test-hard.vw", "-t", "-p", f"{d}/hard.txt"])
