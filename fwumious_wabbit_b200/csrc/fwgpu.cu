@@ -92,6 +92,8 @@ struct fwgpu_ctx {
     bool fast_ok = false;     // k_learn_fixed applies to this model (one namespace per field, k % 4 == 0, ...)
     bool fast_enabled = true; // FWGPU_FAST=0 turns the fused kernel off (measurement / debugging)
     uint32_t fast_nch = 1;
+    bool fast_cta = false;    // wide model: one block per record (k_learn_fixed_cta) instead of one warp
+    int fast_ub = 2;
     uint32_t *err_flag = nullptr;
     uint32_t *err_host = nullptr; // pinned
     int num_sms = 0;
@@ -287,10 +289,18 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     if ((st = upload_vec(c, c->field_off, &c->d_field_off))) return st;
     if ((st = upload_vec(c, c->field_ns, &c->d_field_ns))) return st;
     {
-        bool ok = (c->k % 4 == 0) && c->F <= 32 && c->n_field_refs == c->F && (c->d.n_combos + (c->d.add_constant ? 1u : 0u)) <= 64 && c->d.n_namespaces > 0;
-        for (uint32_t f = 0; ok && f < c->F; f++) ok = (c->field_off[f + 1] - c->field_off[f]) == 1;
+        const uint32_t n_lr_max = c->d.n_combos + (c->d.add_constant ? 1u : 0u);
+        bool base = (c->k % 4 == 0) && c->n_field_refs == c->F && c->d.n_namespaces > 0;
+        for (uint32_t f = 0; base && f < c->F; f++) base = (c->field_off[f + 1] - c->field_off[f]) == 1;
         const uint32_t n_chunks = c->F * (c->Fk / 4);
-        if (n_chunks > 128) ok = false;
+        bool ok = base && c->F <= 32 && n_lr_max <= 64 && n_chunks <= 128; // warp per record
+        if (base && !ok) {
+            // wide model: the block-per-record kernel, if a record's rows fit in shared memory at least twice per SM
+            const size_t smem_need = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 4 + 64;
+            c->fast_cta = c->F <= 256 && n_lr_max <= 256 && smem_need * 2 <= c->smem_optin;
+            ok = c->fast_cta;
+        }
+        if (const char *t = getenv("FWGPU_UB")) c->fast_ub = atoi(t);
         c->fast_ok = ok;
         c->fast_nch = n_chunks <= 32 ? 1 : n_chunks <= 64 ? 2 : n_chunks <= 96 ? 3 : 4;
         if (const char *t = getenv("FWGPU_FAST")) c->fast_enabled = atoi(t) != 0;
@@ -538,6 +548,28 @@ template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedPa
     return cudaGetLastError();
 }
 
+template <int UB> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
+{
+    auto kern = k_learn_fixed_cta<UB>;
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e0 != cudaSuccess) return e0;
+        configured = smem;
+    }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = std::min<uint32_t>(p.n_examples, (uint32_t)(c->num_sms * per_sm));
+    if (p.max_groups) grid = std::min<uint32_t>(grid, p.max_groups);
+    *full_groups = (uint32_t)(c->num_sms * per_sm);
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, 256, smem, c->stream>>>(p);
+    c->launches++;
+    return cudaGetLastError();
+}
+
 // ---- CSR batch entry --------------------------------------------------------------------------
 static fwgpu_status learn_batch_impl(fwgpu_ctx *c, const fwgpu_batch *b, float *preds_out, int update)
 {
@@ -691,7 +723,25 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
             fp.ex_begin = done; fp.n_examples = cnt; fp.max_groups = cap;
             uint32_t full_groups = 0;
             cudaError_t e;
-            {
+            if (c->fast_cta) {
+                FixedCtaParams cp{};
+                cp.lr = fp.lr; cp.ffm_w = fp.ffm_w; cp.ffm_acc = fp.ffm_acc; cp.lut_lr = fp.lut_lr; cp.lut_ffm = fp.lut_ffm;
+                cp.records = fp.records; cp.rec_off = fp.rec_off; cp.off_base = fp.off_base; cp.fixed_len = fp.fixed_len;
+                cp.ex_begin = done; cp.n_examples = cnt;
+                cp.F = c->F; cp.k = c->k; cp.Fk = c->Fk; cp.cpr = c->Fk / 4;
+                cp.div_cpr = fp.div_cpr; cp.div_k4 = fp.div_k4; cp.div_F = make_fastdiv(std::max<uint32_t>(c->F, 1));
+                cp.field_ns = fp.field_ns; cp.n_combos = fp.n_combos; cp.combo_off = fp.combo_off; cp.combo_ns = fp.combo_ns;
+                cp.combo_weight = fp.combo_weight; cp.add_constant = fp.add_constant; cp.lr_mask = fp.lr_mask; cp.ffm_mask = fp.ffm_mask;
+                cp.optimizer = fp.optimizer; cp.lr_lr = fp.lr_lr; cp.lr_mpt = fp.lr_mpt; cp.ffm_lr = fp.ffm_lr; cp.ffm_mpt = fp.ffm_mpt;
+                cp.update = update; cp.preds = fp.preds; cp.leftover_idx = left_idx; cp.leftover_cnt = left_cnt; cp.max_groups = cap;
+                const size_t smem_cta = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 4 + 64;
+                ProfScope ps(c, 0);
+                switch (c->fast_ub) {
+                case 1: e = launch_fixed_cta<1>(c, cp, smem_cta, &full_groups); break;
+                case 4: e = launch_fixed_cta<4>(c, cp, smem_cta, &full_groups); break;
+                default: e = launch_fixed_cta<2>(c, cp, smem_cta, &full_groups); break;
+                }
+            } else {
                 ProfScope ps(c, 0);
                 switch (c->fast_nch) {
                 case 1: e = launch_fixed_n<1>(c, fp, smem, &full_groups); break;

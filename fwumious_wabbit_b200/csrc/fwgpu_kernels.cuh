@@ -755,6 +755,186 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const Fixed
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_learn_fixed_cta<UB>: the fused fast path for WIDE models (F*F*k/4 > 128 chunks, e.g. 39 fields x k=8).
+// Same contract as k_learn_fixed (raw records in the cache's in-place encoding, one namespace per field,
+// k % 4 == 0; anything else -> leftover list), but one 256-thread BLOCK per record and the F rows staged in shared memory:
+//   * the record's header slots are read by F threads (prefetched one record ahead), hashes masked in registers;
+//   * gather: every 16-byte chunk goes HBM -> shared memory with cp.async.cg (LDGSTS, no register staging), all of a
+//     thread's chunks in flight at once, one wait per record;
+//   * forward: sum over z<f of <C[f][z-block], C[z][f-block]> with conflict-free LDS.128, shuffle + shared reduction;
+//   * update: chunk (e,c) takes its partner chunk C[z][e-block] from shared memory, grad = g * partner,
+//     ATOMG.128 on the accumulators (UB chunks in flight per thread), LUT, REDG.128 on the weights; own-field chunks skipped.
+// Shared memory per record: F*F*k*4 B (48.7 KB for 39 x 8) -> 4 records in flight per SM.
+// ---------------------------------------------------------------------------------------------
+struct FixedCtaParams {
+    float2 *lr; float *ffm_w; float *ffm_acc; const float *lut_lr; const float *lut_ffm;
+    const uint32_t *records; const uint32_t *rec_off; uint32_t off_base, fixed_len;
+    uint32_t ex_begin, n_examples;
+    uint32_t F, k, Fk, cpr;        // cpr = Fk / 4
+    FastDiv div_cpr, div_k4, div_F;
+    const uint32_t *field_ns;
+    uint32_t n_combos; const uint32_t *combo_off, *combo_ns; const float *combo_weight; uint32_t add_constant;
+    uint32_t lr_mask, ffm_mask;
+    uint32_t optimizer; float lr_lr, lr_mpt, ffm_lr, ffm_mpt;
+    int update;
+    float *preds;
+    uint32_t *leftover_idx, *leftover_cnt;
+    uint32_t max_groups;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
+{
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
+template <int UB>
+__global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t F = p.F, k = p.k, Fk = p.Fk, cpr = p.cpr, k4 = k >> 2;
+    float *C = reinterpret_cast<float *>(smem_raw);
+    uint32_t *slots = reinterpret_cast<uint32_t *>(C + (size_t)F * Fk);
+    float *red = reinterpret_cast<float *>(slots + F);
+    const uint32_t n_chunks = F * cpr;
+    const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u); // <= 256 (host checks)
+    uint32_t n_blocks = gridDim.x;
+    if (p.max_groups && p.max_groups < n_blocks) n_blocks = p.max_groups;
+    if (blockIdx.x >= n_blocks) return;
+    const uint32_t my_field_ns = tid < F ? __ldg(p.field_ns + tid) : 0;
+    auto rec_ptr = [&](uint32_t ex) { return p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len); };
+
+    uint32_t ex = p.ex_begin + blockIdx.x;
+    const uint32_t ex_end = p.ex_begin + p.n_examples;
+    uint32_t slot_next = (ex < ex_end && tid < F) ? __ldg(rec_ptr(ex) + 3 + my_field_ns) : 0x80000000u;
+
+    for (; ex < ex_end; ex += n_blocks) {
+        const uint32_t *rec = rec_ptr(ex);
+        // ---- translate (feature_buffer.rs:178-338), in-place slots only ----
+        const uint32_t slot = slot_next;
+        bool bad = tid < F && (slot & 0x80000000u) && slot != 0x80000000u;
+        if (tid < F) slots[tid] = slot;
+        uint32_t lr_h = 0; float lr_v = 0.0f; bool lr_ok = false;
+        if (tid < p.n_combos) {
+            const uint32_t o0 = __ldg(p.combo_off + tid), o1 = __ldg(p.combo_off + tid + 1);
+            uint32_t h = 0; bool ok = true;
+            for (uint32_t o = o0; o < o1; o++) {
+                const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
+                if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
+                h = (o == o0) ? sl : ((h * 16777619u) ^ sl);
+            }
+            lr_ok = ok; lr_h = h & p.lr_mask; lr_v = __ldg(p.combo_weight + tid);
+        } else if (tid == p.n_combos && p.add_constant) { lr_ok = true; lr_h = 11650396u & p.lr_mask; lr_v = 1.0f; }
+        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
+        const int any_bad = __syncthreads_or(bad ? 1 : 0); // also publishes slots[] and closes the previous record's use of C
+        // prefetch the next record's slots: their cache lines are warm when the next iteration needs them
+        {
+            const uint32_t nx = ex + n_blocks;
+            slot_next = (nx < ex_end && tid < F) ? __ldg(rec_ptr(nx) + 3 + my_field_ns) : 0x80000000u;
+        }
+        if (any_bad) {
+            if (tid == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+            continue; // uniform
+        }
+
+        // ---- gather: HBM -> shared memory, 16 B per cp.async, everything in flight at once ----
+        for (uint32_t idx = tid; idx < n_chunks; idx += 256) {
+            const uint32_t e = fdiv(idx, p.div_cpr), c = idx - e * cpr;
+            const uint32_t sl = slots[e];
+            float *dst = C + e * Fk + 4 * c;
+            if (sl != 0x80000000u) cp_async16(dst, p.ffm_w + (sl & p.ffm_mask) + 4 * c);
+            else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        const float lr_w = lr_ok ? __ldcg(p.lr + lr_h).x : 0.0f;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();
+
+        // ---- forward ----
+        float part = lr_ok ? __fmul_rn(lr_w, lr_v) : 0.0f;
+        const uint32_t FF = F * F;
+        for (uint32_t idx = tid; idx < FF; idx += 256) {
+            const uint32_t f = fdiv(idx, p.div_F), z = idx - f * F;
+            if (z < f) {
+                const float4 *a = reinterpret_cast<const float4 *>(C + f * Fk + z * k), *b = reinterpret_cast<const float4 *>(C + z * Fk + f * k);
+                float sd = 0.0f;
+                for (uint32_t q = 0; q < k4; q++) {
+                    const float4 x = a[q], y = b[q];
+                    sd = __fadd_rn(sd, __fmul_rn(x.x, y.x)); sd = __fadd_rn(sd, __fmul_rn(x.y, y.y));
+                    sd = __fadd_rn(sd, __fmul_rn(x.z, y.z)); sd = __fadd_rn(sd, __fmul_rn(x.w, y.w));
+                }
+                part += sd;
+            }
+        }
+        float wsum = warp_sum(part);
+        if (lane == 0) red[warp] = wsum;
+        __syncthreads();
+        wsum = 0.0f;
+#pragma unroll
+        for (int w_ = 0; w_ < 8; w_++) wsum += red[w_];
+
+        float pr, g;
+        if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+        else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+        else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+        else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
+        if (tid == 0) p.preds[ex] = pr;
+        if (!(p.update && importance != 0.0f && g != 0.0f)) continue; // uniform; the next iteration's barrier protects C
+
+        // ---- update: UB chunks per thread and round ----
+        for (uint32_t idx0 = tid; idx0 < n_chunks; idx0 += UB * 256) {
+            float4 gr[UB], old[UB];
+            uint32_t addr[UB];
+            bool on[UB];
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                const uint32_t idx = idx0 + u * 256;
+                on[u] = false;
+                if (idx >= n_chunks) continue;
+                const uint32_t e = fdiv(idx, p.div_cpr), c = idx - e * cpr;
+                const uint32_t z = fdiv(c, p.div_k4), q4 = c - z * k4;
+                const uint32_t sl = slots[e];
+                if (z == e || sl == 0x80000000u) continue; // own-field chunk: exactly zero gradient; absent field: no row
+                const float4 pv = *reinterpret_cast<const float4 *>(C + z * Fk + e * k + 4 * q4);
+                gr[u] = make_float4(__fmul_rn(g, pv.x), __fmul_rn(g, pv.y), __fmul_rn(g, pv.z), __fmul_rn(g, pv.w));
+                if (gr[u].x == 0.0f && gr[u].y == 0.0f && gr[u].z == 0.0f && gr[u].w == 0.0f) continue; // partner absent
+                on[u] = true;
+                addr[u] = (sl & p.ffm_mask) + 4 * c;
+                if (p.optimizer != OPT_SGD)
+                    old[u] = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + addr[u]),
+                                       make_float4(__fmul_rn(gr[u].x, gr[u].x), __fmul_rn(gr[u].y, gr[u].y), __fmul_rn(gr[u].z, gr[u].z), __fmul_rn(gr[u].w, gr[u].w)));
+            }
+#pragma unroll
+            for (int u = 0; u < UB; u++) {
+                if (!on[u]) continue;
+                float4 upd;
+                if (p.optimizer == OPT_SGD) upd = make_float4(-__fmul_rn(gr[u].x, p.ffm_lr), -__fmul_rn(gr[u].y, p.ffm_lr), -__fmul_rn(gr[u].z, p.ffm_lr), -__fmul_rn(gr[u].w, p.ffm_lr));
+                else {
+                    upd.x = -opt_step(p.optimizer, gr[u].x, acc_after(old[u].x, gr[u].x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.y = -opt_step(p.optimizer, gr[u].y, acc_after(old[u].y, gr[u].y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.z = -opt_step(p.optimizer, gr[u].z, acc_after(old[u].z, gr[u].z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.w = -opt_step(p.optimizer, gr[u].w, acc_after(old[u].w, gr[u].w), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                }
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + addr[u]), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+            }
+        }
+        // ---- LR update (block_lr.rs:135-151) ----
+        if (lr_ok) {
+            float *cell = reinterpret_cast<float *>(p.lr + lr_h);
+            const float grad = __fmul_rn(g, lr_v);
+            float upd;
+            if (p.optimizer == OPT_SGD) upd = __fmul_rn(grad, p.lr_lr);
+            else {
+                const float old = atomicAdd(cell + 1, __fmul_rn(grad, grad));
+                upd = opt_step(p.optimizer, grad, acc_after(old, grad), p.lut_lr, p.lr_lr, p.lr_mpt);
+            }
+            atomicAdd(cell, -upd);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Translate: raw record -> AoS feature lists (feature_buffer.rs:178-338), one thread per example.
 // ---------------------------------------------------------------------------------------------
 struct TranslateParams {
