@@ -31,7 +31,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c2", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--examples", type=int, default=0, help="examples per step (0 = workload default)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="examples in the cpu_baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -41,9 +41,10 @@ def parse_args():
     return ap.parse_args()
 
 
-DEFAULT_EXAMPLES = {"c1": 10_000_000, "c2": 10_000_000, "c3": 2_000_000, "c4": 2_000_000}
-CPU_SAMPLE = {"c1": 4_000_000, "c2": 2_000_000, "c3": 100_000, "c4": 100_000}
-REF_STEP_EXAMPLES = {"c1": 8_000_000, "c2": 4_000_000, "c3": 200_000, "c4": 200_000}
+DEFAULT_EXAMPLES = {"c1": 10_000_000, "c2": 10_000_000, "c3": 2_000_000, "c4": 2_000_000, "c5": 1_000_000}
+CPU_SAMPLE = {"c1": 4_000_000, "c2": 2_000_000, "c3": 100_000, "c4": 100_000, "c5": 15_000}
+MAX_SLICES = 12
+REF_STEP_EXAMPLES = {"c1": 8_000_000, "c2": 4_000_000, "c3": 200_000, "c4": 200_000, "c5": 30_000}
 
 
 def measured_peaks():
@@ -58,38 +59,46 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clock and throttle reasons during the timed region (pynvml, 100 ms period)."""
+    """Samples SM clock and throttle reasons during the timed region (pynvml, 10 ms period).
+    NVML is initialised in the constructor, i.e. before the timed region starts, so even a region of a
+    few tens of milliseconds gets samples; one more sample is taken when the region closes."""
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.sm, self.reasons, self.max_mhz, self.err = index, False, [], set(), None, None
-
-    def run(self):
+        self.nv = self.h = None
         try:
             import pynvml as nv
 
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.names = {
                 getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
                 getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
                 getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
                 getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
                 getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
             }
-            while not self.stop_flag:
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                try:
-                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                    for bit, name in names.items():
-                        if r & bit:
-                            self.reasons.add(name)
-                except Exception:
-                    pass
-                time.sleep(0.1)
         except Exception as e:  # noqa: BLE001
             self.err = str(e)
+
+    def sample(self):
+        if self.h is None:
+            return
+        try:
+            self.sm.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.names.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception as e:  # noqa: BLE001
+            self.err = str(e)
+
+    def run(self):
+        while not self.stop_flag:
+            self.sample()
+            time.sleep(0.01)
 
     def summary(self):
         if not self.sm:
@@ -176,17 +185,24 @@ def run_ours(args):
     import ctypes as C
 
     nbytes = n * w.record_len * 4
+    # an online learner must not see the same batch twice: every step (warm-up included) trains on a FRESH slice of the
+    # stream (repeating one batch drives the gradients to zero and lets the kernel skip work).  At most MAX_SLICES slices
+    # are kept; longer runs cycle through them.
+    n_slices = max(1, min(args.warmup + args.steps, MAX_SLICES, max(1, (12 << 30) // nbytes)))
     hp = C.c_void_p()
-    assert L.fwgpu_host_alloc(C.byref(hp), nbytes) == 0
-    recs = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n, w.record_len))
+    assert L.fwgpu_host_alloc(C.byref(hp), nbytes * n_slices) == 0
+    recs_all = np.ctypeslib.as_array(C.cast(hp, C.POINTER(C.c_uint32)), shape=(n_slices * n, w.record_len))
     from fwumious_wabbit_b200 import dist_util
 
-    first, _ = dist_util.shard(rank, world, n)
-    w.records(n, first=first, seed=1, out=recs, uniform=args.uniform_ids)
+    first, _ = dist_util.shard(rank, world, n * n_slices)
+    w.records(n * n_slices, first=first * 1, seed=1, out=recs_all, uniform=args.uniform_ids)
     pp = C.c_void_p()
     assert L.fwgpu_host_alloc(C.byref(pp), n * 4) == 0
     preds = np.ctypeslib.as_array(C.cast(pp, C.POINTER(C.c_float)), shape=(n,))
-    ds = re.upload_dataset(recs.reshape(-1), n_examples=n)
+    ds = re.upload_dataset(recs_all.reshape(-1), n_examples=n * n_slices)
+
+    def slice_of(step):
+        return (step % n_slices) * n
 
     def barrier():
         if dist is not None:
@@ -199,26 +215,28 @@ def run_ours(args):
 
     # ---------------- value: records resident in HBM ----------------
     upd = not args.predict_only
-    for _ in range(args.warmup):
-        re.learn_dataset(ds, 0, n, update=True, sync=False)
+    for i in range(args.warmup):
+        re.learn_dataset(ds, slice_of(i), n, update=True, sync=False)
     barrier()
     re.set_profiling(True)
-    re.kernel_time(0); re.kernel_time(1)
+    re.kernel_time(0); re.kernel_time(1); re.kernel_time(2)
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = re.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
-        re.learn_dataset(ds, 0, n, update=upd, sync=False)
+    for i in range(args.steps):
+        re.learn_dataset(ds, slice_of(args.warmup + i), n, update=upd, sync=False)
     ev1.record(stream)
+    sampler.sample()  # the queue is still draining here: a sample under load even for a very short region
     barrier()
     sampler.stop_flag = True
     launches = re.launch_count() - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
     k_ms, k_n = re.kernel_time(0)
     t_ms, t_n = re.kernel_time(1)
+    h_ms, h_n = re.kernel_time(2)
     re.set_profiling(False)
     sampler.join(timeout=2)
     value = dist_util.whole_job_rate(n, args.steps, world, ms_total)
@@ -226,14 +244,18 @@ def run_ours(args):
     # ---------------- e2e: host buffers through the C ABI ----------------
     e2e = None
     if not args.no_e2e:
-        for _ in range(max(1, min(args.warmup, 2))):
-            re.learn_records(recs.reshape(-1), n_examples=n, update=True, out=preds, sync=False)
+        def host_slice(step):
+            return recs_all[slice_of(step):slice_of(step) + n]
+
+        e_warm = max(1, min(args.warmup, 2))
+        for i in range(e_warm):
+            re.learn_records(host_slice(i).reshape(-1), n_examples=n, update=True, out=preds, sync=False)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
         e0.record(stream)
-        for _ in range(args.steps):
-            re.learn_records(recs.reshape(-1), n_examples=n, update=True, out=preds, sync=False)
+        for i in range(args.steps):
+            re.learn_records(host_slice(e_warm + i).reshape(-1), n_examples=n, update=True, out=preds, sync=False)
         e1.record(stream)
         barrier()
         wall_ms = (time.perf_counter() - t0) * 1e3
@@ -242,8 +264,10 @@ def run_ours(args):
         e2e = {"value": world * n * args.steps / (e_ms * 1e-3), "unit": "examples/s",
                "h2d_bytes_per_step": int(nbytes), "d2h_bytes_per_step": int(n * 4),
                "ms_per_step": e_ms / args.steps, "wall_ms_per_step": max_over_ranks(wall_ms) / args.steps}
+        recs = host_slice(e_warm + args.steps - 1)
         ll = float(-np.mean(np.where(recs[:, 1] == 1, np.log(np.clip(preds, 1e-7, 1)), np.log(np.clip(1 - preds, 1e-7, 1)))))
         e2e["last_step_logloss"] = ll
+        e2e["note"] = "second epoch over the slices the value run trained on (same model, host buffers)"
 
     # ---------------- roofline of the dominant kernel (k_learn) ----------------
     peak, peak_src = measured_peaks()
@@ -263,6 +287,18 @@ def run_ours(args):
                 "kernel": "k_learn", "peak_source": peak_src, "algorithmic_bytes_per_example": alg_bytes,
                 "examples_per_launch": ex_per_launch, "avg_launch_ms": k_ms / k_n, "launches_timed": int(k_n),
                 "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1)), "translate_ms_per_launch": (t_ms / t_n) if t_n else None}
+        if h_n:
+            # dense head (config 5): fp32 FFMA GEMMs, reported against the kernel's own flop count (forward + the two backward
+            # GEMMs + the squared-gradient sums of every layer), not against the HBM roofline of the gather/scatter kernel
+            mi = w.mi
+            x_len = mi.num_combos + len(mi.ffm_fields) * (len(mi.ffm_fields) + 1) // 2
+            dims, n_in = [], x_len
+            for layer in mi.nn_layers:
+                dims.append((n_in, int(layer.get("width", 20)))); n_in = dims[-1][1]
+            dims.append((n_in + x_len, 1))
+            fma = sum(a * b * (1 + 1 + 2) for a, b in dims)  # forward, input gradient, sum g and sum g^2
+            roof["head"] = {"ms_per_pass": h_ms / h_n, "passes": int(h_n), "share_of_step": h_ms / ev0.elapsed_time(ev1),
+                            "fp32_tflops": 2 * fma * n * args.steps / (h_ms * 1e-3) * 1e-12, "fma_per_example": fma}
 
     # ---------------- cpu baseline (rank 0, N = 1 only) ----------------
     cpu = None
@@ -277,9 +313,9 @@ def run_ours(args):
             "metric": "examples/sec FFM training", "value": value, "unit": "examples/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{w.name}: {w.description}" + (" [DIAGNOSTIC: uniform ids]" if args.uniform_ids else "") + (" [DIAGNOSTIC: predict only]" if args.predict_only else ""), "examples_per_step_per_gpu": n,
+            "config": {"workload": f"{w.name}: {w.description}" + (" [DIAGNOSTIC: uniform ids]" if args.uniform_ids else "") + (" [DIAGNOSTIC: predict only]" if args.predict_only else ""), "examples_per_step_per_gpu": n, "fresh_slices": n_slices,
                        "parallelism": f"replicas x{world} (independent models, disjoint example shards)" if world > 1 else "single GPU",
-                       "l2_policy": f"inputs larger than L2: {nbytes >> 20} MiB of records per step; table ({(w.mi.ffm_k and ((1 << w.mi.ffm_bit_precision) * 8 >> 20))} MiB w+acc) is L2-resident by nature for c2",
+                       "l2_policy": f"inputs larger than L2: {nbytes >> 20} MiB of records per step; table {(w.mi.ffm_k and ((1 << w.mi.ffm_bit_precision) * 8 >> 20))} MiB w+acc vs 126 MB L2 (c2's 8 MiB table is L2-resident by nature; the records are not)",
                        "optimizer": "AdagradLUT", "semantics": "Hogwild on device, chunked launches"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         }

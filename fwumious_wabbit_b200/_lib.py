@@ -29,6 +29,7 @@ class ModelDesc(C.Structure):
         ("ffm_init_width", C.c_float), ("ffm_init_zero_band", C.c_float), ("ffm_init_center", C.c_float),
         ("nn_num_layers", C.c_uint32),
         ("nn_width", C.c_uint32 * MAX_NN_LAYERS), ("nn_relu", C.c_uint32 * MAX_NN_LAYERS),
+        ("nn_init", C.c_uint32 * MAX_NN_LAYERS),
         ("n_namespaces", C.c_uint32), ("ns_is_f32", u8p),
         ("n_combos", C.c_uint32), ("combo_off", u32p), ("combo_ns", u32p), ("combo_weight", f32p),
         ("add_constant", C.c_uint32),

@@ -2,6 +2,7 @@
 // Pure CUDA runtime; no torch, no CPU fallback (every entry point needs a live ctx on a GPU).
 #include "../../include/fwgpu.h"
 #include "fwgpu_kernels.cuh"
+#include "fwgpu_head.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -9,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -106,10 +108,21 @@ struct fwgpu_ctx {
     uint32_t max_inflight = 0; // 0 = unlimited
     bool ramp_finished = false;
     bool profiling = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[2];
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof[3];
     std::vector<cudaEvent_t> ev_pool;
-    double prof_ms[2] = {0, 0};
-    uint64_t prof_n[2] = {0, 0};
+    double prof_ms[3] = {0, 0, 0};
+    uint64_t prof_n[3] = {0, 0, 0};
+    // dense head (topology "one", regressor.rs:191-320): hidden layers then the final neuron; all parameters of all
+    // layers live in ONE contiguous buffer per kind so the optimizer step is a single launch
+    struct HeadLayer { uint32_t n_in, n_out, relu, init; size_t off; };
+    std::vector<HeadLayer> head;
+    size_t head_params = 0;
+    float *head_w = nullptr, *head_acc = nullptr, *head_G1 = nullptr, *head_G2 = nullptr;
+    uint32_t x_len = 0, ldx = 0;  // head input: num_combos + F(F+1)/2 (regressor.rs:185-189), padded leading dimension
+    uint32_t head_batch = 4096;   // examples per pass around the head's GEMMs = examples in flight
+    double head_ramp_mul = 2.0;   // sub-batches grow as head_ramp_mul * sqrt(examples_seen) (0 = only the linear ramp)
+    uint32_t head_rows_cap = 0;
+    DevBuf hX, hdX, hH[FWGPU_MAX_NN_LAYERS], hdZ[FWGPU_MAX_NN_LAYERS], h_label, h_imp, h_outidx, h_dy;
     std::string err;
     void set_error(const std::string &s) { err = s; }
 };
@@ -162,10 +175,13 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     cudaFree(c->d_field_ns); cudaFree(c->d_combo_weight);
     for (DevBuf *b : {&c->rec[0], &c->rec[1], &c->rec_off_dev[0], &c->rec_off_dev[1], &c->meta, &c->lr_ent, &c->ffm_ent, &c->preds, &c->csr, &c->leftover})
         if (b->p) cudaFree(b->p);
+    cudaFree(c->head_w); cudaFree(c->head_acc); cudaFree(c->head_G1); cudaFree(c->head_G2);
+    for (DevBuf *b : {&c->hX, &c->hdX, &c->h_label, &c->h_imp, &c->h_outidx, &c->h_dy}) if (b->p) cudaFree(b->p);
+    for (int i = 0; i < FWGPU_MAX_NN_LAYERS; i++) { if (c->hH[i].p) cudaFree(c->hH[i].p); if (c->hdZ[i].p) cudaFree(c->hdZ[i].p); }
     cudaFree(c->err_flag);
     if (c->err_host) cudaFreeHost(c->err_host);
     for (int i = 0; i < 2; i++) { if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]); if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]); }
-    for (int kk = 0; kk < 2; kk++) for (auto &pr : c->prof[kk]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (int kk = 0; kk < 3; kk++) for (auto &pr : c->prof[kk]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
@@ -194,7 +210,7 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     const fwgpu_model_desc &d = c->d;
     if (d.bit_precision == 0 || d.bit_precision > 31) { c->set_error("bit_precision must be in 1..31"); return FWGPU_ERR_INVALID; }
     if (d.optimizer > FWGPU_OPT_ADAGRAD_LUT) { c->set_error("unknown optimizer"); return FWGPU_ERR_INVALID; }
-    if (d.nn_num_layers != 0) { c->set_error("dense head (nn_layers) is not implemented by the CUDA path yet"); return FWGPU_ERR_UNSUPPORTED; }
+    if (d.nn_num_layers > FWGPU_MAX_NN_LAYERS) { c->set_error("too many nn layers"); return FWGPU_ERR_INVALID; }
     c->optimizer = d.immutable ? FWGPU_OPT_SGD : d.optimizer;
     c->F = d.ffm_k > 0 ? d.ffm_num_fields : 0;
     c->k = d.ffm_k;
@@ -280,6 +296,57 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());
+    if (d.nn_num_layers > 0) {
+        // BlockNeuronLayer::allocate_and_init_weights (block_neural.rs:367-412): weights by init type, biases 0,
+        // accumulators at initial_data().  Hu / Xavier: see FWGPU_NN_INIT_* in fwgpu.h (parity unpinned).
+        c->x_len = d.num_combos + (c->F ? c->F * (c->F + 1) / 2 : 0);
+        c->ldx = (c->x_len + 3) & ~3u;
+        uint32_t n_in = c->x_len;
+        size_t off = 0;
+        for (uint32_t l = 0; l <= d.nn_num_layers; l++) {
+            const bool fin = l == d.nn_num_layers;
+            fwgpu_ctx::HeadLayer L;
+            L.n_in = fin ? n_in + c->x_len : n_in; // join [h, x] (regressor.rs:303-307)
+            L.n_out = fin ? 1 : d.nn_width[l];
+            L.relu = fin ? 0 : d.nn_relu[l];
+            L.init = fin ? FWGPU_NN_INIT_ONE : d.nn_init[l]; // regressor.rs:308-315
+            if (L.n_out == 0 || L.n_in >= 16000) { c->set_error("nn layer width must be > 0 and inputs < 16000 (block_neural.rs:27,79)"); return FWGPU_ERR_INVALID; }
+            L.off = off;
+            off += (size_t)(L.n_in + 1) * L.n_out;
+            off = (off + 3) & ~(size_t)3;
+            c->head.push_back(L);
+            n_in = L.n_out;
+        }
+        c->head_params = off;
+        std::vector<float> w(off, 0.0f);
+        uint64_t seed = 12345;
+        auto uni = [&]() { seed = seed * 6364136223846793005ULL + 1442695040888963407ULL; return (float)((seed >> 40) & 0xFFFFFF) / 16777216.0f; };
+        for (auto &L : c->head) {
+            const size_t nw = (size_t)L.n_in * L.n_out;
+            if (L.init == FWGPU_NN_INIT_ONE) for (size_t i = 0; i < nw; i++) w[L.off + i] = 1.0f;
+            else if (L.init == FWGPU_NN_INIT_HU || L.init == FWGPU_NN_INIT_XAVIER) {
+                const double sd = L.init == FWGPU_NN_INIT_HU ? sqrt(2.0 / L.n_in) : sqrt(2.0 / (double)nw);
+                const double bound = sd * sqrt(3.0);
+                for (size_t i = 0; i < nw; i++) w[L.off + i] = (float)((2.0 * uni() - 1.0) * bound);
+            }
+        }
+        CUDA_TRY(c, cudaMalloc((void **)&c->head_w, off * 4));
+        CUDA_TRY(c, cudaMemcpy(c->head_w, w.data(), off * 4, cudaMemcpyHostToDevice));
+        if (c->optimizer != FWGPU_OPT_SGD) {
+            CUDA_TRY(c, cudaMalloc((void **)&c->head_acc, off * 4));
+            const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? d.nn_init_acc_gradient : 0.0f;
+            k_fill<<<c->num_sms, 256, 0, c->stream>>>(c->head_acc, off, acc0);
+            c->launches++;
+        }
+        if (!d.immutable) {
+            CUDA_TRY(c, cudaMalloc((void **)&c->head_G1, off * 4));
+            CUDA_TRY(c, cudaMalloc((void **)&c->head_G2, off * 4));
+            CUDA_TRY(c, cudaMemsetAsync(c->head_G1, 0, off * 4, c->stream));
+            CUDA_TRY(c, cudaMemsetAsync(c->head_G2, 0, off * 4, c->stream));
+        }
+        if (const char *t = getenv("FWGPU_HEAD_BATCH")) c->head_batch = std::max(1, atoi(t));
+        if (const char *t = getenv("FWGPU_HEAD_RAMP_MUL")) c->head_ramp_mul = atof(t);
+    }
 
     fwgpu_status st;
     if ((st = upload_vec(c, c->ns_is_f32, &c->d_ns_is_f32))) return st;
@@ -294,10 +361,11 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         for (uint32_t f = 0; base && f < c->F; f++) base = (c->field_off[f + 1] - c->field_off[f]) == 1;
         const uint32_t n_chunks = c->F * (c->Fk / 4);
         bool ok = base && c->F <= 32 && n_lr_max <= 64 && n_chunks <= 128; // warp per record
-        if (base && !ok) {
+        if (base && (!ok || !c->head.empty())) {
             // wide model: the block-per-record kernel, if a record's rows fit in shared memory at least twice per SM
-            const size_t smem_need = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 4 + 64;
-            c->fast_cta = c->F <= 256 && n_lr_max <= 256 && smem_need * 2 <= c->smem_optin;
+            // (models with a dense head always take it: it is the fused kernel that has the two-pass form)
+            const size_t smem_need = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 8 + 64;
+            c->fast_cta = c->F > 0 && c->F <= 256 && n_lr_max <= 256 && smem_need * 2 <= c->smem_optin;
             ok = c->fast_cta;
         }
         if (const char *t = getenv("FWGPU_UB")) c->fast_ub = atoi(t);
@@ -387,7 +455,7 @@ extern "C" fwgpu_status fwgpu_set_profiling(fwgpu_ctx *c, int enabled)
 }
 extern "C" fwgpu_status fwgpu_kernel_time(fwgpu_ctx *c, int kind, double *total_ms, uint64_t *launches)
 {
-    if (!c || kind < 0 || kind > 1) return FWGPU_ERR_INVALID;
+    if (!c || kind < 0 || kind > 2) return FWGPU_ERR_INVALID;
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     for (auto &pr : c->prof[kind]) {
         float ms = 0;
@@ -452,15 +520,14 @@ template <int T> static cudaError_t launch_learn_t(fwgpu_ctx *c, const LearnPara
     }
 }
 
-static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_cap, int update, const uint32_t *n_examples_dev = nullptr,
-                                 bool count_seen = true, uint32_t lr_cap = 0)
+// shape-dependent part of LearnParams, thread-group width T and dynamic shared memory of k_learn
+static fwgpu_status make_learn_params(fwgpu_ctx *c, uint32_t n_cap, int update, uint32_t lr_cap, LearnParams &p, int &T, size_t &smem)
 {
-    if (n_examples == 0) return FWGPU_OK;
-    LearnParams p{};
+    p = LearnParams{};
     p.lr = c->lr; p.ffm_w = c->ffm_w; p.ffm_acc = c->ffm_acc;
     p.lut_lr = c->lut_dev; p.lut_ffm = c->lut_dev + FWGPU_LUT_SIZE;
     p.meta = (const ExMeta *)c->meta.p; p.lr_ent = (const uint4 *)c->lr_ent.p; p.ffm_ent = (const uint4 *)c->ffm_ent.p;
-    p.preds = (float *)c->preds.p; p.n_examples = n_examples;
+    p.preds = (float *)c->preds.p;
     p.F = c->F; p.k = c->k; p.Fk = c->Fk; p.cpr = c->cpr; p.n_cap = std::max<uint32_t>(n_cap, 1);
     p.div_cpr = make_fastdiv(std::max<uint32_t>(c->cpr, 1)); p.div_k = make_fastdiv(std::max<uint32_t>(c->k, 1)); p.div_F = make_fastdiv(std::max<uint32_t>(c->F, 1));
     p.optimizer = c->optimizer;
@@ -473,16 +540,48 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
     size_t words = (size_t)c->F * c->Fk + (size_t)p.n_cap * c->k + 3 * (size_t)p.n_cap + (c->F + 1) + 16 + p.lr_cap;
     size_t group_bytes = ((words * 4 + 15) / 16) * 16;
     p.group_smem_bytes = (uint32_t)group_bytes;
-    int T = 32;
+    T = 32;
     const uint32_t work = c->F * c->cpr;
     if (work > 1536) T = 256; else if (work > 512) T = 128; else if (work > 128) T = 64;
     if (c->force_T == 32 || c->force_T == 64 || c->force_T == 128 || c->force_T == 256) T = c->force_T;
-    size_t smem = group_bytes * (256 / T);
+    smem = group_bytes * (256 / T);
     while (smem > c->smem_optin && T < 256) { T *= 2; smem = group_bytes * (256 / T); }
     if (smem > c->smem_optin) {
         c->set_error("example staging needs " + std::to_string(smem) + " B of shared memory (> " + std::to_string(c->smem_optin) + "): F*F*k or features per example too large");
         return FWGPU_ERR_TOO_LARGE;
     }
+    return FWGPU_OK;
+}
+
+static fwgpu_status dispatch_learn(fwgpu_ctx *c, const LearnParams &q, int T, size_t smem, uint32_t *full_groups)
+{
+    cudaError_t e;
+    {
+        ProfScope ps(c, 0);
+        switch (T) {
+        case 32: e = launch_learn_t<32>(c, q, smem, full_groups); break;
+        case 64: e = launch_learn_t<64>(c, q, smem, full_groups); break;
+        case 128: e = launch_learn_t<128>(c, q, smem, full_groups); break;
+        default: e = launch_learn_t<256>(c, q, smem, full_groups); break;
+        }
+    }
+    if (e != cudaSuccess) { c->set_error(std::string("k_learn launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+    return FWGPU_OK;
+}
+
+static fwgpu_status head_learn(fwgpu_ctx *c, uint32_t count, int update, uint32_t n_cap, uint32_t lr_cap, const FixedCtaParams *cta,
+                               const TranslateParams *tp_left);
+
+static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_cap, int update, const uint32_t *n_examples_dev = nullptr,
+                                 bool count_seen = true, uint32_t lr_cap = 0)
+{
+    if (n_examples == 0) return FWGPU_OK;
+    if (!c->head.empty()) return head_learn(c, n_examples, update, n_cap, lr_cap, nullptr, nullptr);
+    LearnParams p;
+    int T; size_t smem;
+    fwgpu_status st;
+    if ((st = make_learn_params(c, n_cap, update, lr_cap, p, T, smem))) return st;
+    p.n_examples = n_examples;
     // Concurrency ramp (DESIGN.md "semantics"): a cold model is trained with examples_seen / ramp_div examples
     // in flight; segments double until the whole machine is in use.  Predict-only launches are never limited.
     uint32_t done = 0;
@@ -504,17 +603,7 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
         // parity mode: a strictly sequential run (ramp_div >= 2^31-1) or a single-example call sums in the reference's order
         q.exact_order = ((cap == 1 && c->ramp_div >= 0x7fffffffu) || n_examples == 1) ? 1 : 0;
         uint32_t full_groups = 0;
-        cudaError_t e;
-        {
-            ProfScope ps(c, 0);
-            switch (T) {
-            case 32: e = launch_learn_t<32>(c, q, smem, &full_groups); break;
-            case 64: e = launch_learn_t<64>(c, q, smem, &full_groups); break;
-            case 128: e = launch_learn_t<128>(c, q, smem, &full_groups); break;
-            default: e = launch_learn_t<256>(c, q, smem, &full_groups); break;
-            }
-        }
-        if (e != cudaSuccess) { c->set_error(std::string("k_learn launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+        if ((st = dispatch_learn(c, q, T, smem, &full_groups))) return st;
         if (update) {
             if (count_seen) c->examples_seen += cnt;
             if (cap && full_groups && cap >= full_groups) c->ramp_finished = true;
@@ -548,9 +637,9 @@ template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedPa
     return cudaGetLastError();
 }
 
-template <int UB> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
+template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
 {
-    auto kern = k_learn_fixed_cta<UB>;
+    auto kern = k_learn_fixed_cta<UB, PHASE>;
     static thread_local size_t configured = 0;
     if (smem > configured) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -568,6 +657,168 @@ template <int UB> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedC
     kern<<<grid, 256, smem, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
+}
+
+// ---- dense head (fwgpu_head.cuh) ----------------------------------------------------------------
+template <bool A_T, bool B_T, int EPI> static void launch_head_gemm(fwgpu_ctx *c, HeadGemmParams &p)
+{
+    uint32_t splits = 1;
+    if (EPI == HEAD_EPI_SUMS) {
+        // the reduction runs over the sub-batch: split it so that the grid fills the machine about twice
+        const uint32_t tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64);
+        splits = std::max<uint32_t>(1, std::min<uint32_t>((2 * (uint32_t)c->num_sms + tiles - 1) / tiles, (p.K + 63) / 64));
+        p.k_split = (((p.K + splits - 1) / splits) + 15) / 16 * 16;
+        splits = (p.K + p.k_split - 1) / p.k_split;
+    }
+    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, splits);
+    k_head_gemm<A_T, B_T, EPI><<<grid, 256, 0, c->stream>>>(p);
+    c->launches++;
+}
+
+// forward (+ backward and optimizer step when update) of the head over `rows` examples whose inputs sit in hX
+static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
+{
+    ProfScope ps(c, 2);
+    const size_t nl = c->head.size(); // hidden layers + final neuron
+    float *X = (float *)c->hX.p, *dX = (float *)c->hdX.p, *dy = (float *)c->h_dy.p;
+    const float *in = X;
+    uint32_t ld_in = c->ldx;
+    for (size_t l = 0; l + 1 < nl; l++) { // BlockNeuronLayer forward + BlockRELU (block_neural.rs:196-222, block_relu.rs:79-99)
+        const auto &L = c->head[l];
+        HeadGemmParams g{};
+        g.A = in; g.lda = ld_in; g.B = c->head_w + L.off; g.ldb = L.n_in; g.C = (float *)c->hH[l].p; g.ldc = L.n_out;
+        g.M = rows; g.N = L.n_out; g.K = L.n_in; g.bias = c->head_w + L.off + (size_t)L.n_in * L.n_out; g.relu = (int)L.relu;
+        launch_head_gemm<false, false, HEAD_EPI_BIAS_ACT>(c, g);
+        in = g.C; ld_in = L.n_out;
+    }
+    const auto &Lf = c->head[nl - 1];
+    const auto &Ll = c->head[nl - 2]; // last hidden layer
+    {
+        HeadFinalParams f{};
+        f.H = (const float *)c->hH[nl - 2].p; f.ldh = Ll.n_out; f.n_h = Ll.n_out; f.X = X; f.ldx = c->ldx; f.n_x = c->x_len;
+        f.w = c->head_w + Lf.off; f.label = (const float *)c->h_label.p; f.importance = (const float *)c->h_imp.p;
+        f.out_index = (const uint32_t *)c->h_outidx.p; f.preds = (float *)c->preds.p; f.dy = dy;
+        f.dZ = (float *)c->hdZ[nl - 2].p; f.ldz = Ll.n_out; f.n_rows = rows; f.update = update; f.h_relu = (int)Ll.relu;
+        const uint32_t blocks = std::min<uint32_t>((rows + 7) / 8, (uint32_t)c->num_sms * 8);
+        k_head_final<<<blocks, 256, 0, c->stream>>>(f);
+        c->launches++;
+    }
+    if (!update) { CUDA_TRY(c, cudaGetLastError()); return FWGPU_OK; }
+    // final neuron: gradient sums over its inputs [h, x] and its bias (block_neural.rs:266-305 with one neuron)
+    {
+        HeadGemmParams g{};
+        g.A = dy; g.lda = 1; g.B = (const float *)c->hH[nl - 2].p; g.ldb = Ll.n_out; g.M = 1; g.N = Ll.n_out; g.K = rows; g.ldc = Lf.n_in;
+        g.G1 = c->head_G1 + Lf.off; g.G2 = c->head_G2 + Lf.off; g.G1_bias = c->head_G1 + Lf.off + Lf.n_in; g.G2_bias = c->head_G2 + Lf.off + Lf.n_in;
+        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, g);
+        HeadGemmParams h = g;
+        h.B = X; h.ldb = c->ldx; h.N = c->x_len; h.G1 = g.G1 + Ll.n_out; h.G2 = g.G2 + Ll.n_out; h.G1_bias = nullptr; h.G2_bias = nullptr;
+        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, h);
+    }
+    for (size_t li = nl - 1; li-- > 0;) { // hidden layers, last to first
+        const auto &L = c->head[li];
+        const float *dZ = (const float *)c->hdZ[li].p;
+        const float *W = c->head_w + L.off;
+        // errors for the layer below from the PRE-update weights (block_neural.rs:283-284); the step is applied at the end
+        HeadGemmParams g{};
+        g.A = dZ; g.lda = L.n_out; g.B = W; g.ldb = L.n_in; g.M = rows; g.N = L.n_in; g.K = L.n_out;
+        if (li > 0) {
+            g.C = (float *)c->hdZ[li - 1].p; g.ldc = L.n_in; g.mask_src = (const float *)c->hH[li - 1].p; g.ld_mask = L.n_in; g.mask_on = (int)c->head[li - 1].relu;
+            launch_head_gemm<false, true, HEAD_EPI_MASK>(c, g);
+        } else {
+            // BlockCopy backward: d_x = d(path through the layers) + d(direct path into the final neuron) (block_misc.rs:452-473)
+            g.C = dX; g.ldc = c->ldx; g.direct_w = c->head_w + Lf.off + Ll.n_out; g.dy = dy;
+            launch_head_gemm<false, true, HEAD_EPI_ADD_DIRECT>(c, g);
+        }
+        HeadGemmParams u{};
+        u.A = dZ; u.lda = L.n_out; u.B = li > 0 ? (const float *)c->hH[li - 1].p : X; u.ldb = li > 0 ? L.n_in : c->ldx;
+        u.M = L.n_out; u.N = L.n_in; u.K = rows; u.ldc = L.n_in;
+        u.G1 = c->head_G1 + L.off; u.G2 = c->head_G2 + L.off;
+        u.G1_bias = c->head_G1 + L.off + (size_t)L.n_in * L.n_out; u.G2_bias = c->head_G2 + L.off + (size_t)L.n_in * L.n_out;
+        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, u);
+    }
+    k_head_apply<<<(uint32_t)std::min<size_t>((c->head_params + 255) / 256, (size_t)c->num_sms * 8), 256, 0, c->stream>>>(
+        c->head_w, c->head_acc, c->head_G1, c->head_G2, c->head_params, c->optimizer, c->lut_dev + 2 * FWGPU_LUT_SIZE, c->d.nn_learning_rate, -c->d.nn_power_t);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    return FWGPU_OK;
+}
+
+// Regressor::learn for a model with a dense head, over `count` examples: sub-batches of at most head_batch examples
+// (the concurrency ramp shrinks the first ones) go through   LR/FFM forward -> head -> LR/FFM update.
+// cta != nullptr: raw records through k_learn_fixed_cta, leftovers translated (tp_left) and run through k_learn;
+// cta == nullptr: meta / lr_ent / ffm_ent already hold the `count` translated examples.
+static fwgpu_status head_learn(fwgpu_ctx *c, uint32_t count, int update, uint32_t n_cap, uint32_t lr_cap, const FixedCtaParams *cta,
+                               const TranslateParams *tp_left)
+{
+    fwgpu_status st;
+    const uint32_t cap_rows = std::min<uint32_t>(c->head_batch, std::max<uint32_t>(count, 1));
+    if ((st = ensure(c, c->hX, (size_t)cap_rows * c->ldx * 4))) return st;
+    if ((st = ensure(c, c->hdX, (size_t)cap_rows * c->ldx * 4))) return st;
+    for (size_t l = 0; l + 1 < c->head.size(); l++) {
+        if ((st = ensure(c, c->hH[l], (size_t)cap_rows * c->head[l].n_out * 4))) return st;
+        if ((st = ensure(c, c->hdZ[l], (size_t)cap_rows * c->head[l].n_out * 4))) return st;
+    }
+    if ((st = ensure(c, c->h_label, (size_t)cap_rows * 4))) return st;
+    if ((st = ensure(c, c->h_imp, (size_t)cap_rows * 4))) return st;
+    if ((st = ensure(c, c->h_outidx, (size_t)cap_rows * 4))) return st;
+    if ((st = ensure(c, c->h_dy, (size_t)cap_rows * 4))) return st;
+    LearnParams p;
+    int T; size_t smem;
+    if ((st = make_learn_params(c, n_cap, update, lr_cap, p, T, smem))) return st;
+    const size_t smem_cta = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 8 + 64;
+    uint32_t done = 0;
+    while (done < count) {
+        uint32_t rows = std::min<uint32_t>(count - done, cap_rows);
+        if (update && c->ramp_div != 0xffffffffu && !c->ramp_finished) {
+            // Every example of a sub-batch moves EVERY dense weight, so aligned gradients add up: AdaGrad's combined step on a
+            // weight is ~ lr * B / sqrt(n) after n examples and the layer's fan-in multiplies the curvature it acts on.  The
+            // sub-batch therefore grows like sqrt(n) (on top of the linear cold-start ramp of the sparse tables), DESIGN.md.
+            const uint64_t seen = c->examples_seen;
+            uint64_t cap = std::max<uint64_t>(seen / c->ramp_div, 1);
+            if (c->head_ramp_mul > 0.0) cap = std::min<uint64_t>(cap, std::max<uint64_t>((uint64_t)(c->head_ramp_mul * sqrt((double)seen)), 1));
+            rows = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(rows, cap), std::max<uint64_t>(2 * seen, c->ramp_div) - seen);
+            if (cap >= c->head_batch) c->ramp_finished = true;
+        }
+        if (update && c->max_inflight) rows = std::min(rows, c->max_inflight);
+        HeadIO io{};
+        io.X = (float *)c->hX.p; io.dX = (const float *)c->hdX.p; io.ldx = c->ldx; io.n_lr_out = c->d.num_combos;
+        io.row_label = (float *)c->h_label.p; io.row_importance = (float *)c->h_imp.p; io.row_out_index = (uint32_t *)c->h_outidx.p;
+        io.dy = (const float *)c->h_dy.p; io.row_base = done;
+        LearnParams q = p;
+        q.io = io; q.exact_order = 0; q.max_groups = 0;
+        uint32_t full_groups = 0;
+        for (int phase = 1; phase <= (update ? 2 : 1); phase++) {
+            q.phase = phase; q.update = phase == 2 ? 1 : 0;
+            if (cta) {
+                FixedCtaParams cp = *cta;
+                cp.ex_begin = done; cp.n_examples = rows; cp.io = io; cp.update = q.update; cp.max_groups = 0;
+                cudaError_t e;
+                {
+                    ProfScope ps(c, 0);
+                    if (phase == 1) {
+                        CUDA_TRY(c, cudaMemsetAsync(cp.leftover_cnt, 0, 16, c->stream));
+                        e = launch_fixed_cta<2, 1>(c, cp, smem_cta, &full_groups);
+                    } else e = launch_fixed_cta<2, 2>(c, cp, smem_cta, &full_groups);
+                }
+                if (e != cudaSuccess) { c->set_error(std::string("k_learn_fixed_cta launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+                if (phase == 1) { // records the fused kernel cannot take: translate them once, both passes use the result
+                    TranslateParams tp = *tp_left;
+                    tp.n_examples = rows;
+                    ProfScope ps(c, 1);
+                    k_translate<<<(rows + 255) / 256, 256, 0, c->stream>>>(tp);
+                    c->launches++;
+                }
+                q.meta = p.meta; q.n_examples = rows; q.n_examples_dev = cp.leftover_cnt;
+            } else {
+                q.meta = p.meta + done; q.n_examples = rows; q.n_examples_dev = nullptr;
+            }
+            if ((st = dispatch_learn(c, q, T, smem, &full_groups))) return st;
+            if (phase == 1 && (st = head_pass(c, rows, update))) return st;
+        }
+        if (update) c->examples_seen += rows;
+        done += rows;
+    }
+    return FWGPU_OK;
 }
 
 // ---- CSR batch entry --------------------------------------------------------------------------
@@ -693,6 +944,35 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
     tp.ffm_k = c->d.ffm_k;
     tp.lr_stride = lr_stride; tp.ffm_stride = ffm_stride;
     tp.meta = (ExMeta *)c->meta.p; tp.lr_ent = (uint4 *)c->lr_ent.p; tp.ffm_ent = (uint4 *)c->ffm_ent.p; tp.err_flag = c->err_flag;
+    if (run_learn && !c->head.empty()) {
+        // dense head: two passes around the head's GEMMs per sub-batch (head_learn)
+        const bool use_cta = c->fast_ok && c->fast_cta && c->fast_enabled;
+        if (use_cta) {
+            if ((st = ensure(c, c->leftover, (size_t)(count + 4) * 4))) return st;
+            uint32_t *left_cnt = (uint32_t *)c->leftover.p, *left_idx = left_cnt + 4;
+            FixedCtaParams cp{};
+            cp.lr = c->lr; cp.ffm_w = c->ffm_w; cp.ffm_acc = c->ffm_acc; cp.lut_lr = c->lut_dev; cp.lut_ffm = c->lut_dev + FWGPU_LUT_SIZE;
+            cp.records = rv.dev_records; cp.rec_off = rv.dev_rec_off; cp.off_base = rv.off_base; cp.fixed_len = rv.fixed_len;
+            cp.F = c->F; cp.k = c->k; cp.Fk = c->Fk; cp.cpr = c->Fk / 4;
+            cp.div_cpr = make_fastdiv(std::max<uint32_t>(cp.cpr, 1)); cp.div_k4 = make_fastdiv(std::max<uint32_t>(c->k / 4, 1)); cp.div_F = make_fastdiv(std::max<uint32_t>(c->F, 1));
+            cp.field_ns = c->d_field_ns; cp.n_combos = c->d.n_combos; cp.combo_off = c->d_combo_off; cp.combo_ns = c->d_combo_ns;
+            cp.combo_weight = c->d_combo_weight; cp.add_constant = c->d.add_constant; cp.lr_mask = tp.lr_mask; cp.ffm_mask = tp.ffm_mask;
+            cp.optimizer = c->optimizer; cp.lr_lr = c->d.learning_rate; cp.lr_mpt = -c->d.power_t; cp.ffm_lr = c->d.ffm_learning_rate; cp.ffm_mpt = -c->d.ffm_power_t;
+            cp.preds = (float *)c->preds.p; cp.leftover_idx = left_idx; cp.leftover_cnt = left_cnt;
+            tp.ex_list = left_idx; tp.ex_count = left_cnt;
+            if ((st = head_learn(c, count, update, ffm_stride, lr_stride, &cp, &tp))) return st;
+        } else {
+            {
+                ProfScope ps(c, 1);
+                k_translate<<<(count + 255) / 256, 256, 0, c->stream>>>(tp);
+                c->launches++;
+            }
+            CUDA_TRY(c, cudaGetLastError());
+            if ((st = head_learn(c, count, update, ffm_stride, lr_stride, nullptr, nullptr))) return st;
+        }
+        if (preds_host) CUDA_TRY(c, cudaMemcpyAsync(preds_host, c->preds.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream));
+        return FWGPU_OK;
+    }
     const bool use_fast = run_learn && c->fast_ok && c->fast_enabled && c->ramp_div < 0x7fffffffu;
     if (use_fast) {
         // fused kernel on the raw records; records it cannot take are listed and go through the general path below
@@ -734,7 +1014,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 cp.combo_weight = fp.combo_weight; cp.add_constant = fp.add_constant; cp.lr_mask = fp.lr_mask; cp.ffm_mask = fp.ffm_mask;
                 cp.optimizer = fp.optimizer; cp.lr_lr = fp.lr_lr; cp.lr_mpt = fp.lr_mpt; cp.ffm_lr = fp.ffm_lr; cp.ffm_mpt = fp.ffm_mpt;
                 cp.update = update; cp.preds = fp.preds; cp.leftover_idx = left_idx; cp.leftover_cnt = left_cnt; cp.max_groups = cap;
-                const size_t smem_cta = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 4 + 64;
+                const size_t smem_cta = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 8 + 64;
                 ProfScope ps(c, 0);
                 switch (c->fast_ub) {
                 case 1: e = launch_fixed_cta<1>(c, cp, smem_cta, &full_groups); break;
@@ -952,6 +1232,10 @@ extern "C" fwgpu_status fwgpu_block_len(const fwgpu_ctx *c, int block, uint64_t 
     uint64_t n = 0, bytes = 0;
     if (block == FWGPU_BLOCK_LR) { n = c->lr_len; bytes = n * (sgd ? 4 : 8); }
     else if (block == FWGPU_BLOCK_FFM) { n = c->ffm_len; bytes = n * (sgd ? 4 : 8); }
+    else if (block >= FWGPU_BLOCK_NN0 && (size_t)(block - FWGPU_BLOCK_NN0) < c->head.size()) {
+        const auto &L = c->head[block - FWGPU_BLOCK_NN0];
+        n = (uint64_t)(L.n_in + 1) * L.n_out; bytes = n * (sgd ? 4 : 8); // block_neural.rs:414-438
+    }
     else return FWGPU_ERR_INVALID;
     if (n_weights) *n_weights = n;
     if (n_bytes) *n_bytes = bytes;
@@ -975,6 +1259,10 @@ extern "C" fwgpu_status fwgpu_export_block(fwgpu_ctx *c, int block, void *dst, u
             c->launches++;
             CUDA_TRY(c, cudaMemcpyAsync(dst, c->csr.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
         }
+    } else if (block >= FWGPU_BLOCK_NN0) { // weights, then accumulators (block_neural.rs:426-438)
+        const auto &L = c->head[block - FWGPU_BLOCK_NN0];
+        CUDA_TRY(c, cudaMemcpyAsync(dst, c->head_w + L.off, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (!sgd) CUDA_TRY(c, cudaMemcpyAsync((char *)dst + n * 4, c->head_acc + L.off, n * 4, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (n == 0) return FWGPU_OK;
         CUDA_TRY(c, cudaMemcpyAsync(dst, c->ffm_w, n * 4, cudaMemcpyDeviceToHost, c->stream)); // weights, then accumulators (block_ffm.rs:835-848)
@@ -1001,6 +1289,15 @@ extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *
             CUDA_TRY(c, cudaMemcpyAsync(c->csr.p, src, n * 4, cudaMemcpyHostToDevice, c->stream));
             const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? c->d.init_acc_gradient : 0.0f;
             k_lr_set_w<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr, (const float *)c->csr.p, n, acc0);
+            c->launches++;
+        }
+    } else if (block >= FWGPU_BLOCK_NN0) { // block_neural.rs:440-470
+        const auto &L = c->head[block - FWGPU_BLOCK_NN0];
+        CUDA_TRY(c, cudaMemcpyAsync(c->head_w + L.off, src, n * 4, cudaMemcpyHostToDevice, c->stream));
+        if (with_acc) CUDA_TRY(c, cudaMemcpyAsync(c->head_acc + L.off, (const char *)src + n * 4, n * 4, cudaMemcpyHostToDevice, c->stream));
+        else if (!sgd) {
+            const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? c->d.nn_init_acc_gradient : 0.0f;
+            k_fill<<<c->num_sms, 256, 0, c->stream>>>(c->head_acc + L.off, n, acc0);
             c->launches++;
         }
     } else {

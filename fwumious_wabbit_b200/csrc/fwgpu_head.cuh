@@ -1,0 +1,191 @@
+// fwgpu_head.cuh -- sm_100a device code for the dense head of the "one" topology (BASELINE config 5):
+//   x = [LR combo outputs, triangle(FFM outputs)]  -> copy -> hidden layers (BlockNeuronLayer + BlockRELU)
+//   -> join [h, x] -> one neuron (init One) -> sigmoid          (regressor.rs:191-320)
+// replacing, for a sub-batch of B examples evaluated against one weight snapshot,
+//   BlockNeuronLayer::forward_backward   (block_neural.rs:196-341)
+//   BlockRELU                            (block_relu.rs:79-111)
+//   BlockCopy / BlockJoin                (block_misc.rs:435-519)
+//   BlockSigmoid                         (block_loss_functions.rs:105-153)
+//
+// The reference walks one example at a time: for every neuron j and input i it does
+//   g = g_j * x_i ; acc_ji += g^2 ; w_ji -= g * LUT[acc_ji]        (block_neural.rs:266-305)
+// The device evaluates B examples per pass (B = the examples in flight, 1 in sequential/parity mode):
+//   forward   H_l = act(H_{l-1} W_l^T + b_l)                       one tiled fp32 GEMM per layer (bias + ReLU fused)
+//   backward  dH_{l-1} = (dZ_l W_l) .* relu'                       one GEMM per layer (mask / direct path fused)
+//   update    G1_ji = sum_b g_bj x_bi ,  G2_ji = sum_b (g_bj x_bi)^2      one GEMM per layer computing BOTH sums
+//             acc_ji += G2_ji ; w_ji -= G1_ji * LUT[acc_ji]               (per-example squared gradients, as AdaGrad
+//                                                                          would have accumulated them one by one)
+// For B = 1 every sum has one term and the arithmetic is the reference's, rounding included.
+// All contractions are fp32 FFMA on purpose: predictions must stay within 1e-5 of the reference, which single-pass TF32
+// does not give; a 3xTF32 tcgen05 version is the planned replacement for these tiles.
+#pragma once
+#include "fwgpu_kernels.cuh"
+
+namespace fwgpu {
+
+enum { HEAD_EPI_BIAS_ACT = 0, HEAD_EPI_MASK = 1, HEAD_EPI_ADD_DIRECT = 2, HEAD_EPI_SUMS = 3 };
+
+struct HeadGemmParams {
+    const float *A; uint32_t lda;   // A(m,k): A_T ? A[k*lda + m] : A[m*lda + k]
+    const float *B; uint32_t ldb;   // B(n,k): B_T ? B[k*ldb + n] : B[n*ldb + k]
+    float *C; uint32_t ldc;         // C[m*ldc + n]
+    uint32_t M, N, K;
+    uint32_t k_split;               // HEAD_EPI_SUMS: rows of K handled per blockIdx.z
+    // epilogues
+    const float *bias; int relu;    // BIAS_ACT: C = act(acc + bias[n]); a ReLU-clamped output is stored as -0.0f (its mask bit)
+    const float *mask_src; uint32_t ld_mask; int mask_on; // MASK: C = mask_src[m][n] is -0.0f ? 0 : acc    (block_relu.rs:101-108)
+    const float *direct_w; const float *dy;               // ADD_DIRECT: C = acc + direct_w[n] * dy[m]     (block_misc.rs:452-473)
+    float *G1, *G2; float *G1_bias, *G2_bias;             // SUMS: atomicAdd into G1/G2[m*ldc + n]; bias sums from A alone
+};
+
+// 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread.
+template <bool A_T, bool B_T, int EPI>
+__global__ void __launch_bounds__(256) k_head_gemm(const HeadGemmParams p)
+{
+    constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+    __shared__ __align__(16) float As[BK][BM + PAD];
+    __shared__ __align__(16) float Bs[BK][BN + PAD];
+    const uint32_t tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    uint32_t k_begin = 0, k_end = p.K;
+    if (EPI == HEAD_EPI_SUMS) { k_begin = blockIdx.z * p.k_split; k_end = min(p.K, k_begin + p.k_split); }
+    float acc[4][4], acc2[4][4], bsum[4], bsum2[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        bsum[i] = bsum2[i] = 0.0f;
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = acc2[i][j] = 0.0f;
+    }
+    for (uint32_t k0 = k_begin; k0 < k_end; k0 += BK) {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const uint32_t e = tid + 256 * r;
+            {
+                const uint32_t kk = A_T ? e / BM : e % BK, mm = A_T ? e % BM : e / BK;
+                const uint32_t gm = m0 + mm, gk = k0 + kk;
+                float v = 0.0f;
+                if (gm < p.M && gk < k_end) v = A_T ? p.A[(size_t)gk * p.lda + gm] : p.A[(size_t)gm * p.lda + gk];
+                As[kk][mm] = v;
+            }
+            {
+                const uint32_t kk = B_T ? e / BN : e % BK, nn = B_T ? e % BN : e / BK;
+                const uint32_t gn = n0 + nn, gk = k0 + kk;
+                float v = 0.0f;
+                if (gn < p.N && gk < k_end) v = B_T ? p.B[(size_t)gk * p.ldb + gn] : p.B[(size_t)gn * p.ldb + gk];
+                Bs[kk][nn] = v;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                if (EPI == HEAD_EPI_SUMS) { bsum[i] += a[i]; bsum2[i] = fmaf(a[i], a[i], bsum2[i]); }
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    if (EPI == HEAD_EPI_SUMS) {
+                        const float g = __fmul_rn(a[i], b[j]); // the per-example gradient g_j * x_i (block_neural.rs:268-269)
+                        acc[i][j] += g;
+                        acc2[i][j] += __fmul_rn(g, g);          // two roundings like optimizer.rs:148-151
+                    } else {
+                        acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t gm = m0 + ty * 4 + i;
+        if (gm >= p.M) continue;
+        if (EPI == HEAD_EPI_SUMS && blockIdx.x == 0 && tx == 0 && p.G1_bias) {
+            if (bsum[i] != 0.0f || bsum2[i] != 0.0f) { atomicAdd(p.G1_bias + gm, bsum[i]); atomicAdd(p.G2_bias + gm, bsum2[i]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t gn = n0 + tx * 4 + j;
+            if (gn >= p.N) continue;
+            const size_t o = (size_t)gm * p.ldc + gn;
+            if (EPI == HEAD_EPI_BIAS_ACT) {
+                float y = __fadd_rn(p.bias[gn], acc[i][j]);          // output = bias, then sgemv adds W x (block_neural.rs:207-220)
+                if (p.relu && y < 0.0f) y = -0.0f;                   // block_relu.rs:88-97: output 0, mask 0
+                p.C[o] = y;
+            } else if (EPI == HEAD_EPI_MASK) {
+                float v = acc[i][j];
+                if (p.mask_on && __float_as_uint(p.mask_src[(size_t)gm * p.ld_mask + gn]) == 0x80000000u) v = 0.0f;
+                p.C[o] = v;
+            } else if (EPI == HEAD_EPI_ADD_DIRECT) {
+                p.C[o] = __fadd_rn(acc[i][j], __fmul_rn(p.direct_w[gn], p.dy[gm]));
+            } else {
+                if (acc[i][j] != 0.0f || acc2[i][j] != 0.0f) { atomicAdd(p.G1 + o, acc[i][j]); atomicAdd(p.G2 + o, acc2[i][j]); }
+            }
+        }
+    }
+}
+
+// Final neuron (one output, inputs [h, x]) + sigmoid + logloss gradient, one warp per example
+// (block_neural.rs:196-222 with num_neurons = 1, block_loss_functions.rs:105-153), and -- when updating -- the
+// gradient of the last hidden layer's pre-activations: dZ[b][j] = w_out[j] * g_b * relu'(h_bj).
+struct HeadFinalParams {
+    const float *H; uint32_t ldh, n_h;   // last hidden layer's outputs
+    const float *X; uint32_t ldx, n_x;   // the head's input (direct path)
+    const float *w;                      // final neuron: [n_h + n_x] weights, then the bias
+    const float *label, *importance;     // per row
+    const uint32_t *out_index;           // where the prediction of row b goes (nullptr: preds[b])
+    float *preds; float *dy; float *dZ; uint32_t ldz;
+    uint32_t n_rows; int update; int h_relu;
+};
+__global__ void __launch_bounds__(256) k_head_final(const HeadFinalParams p)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t b = warp; b < p.n_rows; b += n_warps) {
+        const float *h = p.H + (size_t)b * p.ldh, *x = p.X + (size_t)b * p.ldx;
+        float s = 0.0f;
+        for (uint32_t i = lane; i < p.n_h; i += 32) s = fmaf(p.w[i], h[i], s);
+        for (uint32_t i = lane; i < p.n_x; i += 32) s = fmaf(p.w[p.n_h + i], x[i], s);
+        s = warp_sum(s);
+        const float y = __fadd_rn(p.w[p.n_h + p.n_x], s);
+        const float label = p.label[b], importance = p.importance[b];
+        float pr, g;
+        if (isnan(y)) { pr = logistic(0.0f); g = 0.0f; }
+        else if (y < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+        else if (y > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+        else { pr = logistic(y); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
+        if (!(p.update && importance != 0.0f)) g = 0.0f; // regressor.rs:366-370: no update for this example
+        if (lane == 0) { p.preds[p.out_index ? p.out_index[b] : b] = pr; p.dy[b] = g; }
+        if (p.update) {
+            float *dz = p.dZ + (size_t)b * p.ldz;
+            for (uint32_t j = lane; j < p.n_h; j += 32) {
+                float v = __fmul_rn(p.w[j], g);
+                if (p.h_relu && __float_as_uint(h[j]) == 0x80000000u) v = 0.0f;
+                dz[j] = v;
+            }
+        }
+    }
+}
+
+// acc += G2 ; w -= G1 * step(acc)  over every head parameter at once; clears G1/G2 for the next sub-batch
+// (optimizer.rs:35-37, 76-89, 147-156 with the nn_* hyper-parameters, block_neural.rs:108-109).
+__global__ void __launch_bounds__(256) k_head_apply(float *w, float *acc, float *G1, float *G2, size_t n, uint32_t optimizer,
+                                                    const float *__restrict__ lut, float lr, float mpt)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float g1 = G1[i], g2 = G2[i];
+        if (g1 == 0.0f && g2 == 0.0f) continue;
+        G1[i] = 0.0f; G2[i] = 0.0f;
+        float upd;
+        if (optimizer == OPT_SGD) upd = __fmul_rn(g1, lr);
+        else {
+            const float a = __fadd_rn(acc[i], g2);
+            acc[i] = a;
+            upd = opt_step(optimizer, g1, a, lut, lr, mpt);
+        }
+        w[i] = __fsub_rn(w[i], upd);
+    }
+}
+
+} // namespace fwgpu

@@ -38,6 +38,22 @@ struct __align__(16) ExMeta {
 
 enum { OPT_SGD = 0, OPT_FLEX = 1, OPT_LUT = 2 };
 
+// Models with a dense head (regressor.rs:191-320) run the LR/FFM blocks in two passes around the head's GEMMs:
+//   PHASE 1  gather + forward only: row b of X receives the head's input [LR combo outputs, triangle(FFM outputs)]
+//            (block_lr.rs:28-47, block_ffm.rs:219-261, block_misc.rs:862-884) plus the example's label / importance;
+//   PHASE 2  gather again + update: the gradient of every input comes from row b of dX (what the head's backward pass left
+//            on the tape), so each field pair has its own gradient instead of the single sigmoid gradient g
+//            (block_misc.rs:814-833 mirrors d_tri onto out[f][z] and out[z][f]; block_ffm.rs:265-288; block_lr.rs:135-151).
+// PHASE 0 is the fused single pass of head-less models.  Row b = example index - row_base.
+struct HeadIO {
+    float *X; const float *dX; uint32_t ldx;
+    uint32_t n_lr_out;             // number of LR outputs = num_combos; triangle outputs follow
+    float *row_label, *row_importance; uint32_t *row_out_index;
+    const float *dy;               // PHASE 2: the sigmoid gradient of row b (0 = nothing to update)
+    uint32_t row_base;
+};
+__device__ __forceinline__ uint32_t tri_index(uint32_t a, uint32_t b) { const uint32_t f = a > b ? a : b, z = a > b ? b : a; return f * (f + 1) / 2 + z; }
+
 struct LearnParams {
     // tables (HBM)
     float2 *lr;          // {w, acc} x (1 << bit_precision)            block_lr.rs:19-25
@@ -66,6 +82,8 @@ struct LearnParams {
     uint32_t lr_cap;        // LR hashes staged in shared memory for the duplicate check (0 = read them from global)
     int simple_update;      // debug knob: one chunk at a time (ATOMG -> REDG) instead of rounds of four
     int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
+    int phase;              // 0 = fused single pass; 1 / 2 = the two passes around a dense head (HeadIO)
+    HeadIO io;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -202,6 +220,9 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
         }
         float part = 0.0f;
         bool overlap = false;
+        const uint32_t row = p.phase ? m.out_index - p.io.row_base : 0;
+        float *xrow = p.phase == 1 ? p.io.X + (size_t)row * p.io.ldx : nullptr;
+        const float *dxr = p.phase == 2 ? p.io.dX + (size_t)row * p.io.ldx : nullptr;
 
         const bool lr_staged = nlr <= p.lr_cap;
         if (lr_staged) for (uint32_t i = tg; i < nlr; i += T) lrh[i] = __ldg(&le[i].x); // visible after the next group_sync
@@ -285,16 +306,18 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
             // ---- forward: FFM outputs through the triangle (block_ffm.rs:219-261, block_misc.rs:862-884) ----
             // sum over z<f of 2*out[f][z] + out[f][f], with out[f][z] = 0.5*sum_k C[f][zk..]*C[z][fk..]
             const uint32_t FF = F * F;
-            for (uint32_t idx = tg; idx < FF; idx += T) {
+            for (uint32_t idx = tg; p.phase != 2 && idx < FF; idx += T) {
                 const uint32_t f = fdiv(idx, p.div_F), z = idx - f * F;
                 if (z < f) {
                     // 2 * out[f][z] = sum_q w_f[z][q] * (v * contra) with separate roundings (block_ffm.rs:246-257)
                     const float *a = C + f * Fk + z * k, *b = C + z * Fk + f * k;
                     float s = 0.0f;
                     for (uint32_t q = 0; q < k; q++) s = __fadd_rn(s, __fmul_rn(a[q], b[q]));
-                    part += s;
+                    if (p.phase == 1) xrow[p.io.n_lr_out + tri_index(f, z)] = s;
+                    else part += s;
                 } else if (z == f) {
                     const uint32_t b0 = fstart[f], b1 = fstart[f + 1];
+                    if (p.phase == 1 && b1 - b0 <= 1) xrow[p.io.n_lr_out + tri_index(f, f)] = 0.0f;
                     if (b1 - b0 > 1) { // intra-field pairs of a multi-valued field; a lone feature contributes exactly 0
                         const float *cf = C + f * Fk + f * k;
                         float s = 0.0f;
@@ -306,17 +329,33 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                                 s = __fadd_rn(s, __fmul_rn(wq, g_));
                             }
                         }
-                        part += 0.5f * s;
+                        if (p.phase == 1) xrow[p.io.n_lr_out + tri_index(f, f)] = __fmul_rn(s, 0.5f);
+                        else part += 0.5f * s;
                     }
                 }
             }
         }
 
         // ---- LR forward (block_lr.rs:28-47) -------------------------------------------------------
-        for (uint32_t i = tg; i < nlr; i += T) {
-            uint4 e = __ldg(le + i);
-            float2 cell = __ldcg(p.lr + e.x);
-            part += __fmul_rn(cell.x, __uint_as_float(e.y));
+        if (p.phase == 0) {
+            for (uint32_t i = tg; i < nlr; i += T) {
+                uint4 e = __ldg(le + i);
+                float2 cell = __ldcg(p.lr + e.x);
+                part += __fmul_rn(cell.x, __uint_as_float(e.y));
+            }
+        } else if (p.phase == 1) {
+            // one output per combo, features added in buffer order (block_lr.rs:38-45); entries arrive in combo order
+            for (uint32_t c = tg; c < p.io.n_lr_out; c += T) {
+                float comb = 0.0f;
+                for (uint32_t i = 0; i < nlr; i++) {
+                    const uint4 e = __ldg(le + i);
+                    if (e.z == c) comb = __fadd_rn(comb, __fmul_rn(__ldcg(p.lr + e.x).x, __uint_as_float(e.y)));
+                }
+                xrow[c] = comb;
+            }
+            if (tg == 0) { p.io.row_label[row] = m.label; p.io.row_importance[row] = m.importance; p.io.row_out_index[row] = m.out_index; }
+            group_sync<T>(gib); // C / staging are reused by the next example
+            continue;
         }
 
         // ---- reduce over the group -----------------------------------------------------------------
@@ -376,11 +415,16 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
 
         // ---- sigmoid + logloss gradient (block_loss_functions.rs:105-153) ---------------------------
         float pr, g;
-        if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
-        else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
-        else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
-        else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(m.label, pr), m.importance); }
-        if (tg == 0) p.preds[m.out_index] = pr;
+        if (p.phase == 2) g = __ldg(p.io.dy + row); // the head's sigmoid already produced the prediction and the gradient
+        else {
+            if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+            else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+            else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+            else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(m.label, pr), m.importance); }
+            if (tg == 0) p.preds[m.out_index] = pr;
+        }
+        // d_out[f][z]: the sigmoid gradient itself, or with a dense head what its backward pass left for that pair
+        auto gpair = [&](uint32_t f, uint32_t z) -> float { return p.phase == 2 ? __ldg(dxr + p.io.n_lr_out + tri_index(f, z)) : g; };
 
         // regressor.rs:366-370: update && importance != 0; a zero gradient changes nothing
         const bool do_update = p.update && m.importance != 0.0f && g != 0.0f;
@@ -398,12 +442,13 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                         // a lone feature's own-field block: the gradient is exactly 0, the reference's update a no-op
                         if (own && fstart[f + 1] - fstart[f] == 1) return;
                         const float *cp = C + zc * Fk + f * k + q0;
+                        const float gz = gpair(f, zc);
                         bool any = false;
 #pragma unroll
                         for (int j = 0; j < VEC; j++) {
                             float cz = cp[j];
                             if (own) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q0 + j], v));
-                            grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
+                            grad[j] = __fmul_rn(gz, __fmul_rn(v, cz));
                             gg[j] = __fmul_rn(grad[j], grad[j]);
                             any = any || grad[j] != 0.0f;
                         }
@@ -418,7 +463,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                             // self-interaction must cancel to exactly 0 like the reference's (block_ffm.rs:238-240);
                             // AdaGrad with a zero initial accumulator turns any residue into a full-size step.
                             if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
-                            grad[j] = __fmul_rn(g, __fmul_rn(v, cz));
+                            grad[j] = __fmul_rn(gpair(f, z), __fmul_rn(v, cz));
                             gg[j] = __fmul_rn(grad[j], grad[j]);
                         }
                     }
@@ -458,7 +503,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                             const uint32_t z = fdiv(x, p.div_k), q = x - z * k;
                             float cz = C[z * Fk + f * k + q];
                             if (z == f) cz = __fsub_rn(cz, __fmul_rn(d[e * k + q], v));
-                            gr[j] = __fmul_rn(g, __fmul_rn(v, cz));
+                            gr[j] = __fmul_rn(gpair(f, z), __fmul_rn(v, cz));
                             any = any || (gr[j] != 0.0f);
                         }
                         return any; // an all-zero gradient (own block of a lone feature, absent field) changes nothing
@@ -517,7 +562,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
                     if (lr_staged && j != i && lrh[j] != e.x) continue;
                     const uint4 ej = (j == i) ? e : __ldg(le + j);
                     if (ej.x != e.x) continue;
-                    const float grad = g * __uint_as_float(ej.y);
+                    const float grad = (p.phase == 2 ? __ldg(dxr + ej.z) : g) * __uint_as_float(ej.y);
                     float upd;
                     if (p.optimizer == OPT_SGD) upd = grad * p.lr_lr;
                     else {
@@ -780,6 +825,7 @@ struct FixedCtaParams {
     float *preds;
     uint32_t *leftover_idx, *leftover_cnt;
     uint32_t max_groups;
+    HeadIO io;                     // dense-head models only (PHASE 1 / 2)
 };
 
 __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
@@ -788,15 +834,15 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
 }
 
-template <int UB>
+template <int UB, int PHASE>
 __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t F = p.F, k = p.k, Fk = p.Fk, cpr = p.cpr, k4 = k >> 2;
     float *C = reinterpret_cast<float *>(smem_raw);
-    uint32_t *slots = reinterpret_cast<uint32_t *>(C + (size_t)F * Fk);
-    float *red = reinterpret_cast<float *>(slots + F);
+    uint32_t *slots2 = reinterpret_cast<uint32_t *>(C + (size_t)F * Fk); // [2][F], double-buffered by record parity: a thread
+    float *red = reinterpret_cast<float *>(slots2 + 2 * F);               // may still read record i's slots while another stores i+1's
     const uint32_t n_chunks = F * cpr;
     const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u); // <= 256 (host checks)
     uint32_t n_blocks = gridDim.x;
@@ -809,8 +855,9 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
     const uint32_t ex_end = p.ex_begin + p.n_examples;
     uint32_t slot_next = (ex < ex_end && tid < F) ? __ldg(rec_ptr(ex) + 3 + my_field_ns) : 0x80000000u;
 
-    for (; ex < ex_end; ex += n_blocks) {
+    for (uint32_t it = 0; ex < ex_end; ex += n_blocks, it++) {
         const uint32_t *rec = rec_ptr(ex);
+        uint32_t *slots = slots2 + (it & 1) * F;
         // ---- translate (feature_buffer.rs:178-338), in-place slots only ----
         const uint32_t slot = slot_next;
         bool bad = tid < F && (slot & 0x80000000u) && slot != 0x80000000u;
@@ -834,9 +881,13 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
             slot_next = (nx < ex_end && tid < F) ? __ldg(rec_ptr(nx) + 3 + my_field_ns) : 0x80000000u;
         }
         if (any_bad) {
-            if (tid == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+            // PHASE 2 walks the same records as PHASE 1: the leftover list already holds this one
+            if (PHASE != 2 && tid == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
             continue; // uniform
         }
+        const uint32_t row = ex - p.io.row_base;
+        float g_row = 0.0f;
+        if (PHASE == 2) { g_row = __ldg(p.io.dy + row); if (g_row == 0.0f) continue; } // uniform: nothing to update
 
         // ---- gather: HBM -> shared memory, 16 B per cp.async, everything in flight at once ----
         for (uint32_t idx = tid; idx < n_chunks; idx += 256) {
@@ -846,16 +897,24 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
             if (sl != 0x80000000u) cp_async16(dst, p.ffm_w + (sl & p.ffm_mask) + 4 * c);
             else *reinterpret_cast<float4 *>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const float lr_w = lr_ok ? __ldcg(p.lr + lr_h).x : 0.0f;
+        const float lr_w = (PHASE != 2 && lr_ok) ? __ldcg(p.lr + lr_h).x : 0.0f;
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncthreads();
 
+        float g;
+        if (PHASE != 2) {
         // ---- forward ----
         float part = lr_ok ? __fmul_rn(lr_w, lr_v) : 0.0f;
+        float *xr = PHASE == 1 ? p.io.X + (size_t)row * p.io.ldx : nullptr;
+        if (PHASE == 1) {
+            if (tid < n_lr) xr[tid] = part; // one feature of value 1.0 per combo: out[combo] = w * combo weight (block_lr.rs:38-45)
+            if (tid == 0) { p.io.row_label[row] = label; p.io.row_importance[row] = importance; p.io.row_out_index[row] = ex; }
+        }
         const uint32_t FF = F * F;
         for (uint32_t idx = tid; idx < FF; idx += 256) {
             const uint32_t f = fdiv(idx, p.div_F), z = idx - f * F;
+            if (PHASE == 1 && z == f) xr[p.io.n_lr_out + tri_index(f, f)] = 0.0f; // a lone feature has no intra-field term
             if (z < f) {
                 const float4 *a = reinterpret_cast<const float4 *>(C + f * Fk + z * k), *b = reinterpret_cast<const float4 *>(C + z * Fk + f * k);
                 float sd = 0.0f;
@@ -864,9 +923,11 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
                     sd = __fadd_rn(sd, __fmul_rn(x.x, y.x)); sd = __fadd_rn(sd, __fmul_rn(x.y, y.y));
                     sd = __fadd_rn(sd, __fmul_rn(x.z, y.z)); sd = __fadd_rn(sd, __fmul_rn(x.w, y.w));
                 }
-                part += sd;
+                if (PHASE == 1) xr[p.io.n_lr_out + tri_index(f, z)] = sd; // = 2 * out[f][z] (block_misc.rs:871-881)
+                else part += sd;
             }
         }
+        if (PHASE == 1) continue; // uniform; the next iteration's barrier protects C
         float wsum = warp_sum(part);
         if (lane == 0) red[warp] = wsum;
         __syncthreads();
@@ -874,13 +935,17 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
 #pragma unroll
         for (int w_ = 0; w_ < 8; w_++) wsum += red[w_];
 
-        float pr, g;
+        float pr;
         if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
         else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
         else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
         else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
         if (tid == 0) p.preds[ex] = pr;
         if (!(p.update && importance != 0.0f && g != 0.0f)) continue; // uniform; the next iteration's barrier protects C
+        } else {
+            g = g_row;
+        }
+        const float *dxr = PHASE == 2 ? p.io.dX + (size_t)row * p.io.ldx : nullptr;
 
         // ---- update: UB chunks per thread and round ----
         for (uint32_t idx0 = tid; idx0 < n_chunks; idx0 += UB * 256) {
@@ -897,7 +962,8 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
                 const uint32_t sl = slots[e];
                 if (z == e || sl == 0x80000000u) continue; // own-field chunk: exactly zero gradient; absent field: no row
                 const float4 pv = *reinterpret_cast<const float4 *>(C + z * Fk + e * k + 4 * q4);
-                gr[u] = make_float4(__fmul_rn(g, pv.x), __fmul_rn(g, pv.y), __fmul_rn(g, pv.z), __fmul_rn(g, pv.w));
+                const float gz = PHASE == 2 ? __ldg(dxr + p.io.n_lr_out + tri_index(e, z)) : g; // d_out[e][z] (block_misc.rs:823-832)
+                gr[u] = make_float4(__fmul_rn(gz, pv.x), __fmul_rn(gz, pv.y), __fmul_rn(gz, pv.z), __fmul_rn(gz, pv.w));
                 if (gr[u].x == 0.0f && gr[u].y == 0.0f && gr[u].z == 0.0f && gr[u].w == 0.0f) continue; // partner absent
                 on[u] = true;
                 addr[u] = (sl & p.ffm_mask) + 4 * c;
@@ -922,7 +988,7 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
         // ---- LR update (block_lr.rs:135-151) ----
         if (lr_ok) {
             float *cell = reinterpret_cast<float *>(p.lr + lr_h);
-            const float grad = __fmul_rn(g, lr_v);
+            const float grad = __fmul_rn(PHASE == 2 ? __ldg(dxr + tid) : g, lr_v);
             float upd;
             if (p.optimizer == OPT_SGD) upd = __fmul_rn(grad, p.lr_lr);
             else {

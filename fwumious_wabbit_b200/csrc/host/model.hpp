@@ -243,6 +243,26 @@ inline void mi_to_desc(const ModelInstanceH &m, const VwMap &vw, bool immutable,
     d.optimizer = m.optimizer; d.immutable = immutable ? 1 : 0;
     d.ffm_init_width = m.ffm_init_width; d.ffm_init_zero_band = m.ffm_init_zero_band; d.ffm_init_center = m.ffm_init_center;
     d.nn_num_layers = (uint32_t)m.nn_layers.size();
+    if (d.nn_num_layers > FWGPU_MAX_NN_LAYERS) throw std::runtime_error("too many --nn_layers for the CUDA head");
+    if (d.nn_num_layers && m.nn_topology != "one") throw std::runtime_error("only nn topology \"one\" is implemented by the CUDA head");
+    for (uint32_t i = 0; i < d.nn_num_layers; i++) { // per-layer defaults: regressor.rs:217-251
+        d.nn_width[i] = 20; d.nn_relu[i] = 0; d.nn_init[i] = FWGPU_NN_INIT_HU;
+        for (auto &kv : m.nn_layers[i]) {
+            if (kv.first == "width") d.nn_width[i] = (uint32_t)strtoul(kv.second.c_str(), nullptr, 10);
+            else if (kv.first == "activation") {
+                if (kv.second == "relu") d.nn_relu[i] = 1;
+                else if (kv.second != "none") throw std::runtime_error("unknown nn activation type: \"" + kv.second + "\"");
+            } else if (kv.first == "init") {
+                if (kv.second == "xavier") d.nn_init[i] = FWGPU_NN_INIT_XAVIER; else if (kv.second == "hu") d.nn_init[i] = FWGPU_NN_INIT_HU;
+                else if (kv.second == "one") d.nn_init[i] = FWGPU_NN_INIT_ONE; else if (kv.second == "zero") d.nn_init[i] = FWGPU_NN_INIT_ZERO;
+                else throw std::runtime_error("unknown nn initialization type: \"" + kv.second + "\"");
+            } else if (kv.first == "dropout" || kv.first == "maxnorm") {
+                if (strtof(kv.second.c_str(), nullptr) != 0.0f) throw std::runtime_error("--nn " + kv.first + " is not implemented by the CUDA head");
+            } else if (kv.first == "layernorm") {
+                if (kv.second != "none") throw std::runtime_error("--nn layernorm is not implemented by the CUDA head");
+            } else throw std::runtime_error("Unknown --nn parameter for layer number " + std::to_string(i) + " : " + kv.first);
+        }
+    }
     f.ns_is_f32.assign(vw.num_namespaces, 0);
     for (auto &e : vw.entries) if (e.index < vw.num_namespaces) f.ns_is_f32[e.index] = e.f32 ? 1 : 0;
     f.combo_off.assign(1, 0);

@@ -83,6 +83,12 @@ class ModelInstance:
         for i, layer in enumerate(self.nn_layers[: _lib.MAX_NN_LAYERS]):
             d.nn_width[i] = int(layer.get("width", 20))
             d.nn_relu[i] = 1 if layer.get("activation", "none") == "relu" else 0
+            d.nn_init[i] = {"xavier": 0, "hu": 1, "one": 2, "zero": 3}[layer.get("init", "hu")]
+            unsupported = {k_: v for k_, v in layer.items() if k_ in ("dropout", "maxnorm") and float(v) != 0.0}
+            if layer.get("layernorm", "none") != "none" or unsupported:
+                raise ValueError(f"--nn {i}: dropout / maxnorm / layernorm are not implemented by the CUDA head")
+        if self.nn_layers and self.nn_topology != "one":
+            raise ValueError("only nn topology \"one\" is implemented by the CUDA head")
         nns = self.num_namespaces
         for ns_list, _ in self.feature_combo_descs:
             nns = max(nns, max(ns_list) + 1 if ns_list else 0)

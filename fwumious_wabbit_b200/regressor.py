@@ -189,6 +189,22 @@ class Regressor:
         else:
             self.import_block(_lib.BLOCK_FFM, np.concatenate([w, acc]).astype(np.float32), True)
 
+    # dense head: layer l < len(mi.nn_layers) is hidden layer l, l == len(mi.nn_layers) the final neuron
+    def nn_layer_count(self):
+        return len(self.mi.nn_layers) + 1 if self.mi.nn_layers else 0
+
+    def get_nn(self, layer):
+        """(weights, accumulators or None) of a head layer: (n_in + 1) * n_out floats, biases last (block_neural.rs:83-86)."""
+        n, nbytes = self.block_len(_lib.BLOCK_NN0 + layer)
+        raw = self.export_block(_lib.BLOCK_NN0 + layer)
+        return (raw[:n], raw[n:]) if nbytes == n * 8 else (raw[:n], None)
+
+    def set_nn(self, layer, w, acc=None):
+        if acc is None:
+            self.import_block(_lib.BLOCK_NN0 + layer, w, with_optimizer_state=False)
+        else:
+            self.import_block(_lib.BLOCK_NN0 + layer, np.concatenate([w, acc]).astype(np.float32), True)
+
     def set_lr_table(self, table):
         table = np.ascontiguousarray(table, dtype=np.float32)
         self.import_block(_lib.BLOCK_LR, table.reshape(-1), with_optimizer_state=(table.ndim == 2 and table.shape[1] == 2))

@@ -74,6 +74,11 @@ class Workload:
         F = len(mi.ffm_fields) if mi.ffm_k else 0
         n_lr = mi.num_combos
         inp = 4 * (3 + self.n_namespaces)
+        if train and mi.nn_layers:
+            # two passes around the head: the rows are read twice (4 B/slot more), the head input X is written and read
+            # and its gradient dX written and read (4 floats per input); head weights are per sub-batch, not per example
+            x_len = n_lr + F * (F + 1) // 2
+            return 20 * F * F * mi.ffm_k + 16 * n_lr + inp + 4 + 16 * x_len
         if train:
             return 16 * F * F * mi.ffm_k + 16 * n_lr + inp + 4
         return 4 * F * F * mi.ffm_k + 4 * n_lr + inp + 4
@@ -96,7 +101,7 @@ def _mi(n_ns, *, ffm_k, ffm_bits, bits, interactions=(), lr=0.1, ffm_lr=0.05, po
 
 def workload(name: str) -> Workload:
     """BASELINE.json configs: c1 (LR only), c2 (FFM k=4, 8 fields), c3 (FFM k=8, 39 fields, Criteo shape),
-    c4 (c3 with ffm_bit_precision 28)."""
+    c4 (c3 with ffm_bit_precision 28), c5 (c3 + 2x256 ReLU head)."""
     if name == "c1":
         # benchmark/generate.py shape with 6 random namespaces -> A..H; --interactions AB, -b 18, power_t 0
         mi = _mi(8, ffm_k=0, ffm_bits=18, bits=18, interactions=[(0, 1)], lr=0.1, power_t=0.0)
@@ -106,6 +111,15 @@ def workload(name: str) -> Workload:
         mi = _mi(8, ffm_k=4, ffm_bits=20, bits=18)
         return Workload("c2", mi, NS_LETTERS[:8], [100000] * 8,
                         "FFM k=4, 8 fields (one namespace each, 1e5 Zipf ids), ffm_bit_precision=20, -b 18")
+    if name == "c5":
+        w = workload("c3")
+        # --nn_layers 2 --nn 0:width:256 --nn 0:activation:relu --nn 1:width:256 --nn 1:activation:relu;
+        # nn_learning_rate / nn_power_t / nn_init_acc_gradient default to the ffm values (model_instance.rs:418-428)
+        w.mi.nn_layers = [{"width": "256", "activation": "relu"}, {"width": "256", "activation": "relu"}]
+        w.mi.nn_learning_rate, w.mi.nn_power_t, w.mi.nn_init_acc_gradient = w.mi.ffm_learning_rate, w.mi.ffm_power_t, w.mi.ffm_init_acc_gradient
+        w.name = "c5"
+        w.description = w.description.replace("FFM k=8", "Deep FFM k=8 + 2x256 ReLU head (topology one)")
+        return w
     if name in ("c3", "c4"):
         card = [100] * 13 + [10 ** (3 + (j % 5)) for j in range(26)]  # 13 binned numeric + 26 categorical 1e3..1e7
         # -l 0.05 --ffm_learning_rate 0.02 --ffm_init_acc_gradient 0.1: with 39 fields the reference's defaults

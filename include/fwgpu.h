@@ -41,8 +41,15 @@ enum {
 
 /* model_instance.rs:24-29 Optimizer */
 enum { FWGPU_OPT_SGD = 0, FWGPU_OPT_ADAGRAD_FLEX = 1, FWGPU_OPT_ADAGRAD_LUT = 2 };
-/* weight blocks in the order regressor.rs:426-442 serialises them */
+/* weight blocks in the order regressor.rs:426-442 serialises them; FWGPU_BLOCK_NN0 + i = hidden layer i,
+ * FWGPU_BLOCK_NN0 + nn_num_layers = the final neuron.  A layer holds (n_in + 1) * n_out weights: row-major per neuron,
+ * then the biases (block_neural.rs:83-86), followed by as many accumulators (block_neural.rs:426-438). */
 enum { FWGPU_BLOCK_LR = 0, FWGPU_BLOCK_FFM = 1, FWGPU_BLOCK_NN0 = 2 /* + layer index */ };
+
+/* block_neural.rs:29-35 InitType.  Hu / Xavier draw from rand_xoshiro + rand_distr in the reference, which no test
+ * observes and which cannot be reproduced without those crates ("parity unpinned"): fwgpu draws uniform
+ * weights of the same variance from a fixed LCG.  Parity runs import identical weights (fwgpu_import_block). */
+enum { FWGPU_NN_INIT_XAVIER = 0, FWGPU_NN_INIT_HU = 1, FWGPU_NN_INIT_ONE = 2, FWGPU_NN_INIT_ZERO = 3 };
 
 #define FWGPU_MAX_NN_LAYERS 8
 #define FWGPU_LUT_SIZE 2048 /* optimizer.rs:101-102 */
@@ -66,9 +73,10 @@ typedef struct fwgpu_model_desc {
     uint32_t immutable;         /* 1 = forward-only regressor (regressor.rs:471-534): SGD, no accumulators */
     float ffm_init_width, ffm_init_zero_band, ffm_init_center; /* block_ffm.rs:796-822 */
     /* dense head, topology "one" (regressor.rs:191-320); 0 layers = none */
-    uint32_t nn_num_layers;
-    uint32_t nn_width[FWGPU_MAX_NN_LAYERS];
-    uint32_t nn_relu[FWGPU_MAX_NN_LAYERS];
+    uint32_t nn_num_layers;                 /* hidden layers; the final single neuron (init One) is implied   */
+    uint32_t nn_width[FWGPU_MAX_NN_LAYERS]; /* --nn i:width:W (default 20, regressor.rs:228-232)               */
+    uint32_t nn_relu[FWGPU_MAX_NN_LAYERS];  /* --nn i:activation:relu|none                                      */
+    uint32_t nn_init[FWGPU_MAX_NN_LAYERS];  /* FWGPU_NN_INIT_* (--nn i:init:..., default hu; block_neural.rs:367-412) */
     /* translate spec (only needed for fwgpu_*_records) */
     uint32_t n_namespaces;        /* vwmap.rs:31 num_namespaces                               */
     const uint8_t *ns_is_f32;     /* [n_namespaces] NamespaceFormat::F32 (vwmap.rs:16-20)      */

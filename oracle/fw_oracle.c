@@ -606,6 +606,61 @@ static float sigmoid_block(const float *inputs, uint32_t n, float label, float i
     return p;
 }
 
+/* One BlockNeuronLayer forward (+ BlockRELU when the layer has one): block_neural.rs:196-222, block_relu.rs:79-99.
+ * The layer's input must already be in L->in. */
+static void layer_forward(nn_layer *L)
+{
+    size_t bias_offset = (size_t)L->n_in * L->n_out;
+    for (uint32_t j = 0; j < L->n_out; j++) {
+        /* output = bias; sgemv('T') adds W x (block_neural.rs:207-220).  MKL's internal
+         * summation order is unspecified; sequential here (pinned to 5e-6 only). */
+        float acc = 0.0f;
+        const float *wj = L->w + (size_t)j * L->n_in;
+        for (uint32_t i = 0; i < L->n_in; i++) acc += wj[i] * L->in[i];
+        float y = L->w[bias_offset + j] + acc;
+        if (L->relu) { /* block_relu.rs:88-97: w < 0 -> 0 (mask 0) else w (mask 1) */
+            if (y < 0.0f) { L->out[j] = 0.0f; L->mask[j] = 0.0f; }
+            else { L->out[j] = y; L->mask[j] = 1.0f; }
+        } else {
+            L->out[j] = y; L->mask[j] = 1.0f;
+        }
+    }
+}
+
+/* One BlockNeuronLayer backward (block_neural.rs:252-341): up[n_out] = gradient of the layer's outputs (after the
+ * layer's own relu backward), out_err[n_in] receives the gradient of its inputs (from the pre-update weights). */
+static void layer_backward(fwo_opt *opt, nn_layer *L, const float *up, float *out_err, uint64_t example_number)
+{
+    for (uint32_t i = 0; i < L->n_in; i++) out_err[i] = 0.0f;
+    size_t bias_offset = (size_t)L->n_in * L->n_out;
+    for (uint32_t j = 0; j < L->n_out; j++) {
+        float general_gradient = up[j] * 1.0f; /* dropout_inv == 1 */
+        if (general_gradient == 0.0f) continue;
+        size_t j_offset = (size_t)j * L->n_in;
+        for (uint32_t i = 0; i < L->n_in; i++) {
+            float feature_value = L->in[i];
+            float gradient = general_gradient * feature_value;
+            float update = opt_update(opt, gradient, &L->acc[i + j_offset]);
+            out_err[i] += L->w[i + j_offset] * general_gradient;
+            L->w[i + j_offset] -= update;
+        }
+        {
+            float gradient = general_gradient * 1.0f;
+            float update = opt_update(opt, gradient, &L->acc[bias_offset + j]);
+            L->w[bias_offset + j] -= update;
+        }
+        if (L->maxnorm != 0.0f && example_number % 10 == 0) { /* block_neural.rs:307-320 */
+            float wsq = 0.000001f;
+            for (uint32_t i = 0; i < L->n_in; i++) { float w = L->w[i + j_offset]; wsq += w * w; }
+            float norm = sqrtf(wsq);
+            if (norm > L->maxnorm) {
+                float scaling = L->maxnorm / norm;
+                for (uint32_t i = 0; i < L->n_in; i++) L->w[i + j_offset] *= scaling;
+            }
+        }
+    }
+}
+
 /* Head forward (training and predict share it: block_neural.rs:196-222, block_relu.rs:79-99).
  * x: [x_len] input; returns the single output of the final neuron. */
 static float head_forward(fwo_regressor *r, const float *x, uint32_t x_len)
@@ -615,27 +670,9 @@ static float head_forward(fwo_regressor *r, const float *x, uint32_t x_len)
     for (uint32_t l = 0; l < r->n_layers; l++) {
         nn_layer *L = &r->layers[l];
         int final = (l + 1 == r->n_layers);
-        if (final) { /* join [h, x] */
-            memcpy(L->in, in, sizeof(float) * n_in);
-            memcpy(L->in + n_in, x, sizeof(float) * x_len);
-        } else {
-            memcpy(L->in, in, sizeof(float) * n_in);
-        }
-        size_t bias_offset = (size_t)L->n_in * L->n_out;
-        for (uint32_t j = 0; j < L->n_out; j++) {
-            /* output = bias; sgemv('T') adds W x (block_neural.rs:207-220).  MKL's internal
-             * summation order is unspecified; sequential here (pinned to 5e-6 only). */
-            float acc = 0.0f;
-            const float *wj = L->w + (size_t)j * L->n_in;
-            for (uint32_t i = 0; i < L->n_in; i++) acc += wj[i] * L->in[i];
-            float y = L->w[bias_offset + j] + acc;
-            if (L->relu) { /* block_relu.rs:88-97: w < 0 -> 0 (mask 0) else w (mask 1) */
-                if (y < 0.0f) { L->out[j] = 0.0f; L->mask[j] = 0.0f; }
-                else { L->out[j] = y; L->mask[j] = 1.0f; }
-            } else {
-                L->out[j] = y; L->mask[j] = 1.0f;
-            }
-        }
+        memcpy(L->in, in, sizeof(float) * n_in);
+        if (final) memcpy(L->in + n_in, x, sizeof(float) * x_len); /* join [h, x] */
+        layer_forward(L);
         in = L->out;
         n_in = L->n_out;
     }
@@ -655,35 +692,7 @@ static void head_backward(fwo_regressor *r, float g_out, uint32_t x_len, float *
         nn_layer *L = &r->layers[l];
         if (gcap[l] < L->n_in + 1) { free(gbuf[l]); gcap[l] = L->n_in + 16; gbuf[l] = (float *)malloc(sizeof(float) * gcap[l]); }
         float *out_err = gbuf[l];
-        for (uint32_t i = 0; i < L->n_in; i++) out_err[i] = 0.0f;
-        size_t bias_offset = (size_t)L->n_in * L->n_out;
-        for (uint32_t j = 0; j < L->n_out; j++) {
-            float general_gradient = up[j] * 1.0f; /* dropout_inv == 1 */
-            if (L->relu) general_gradient = up[j]; /* relu already applied below */
-            if (general_gradient == 0.0f) continue;
-            size_t j_offset = (size_t)j * L->n_in;
-            for (uint32_t i = 0; i < L->n_in; i++) {
-                float feature_value = L->in[i];
-                float gradient = general_gradient * feature_value;
-                float update = opt_update(&r->opt_nn, gradient, &L->acc[i + j_offset]);
-                out_err[i] += L->w[i + j_offset] * general_gradient;
-                L->w[i + j_offset] -= update;
-            }
-            {
-                float gradient = general_gradient * 1.0f;
-                float update = opt_update(&r->opt_nn, gradient, &L->acc[bias_offset + j]);
-                L->w[bias_offset + j] -= update;
-            }
-            if (L->maxnorm != 0.0f && example_number % 10 == 0) { /* block_neural.rs:307-320 */
-                float wsq = 0.000001f;
-                for (uint32_t i = 0; i < L->n_in; i++) { float w = L->w[i + j_offset]; wsq += w * w; }
-                float norm = sqrtf(wsq);
-                if (norm > L->maxnorm) {
-                    float scaling = L->maxnorm / norm;
-                    for (uint32_t i = 0; i < L->n_in; i++) L->w[i + j_offset] *= scaling;
-                }
-            }
-        }
+        layer_backward(&r->opt_nn, L, up, out_err, example_number);
         if (l == (int)r->n_layers - 1) {
             /* final neuron's inputs are [h, x]: split */
             uint32_t h_len = L->n_in - x_len;
@@ -700,6 +709,35 @@ static void head_backward(fwo_regressor *r, float g_out, uint32_t x_len, float *
             for (uint32_t i = 0; i < x_len; i++) d_x[i] = out_err[i] + direct[i];
         }
     }
+}
+
+/* Test hook: ONE neuron layer (optionally followed by a relu) in isolation, driven the way the reference's own unit
+ * tests drive it (block_neural.rs:507-581, block_relu.rs:156-173): constant input x, an observe block that returns
+ * the outputs and feeds back d_out as the gradient.  outs: [n_steps][n_out] forward outputs of each step (every step
+ * updates); d_in: [n_in] input gradient of the last step.  Pins layer_forward / layer_backward to those goldens. */
+int fwo_test_neuron_layer(uint32_t optimizer, float lr, float power_t, float init_acc, uint32_t n_in, uint32_t n_out, uint32_t init,
+                          uint32_t relu, const float *x, const float *d_out, uint32_t n_steps, float *outs, float *d_in)
+{
+    fwo_opt opt;
+    opt_init(&opt, optimizer, lr, power_t, init_acc);
+    nn_layer L;
+    memset(&L, 0, sizeof(L));
+    L.n_in = n_in; L.n_out = n_out; L.relu = relu; L.init = init;
+    size_t len = (size_t)(n_in + 1) * n_out;
+    L.w = (float *)malloc(sizeof(float) * len); L.acc = (float *)malloc(sizeof(float) * len);
+    L.in = (float *)malloc(sizeof(float) * n_in); L.out = (float *)malloc(sizeof(float) * n_out); L.mask = (float *)malloc(sizeof(float) * n_out);
+    float *up = (float *)malloc(sizeof(float) * n_out), *err = (float *)malloc(sizeof(float) * (n_in + 1));
+    for (size_t i = 0; i < len; i++) { L.w[i] = init == FWO_NN_INIT_ZERO ? 0.0f : 1.0f; L.acc[i] = opt_initial_data(&opt); }
+    for (uint32_t j = 0; j < n_out; j++) L.w[(size_t)n_in * n_out + j] = 0.0f; /* block_neural.rs:409-412 */
+    for (uint32_t s = 0; s < n_steps; s++) {
+        memcpy(L.in, x, sizeof(float) * n_in);
+        layer_forward(&L);
+        for (uint32_t j = 0; j < n_out; j++) { outs[(size_t)s * n_out + j] = L.out[j]; up[j] = L.mask[j] * d_out[j]; }
+        layer_backward(&opt, &L, up, err, s);
+    }
+    if (d_in) memcpy(d_in, err, sizeof(float) * n_in);
+    free(L.w); free(L.acc); free(L.in); free(L.out); free(L.mask); free(up); free(err);
+    return 0;
 }
 
 /* LR forward, block_lr.rs:28-47 */

@@ -149,6 +149,9 @@ uint32_t fwo_nn_layer_len(const fwo_regressor *r, uint32_t layer); /* (n_in+1)*n
 float *fwo_nn_weights(fwo_regressor *r, uint32_t layer);
 float *fwo_nn_acc(fwo_regressor *r, uint32_t layer);
 const float *fwo_lut(const fwo_regressor *r, int which /*0 lr, 1 ffm, 2 nn*/);
+/* one neuron layer (+ relu) in isolation, as block_neural.rs:507-581 / block_relu.rs:156-173 test it */
+int fwo_test_neuron_layer(uint32_t optimizer, float lr, float power_t, float init_acc, uint32_t n_in, uint32_t n_out, uint32_t init,
+                          uint32_t relu, const float *x, const float *d_out, uint32_t n_steps, float *outs, float *d_in);
 
 /* ---- batch drivers used by tests and the CPU baseline ----
  * Fixed-capacity CSR batch identical to include/fwgpu.h's fwgpu_batch (plain arrays). */

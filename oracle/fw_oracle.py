@@ -135,6 +135,9 @@ def lib():
         f.argtypes = [C.c_void_p, C.c_uint32]
     L.fwo_lut.restype = C.POINTER(C.c_float)
     L.fwo_lut.argtypes = [C.c_void_p, C.c_int]
+    L.fwo_test_neuron_layer.restype = C.c_int
+    L.fwo_test_neuron_layer.argtypes = [C.c_uint32, C.c_float, C.c_float, C.c_float, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                        C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]
     L.fwo_learn_batch_sequential.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(C.c_float), C.c_int]
     L.fwo_hogwild_run.restype = C.c_double
     L.fwo_hogwild_run.argtypes = [C.c_void_p, C.POINTER(TranslateSpec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
@@ -154,6 +157,18 @@ def lut_build(lr, power_t, init_acc):
     out = np.zeros(2048, dtype=np.float32)
     lib().fwo_lut_build(lr, power_t, init_acc, out.ctypes.data_as(C.POINTER(C.c_float)))
     return out
+
+
+def neuron_layer_test(optimizer, lr, power_t, init_acc, n_in, n_out, init, relu, x, d_out, n_steps):
+    """One neuron layer (+ relu) in isolation (block_neural.rs:507-581, block_relu.rs:156-173): returns
+    (outs[n_steps, n_out], d_in[n_in] of the last step)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    d_out = np.ascontiguousarray(d_out, dtype=np.float32)
+    outs = np.zeros((n_steps, n_out), np.float32)
+    d_in = np.zeros(n_in, np.float32)
+    lib().fwo_test_neuron_layer(optimizer, lr, power_t, init_acc, n_in, n_out, init, 1 if relu else 0, x.ctypes.data, d_out.ctypes.data,
+                                n_steps, outs.ctypes.data, d_in.ctypes.data)
+    return outs, d_in
 
 
 def merand48(seed: int) -> float:

@@ -462,6 +462,63 @@ def test_triangle_and_neuron_blocks():
     eq(p, 0.5)  # LR weights start at zero -> x = 0 -> everything 0
 
 
+def test_neuron_layer_goldens():
+    # block_neural.rs:507-537 test_simple: const input [2.0], one neuron init One, SGD nn lr 0.1, observe gradient 1.0:
+    # 2.0, then 1.5 (w = 1 - 0.1*2 = 0.8, bias = -0.1)
+    outs, d_in = fo.neuron_layer_test(fo.OPT_SGD, 0.1, 0.0, 0.0, 1, 1, fo.NN_INIT_ONE, False, [2.0], [1.0], 2)
+    eq(outs[0, 0], 2.0)
+    eq(outs[1, 0], 1.5)
+    # block_neural.rs:539-581 test_two_neurons: both neurons see 2.0, then 1.5
+    outs, _ = fo.neuron_layer_test(fo.OPT_SGD, 0.1, 0.0, 0.0, 1, 2, fo.NN_INIT_ONE, False, [2.0], [1.0, 1.0], 2)
+    assert outs[0].tolist() == [2.0, 2.0]
+    eq(outs[1, 0], 1.5)
+    eq(outs[1, 1], 1.5)
+    # the input gradient uses the PRE-update weights (block_neural.rs:283-284): first step 1.0 * 1.0 per neuron
+    _, d_in = fo.neuron_layer_test(fo.OPT_SGD, 0.1, 0.0, 0.0, 1, 2, fo.NN_INIT_ONE, False, [2.0], [1.0, 1.0], 1)
+    eq(d_in[0], 2.0)
+    # block_relu.rs:156-173: relu passes 2.0 and "doesn't learn" (no weights of its own); a clamped output blocks the gradient
+    outs, d_in = fo.neuron_layer_test(fo.OPT_SGD, 0.1, 0.0, 0.0, 1, 1, fo.NN_INIT_ONE, True, [-2.0], [1.0], 2)
+    assert outs[:, 0].tolist() == [0.0, 0.0] and d_in[0] == 0.0
+
+
+def test_head_matches_numpy_restatement():
+    """The oracle's whole head (copy -> layers -> join -> neuron -> sigmoid) against an independent numpy float32
+    restatement of regressor.rs:191-320 on random weights: forward value and every updated parameter."""
+    rng = np.random.default_rng(4)
+    r = fo.Regressor(learning_rate=0.1, power_t=0.0, nn_learning_rate=0.1, nn_power_t=0.0, optimizer=fo.OPT_SGD, bit_precision=8,
+                     num_combos=3, nn_layers=[{"width": 4, "activation": "relu"}, {"width": 3, "activation": "none"}])
+    r.lr_table[:, 0] = rng.normal(0, 0.5, r.lr_table.shape[0]).astype(np.float32)
+    for l in range(r.nn_layer_count):
+        r.nn_weights(l)[:] = rng.normal(0, 0.5, r.nn_weights(l).shape[0]).astype(np.float32)
+    fb = lr_fb([(1, 1.0, 0), (2, 2.0, 1), (3, 0.5, 2)])
+    fb.label = 1.0
+    f32 = np.float32
+    x = np.array([r.lr_table[1, 0] * f32(1.0), r.lr_table[2, 0] * f32(2.0), r.lr_table[3, 0] * f32(0.5)], f32)
+    W = [r.nn_weights(l).copy() for l in range(3)]
+    def layer(w, n_in, n_out, inp):
+        return (w[:n_in * n_out].reshape(n_out, n_in).astype(np.float64) @ inp.astype(np.float64)).astype(f32) + w[n_in * n_out:]
+    z0 = layer(W[0], 3, 4, x); h0 = np.where(z0 < 0, f32(0), z0)
+    h1 = layer(W[1], 4, 3, h0)
+    y = layer(W[2], 6, 1, np.concatenate([h1, x]))[0]
+    p_want = 1.0 / (1.0 + np.exp(-np.float64(y)))
+    p = r.learn(fb, True)
+    assert abs(p - p_want) < 2e-6, (p, p_want)
+    g = f32(-(1.0 - p))
+    # SGD lr 0.1: final neuron w -= 0.1 * g * in ; hidden layers through the pre-update weights
+    in2 = np.concatenate([h1, x])
+    w2 = W[2].copy(); w2[:6] -= f32(0.1) * g * in2; w2[6] -= f32(0.1) * g
+    np.testing.assert_allclose(r.nn_weights(2), w2, rtol=0, atol=1e-6)
+    d_h1 = W[2][:3] * g
+    w1 = W[1].copy(); w1[:12] -= (f32(0.1) * np.outer(d_h1, h0)).reshape(-1); w1[12:] -= f32(0.1) * d_h1
+    np.testing.assert_allclose(r.nn_weights(1), w1, rtol=0, atol=1e-6)
+    d_h0 = (W[1][:12].reshape(3, 4).T @ d_h1) * (z0 >= 0)
+    w0 = W[0].copy(); w0[:12] -= (f32(0.1) * np.outer(d_h0, x)).reshape(-1); w0[12:] -= f32(0.1) * d_h0
+    np.testing.assert_allclose(r.nn_weights(0), w0, rtol=0, atol=1e-6)
+    d_x = W[0][:12].reshape(4, 3).T @ d_h0 + W[2][3:6] * g   # BlockCopy backward adds both paths (block_misc.rs:452-473)
+    want_lr = [r_w - f32(0.1) * d * v for r_w, d, v in zip([x[0] / f32(1.0), x[1] / f32(2.0), x[2] / f32(0.5)], d_x, [1.0, 2.0, 0.5])]
+    np.testing.assert_allclose([r.lr_table[1, 0], r.lr_table[2, 0], r.lr_table[3, 0]], want_lr, rtol=0, atol=1e-6)
+
+
 def test_merand48_range_and_determinism():
     # parity unpinned (no reference test observes it) -- sanity only
     xs = [fo.merand48(i) for i in range(1000)]

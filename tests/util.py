@@ -114,3 +114,9 @@ def sync_tables_from_oracle(gpu_reg, ora):
             gpu_reg.import_block(_lib.BLOCK_FFM, np.concatenate([ora.ffm_weights, ora.ffm_acc]), True)
         else:
             gpu_reg.import_block(_lib.BLOCK_FFM, ora.ffm_weights.copy(), False)
+    for l in range(ora.nn_layer_count):
+        n, nbytes = gpu_reg.block_len(_lib.BLOCK_NN0 + l)
+        if nbytes == n * 8:
+            gpu_reg.import_block(_lib.BLOCK_NN0 + l, np.concatenate([ora.nn_weights(l), ora.nn_acc(l)]), True)
+        else:
+            gpu_reg.import_block(_lib.BLOCK_NN0 + l, ora.nn_weights(l).copy(), False)
