@@ -36,6 +36,8 @@ def parse_args():
     ap.add_argument("--cpu-sample", type=int, default=0, help="examples in the cpu_baseline sample (0 = default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sharded", action="store_true",
+                    help="N > 1: ONE model whose tables are hash-range-sharded over the N GPUs (NVLink peer memory) instead of N replicas")
     ap.add_argument("--predict-only", action="store_true", help="diagnostic: time the forward pass only (update = 0)")
     ap.add_argument("--uniform-ids", action="store_true", help="diagnostic: uniform feature ids instead of Zipf (no hot rows)")
     return ap.parse_args()
@@ -177,7 +179,9 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     w = synth.workload(args.workload)
     n = args.examples or DEFAULT_EXAMPLES[args.workload]
-    re = fw.Regressor(w.mi, device=local_rank)
+    sharded = args.sharded and world > 1
+    shard = (rank, world, f"/tmp/fwgpu_shard_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}") if sharded else None
+    re = fw.Regressor(w.mi, device=local_rank, shard=shard)
     stream = torch.cuda.ExternalStream(re.stream_ptr(), device=torch.device("cuda", local_rank))
 
     # every rank trains its own replica on a disjoint shard of the stream
@@ -314,7 +318,8 @@ def run_ours(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{w.name}: {w.description}" + (" [DIAGNOSTIC: uniform ids]" if args.uniform_ids else "") + (" [DIAGNOSTIC: predict only]" if args.predict_only else ""), "examples_per_step_per_gpu": n, "fresh_slices": n_slices,
-                       "parallelism": f"replicas x{world} (independent models, disjoint example shards)" if world > 1 else "single GPU",
+                       "parallelism": (f"one model, tables hash-range-sharded x{world} over NVLink peer memory, disjoint example shards" if sharded else
+                                       f"replicas x{world} (independent models, disjoint example shards)") if world > 1 else "single GPU",
                        "l2_policy": f"inputs larger than L2: {nbytes >> 20} MiB of records per step; table {(w.mi.ffm_k and ((1 << w.mi.ffm_bit_precision) * 8 >> 20))} MiB w+acc vs 126 MB L2 (c2's 8 MiB table is L2-resident by nature; the records are not)",
                        "optimizer": "AdagradLUT", "semantics": "Hogwild on device, chunked launches"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
@@ -329,6 +334,9 @@ def run_ours(args):
 
 
 def main():
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION/INFO; stdout carries exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FWGPU_KEEP_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = "WARN"
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)

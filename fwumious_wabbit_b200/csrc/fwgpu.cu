@@ -3,6 +3,7 @@
 #include "../../include/fwgpu.h"
 #include "fwgpu_kernels.cuh"
 #include "fwgpu_head.cuh"
+#include "fwgpu_shard.hpp"
 
 #include <algorithm>
 #include <cmath>
@@ -120,12 +121,18 @@ struct fwgpu_ctx {
     float *head_w = nullptr, *head_acc = nullptr, *head_G1 = nullptr, *head_G2 = nullptr;
     uint32_t x_len = 0, ldx = 0;  // head input: num_combos + F(F+1)/2 (regressor.rs:185-189), padded leading dimension
     uint32_t head_batch = 4096;   // examples per pass around the head's GEMMs = examples in flight
+    int head_tile = 0;            // FWGPU_HEAD_TILE: 0 = choose per GEMM, 64 = always 64 x 64 tiles
     double head_ramp_mul = 2.0;   // sub-batches grow as head_ramp_mul * sqrt(examples_seen) (0 = only the linear ramp)
     uint32_t head_rows_cap = 0;
     DevBuf hX, hdX, hH[FWGPU_MAX_NN_LAYERS], hdZ[FWGPU_MAX_NN_LAYERS], h_label, h_imp, h_outidx, h_dy;
+    // hash-range-sharded tables over the GPUs of one box (fwgpu_shard.hpp); null = everything in this GPU's HBM
+    ShardGroup *shard = nullptr;
+    ShardedArray sh_lr, sh_w, sh_acc;
     std::string err;
     void set_error(const std::string &s) { err = s; }
 };
+
+struct ShardCfg { uint32_t rank, world; const char *rendezvous; uint32_t timeout_ms; };
 
 static fwgpu_status ensure(fwgpu_ctx *c, DevBuf &b, size_t bytes)
 {
@@ -170,6 +177,11 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->shard) {
+        c->shard->destroy_array(c->sh_lr); c->shard->destroy_array(c->sh_w); c->shard->destroy_array(c->sh_acc);
+        delete c->shard;
+        c->lr = nullptr; c->ffm_w = nullptr; c->ffm_acc = nullptr;
+    }
     cudaFree(c->lr); cudaFree(c->ffm_w); cudaFree(c->ffm_acc); cudaFree(c->lut_dev);
     cudaFree(c->d_ns_is_f32); cudaFree(c->d_combo_off); cudaFree(c->d_combo_ns); cudaFree(c->d_field_off);
     cudaFree(c->d_field_ns); cudaFree(c->d_combo_weight);
@@ -188,7 +200,7 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     delete c;
 }
 
-static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_ctx *c)
+static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_ctx *c, const ShardCfg *sc)
 {
     int ndev = 0;
     cudaError_t e0 = cudaGetDeviceCount(&ndev);
@@ -279,19 +291,53 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
 
     // tables
     c->lr_len = 1ull << d.bit_precision;
-    CUDA_TRY(c, cudaMalloc((void **)&c->lr, c->lr_len * sizeof(float2)));
-    // initial_data(): Flex starts at init_acc (optimizer.rs:91-93), LUT at 0 (optimizer.rs:158-161)
-    const float lr_acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? d.init_acc_gradient : 0.0f;
-    k_init_lr<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr, c->lr_len, lr_acc0);
-    c->launches++;
     if (d.ffm_k > 0) {
         c->ffm_len = (1ull << d.ffm_bit_precision) + c->Fk; // block_ffm.rs:93-94
         c->ffm_alloc = c->ffm_len + 64;
-        CUDA_TRY(c, cudaMalloc((void **)&c->ffm_w, c->ffm_alloc * sizeof(float)));
-        if (c->optimizer != FWGPU_OPT_SGD) CUDA_TRY(c, cudaMalloc((void **)&c->ffm_acc, c->ffm_alloc * sizeof(float)));
+    }
+    // which elements this rank initialises: everything, or (sharded) the hash range it owns
+    uint64_t lr_lo = 0, lr_hi = c->lr_len, ffm_lo = 0, ffm_hi = c->ffm_alloc;
+    if (sc) {
+        if (d.nn_num_layers) { c->set_error("a dense head is replicated per GPU and cannot be combined with a sharded table yet"); return FWGPU_ERR_UNSUPPORTED; }
+        c->shard = new ShardGroup();
+        ShardGroup &g = *c->shard;
+        if (!g.start(sc->rank, sc->world, device, sc->rendezvous, sc->timeout_ms)) { c->set_error("shard group: " + g.error); return FWGPU_ERR_CUDA; }
+        std::vector<size_t> sizes;
+        auto range = [&](const ShardedArray &a, size_t elem, uint64_t n, uint64_t &lo, uint64_t &hi) {
+            lo = std::min<uint64_t>(a.offsets[g.rank] / elem, n);
+            hi = a.sizes[g.rank] ? std::min<uint64_t>((a.offsets[g.rank] + a.sizes[g.rank]) / elem, n) : lo;
+        };
+        shard_plan(c->lr_len * sizeof(float2), 0, g.world, g.granularity, sizes);
+        if (!g.create_array(c->sh_lr, sizes)) { c->set_error("sharded LR table: " + g.error); return FWGPU_ERR_CUDA; }
+        c->lr = (float2 *)c->sh_lr.va;
+        range(c->sh_lr, sizeof(float2), c->lr_len, lr_lo, lr_hi);
+        if (d.ffm_k > 0) {
+            shard_plan((1ull << d.ffm_bit_precision) * 4, (c->ffm_alloc - (1ull << d.ffm_bit_precision)) * 4, g.world, g.granularity, sizes);
+            if (!g.create_array(c->sh_w, sizes)) { c->set_error("sharded FFM weights: " + g.error); return FWGPU_ERR_CUDA; }
+            c->ffm_w = (float *)c->sh_w.va;
+            if (c->optimizer != FWGPU_OPT_SGD) {
+                if (!g.create_array(c->sh_acc, sizes)) { c->set_error("sharded FFM accumulators: " + g.error); return FWGPU_ERR_CUDA; }
+                c->ffm_acc = (float *)c->sh_acc.va;
+            }
+            range(c->sh_w, 4, c->ffm_alloc, ffm_lo, ffm_hi);
+        }
+    } else {
+        CUDA_TRY(c, cudaMalloc((void **)&c->lr, c->lr_len * sizeof(float2)));
+        if (d.ffm_k > 0) {
+            CUDA_TRY(c, cudaMalloc((void **)&c->ffm_w, c->ffm_alloc * sizeof(float)));
+            if (c->optimizer != FWGPU_OPT_SGD) CUDA_TRY(c, cudaMalloc((void **)&c->ffm_acc, c->ffm_alloc * sizeof(float)));
+        }
+    }
+    // initial_data(): Flex starts at init_acc (optimizer.rs:91-93), LUT at 0 (optimizer.rs:158-161)
+    const float lr_acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? d.init_acc_gradient : 0.0f;
+    if (lr_hi > lr_lo) {
+        k_init_lr<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr + lr_lo, lr_hi - lr_lo, lr_acc0);
+        c->launches++;
+    }
+    if (d.ffm_k > 0 && ffm_hi > ffm_lo) {
         const float ffm_acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? d.ffm_init_acc_gradient : 0.0f;
         const float one_over_k_root = 1.0f / sqrtf((float)d.ffm_k) / 50.0f; // block_ffm.rs:798
-        k_init_ffm<<<c->num_sms * 8, 256, 0, c->stream>>>(c->ffm_w, c->ffm_acc, (uint32_t)c->ffm_len, (uint32_t)c->ffm_alloc, one_over_k_root,
+        k_init_ffm<<<c->num_sms * 8, 256, 0, c->stream>>>(c->ffm_w, c->ffm_acc, (uint32_t)c->ffm_len, (uint32_t)ffm_lo, (uint32_t)ffm_hi, one_over_k_root,
                                                           ffm_acc0, d.ffm_init_width, d.ffm_init_zero_band, d.ffm_init_center);
         c->launches++;
     }
@@ -346,6 +392,7 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         }
         if (const char *t = getenv("FWGPU_HEAD_BATCH")) c->head_batch = std::max(1, atoi(t));
         if (const char *t = getenv("FWGPU_HEAD_RAMP_MUL")) c->head_ramp_mul = atof(t);
+        if (const char *t = getenv("FWGPU_HEAD_TILE")) c->head_tile = atoi(t);
     }
 
     fwgpu_status st;
@@ -383,21 +430,65 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         if (const char *t = getenv("FWGPU_MAX_INFLIGHT")) c->max_inflight = (uint32_t)strtoul(t, nullptr, 10);
     }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    // nobody trains before every shard is initialised
+    if (c->shard && !c->shard->barrier()) { c->set_error("shard group: " + c->shard->error); return FWGPU_ERR_CUDA; }
     return FWGPU_OK;
 }
 
-extern "C" fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **out)
+static fwgpu_status create_common(const fwgpu_model_desc *desc, int device, const ShardCfg *sc, fwgpu_ctx **out)
 {
     if (!desc || !out) { g_create_error = "null argument"; return FWGPU_ERR_INVALID; }
     *out = nullptr;
     fwgpu_ctx *c = new fwgpu_ctx();
-    fwgpu_status st = create_impl(desc, device, c);
+    fwgpu_status st;
+    try {
+        st = create_impl(desc, device, c, sc);
+    } catch (const std::exception &e) {
+        c->set_error(e.what());
+        st = FWGPU_ERR_INVALID;
+    }
     if (st != FWGPU_OK) {
         g_create_error = c->err;
         fwgpu_destroy(c);
         return st;
     }
     *out = c;
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **out) { return create_common(desc, device, nullptr, out); }
+
+extern "C" fwgpu_status fwgpu_create_sharded(const fwgpu_model_desc *desc, int device, uint32_t rank, uint32_t world, const char *rendezvous,
+                                             uint32_t timeout_ms, fwgpu_ctx **out)
+{
+    if (!rendezvous || world == 0 || rank >= world) { g_create_error = "bad shard arguments"; return FWGPU_ERR_INVALID; }
+    ShardCfg sc{rank, world, rendezvous, timeout_ms};
+    return create_common(desc, device, &sc, out);
+}
+
+extern "C" fwgpu_status fwgpu_shard_barrier(fwgpu_ctx *c)
+{
+    if (!c) return FWGPU_ERR_INVALID;
+    fwgpu_status st = fwgpu_sync(c); // this rank's updates have reached the owners' L2 before anyone moves on
+    if (st != FWGPU_OK) return st;
+    if (!c->shard) return FWGPU_OK;
+    if (!c->shard->barrier()) { c->set_error("shard group: " + c->shard->error); return FWGPU_ERR_CUDA; }
+    return FWGPU_OK;
+}
+
+extern "C" fwgpu_status fwgpu_shard_info(const fwgpu_ctx *c, uint32_t *rank, uint32_t *world, uint64_t *ffm_first, uint64_t *ffm_count)
+{
+    if (!c) return FWGPU_ERR_INVALID;
+    if (rank) *rank = c->shard ? c->shard->rank : 0;
+    if (world) *world = c->shard ? c->shard->world : 1;
+    uint64_t lo = 0, n = c->ffm_len;
+    if (c->shard && c->ffm_len) {
+        const ShardedArray &a = c->sh_w;
+        lo = std::min<uint64_t>(a.offsets[c->shard->rank] / 4, c->ffm_len);
+        n = std::min<uint64_t>((a.offsets[c->shard->rank] + a.sizes[c->shard->rank]) / 4, c->ffm_len) - lo;
+    }
+    if (ffm_first) *ffm_first = lo;
+    if (ffm_count) *ffm_count = n;
     return FWGPU_OK;
 }
 
@@ -660,19 +751,30 @@ template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *
 }
 
 // ---- dense head (fwgpu_head.cuh) ----------------------------------------------------------------
-template <bool A_T, bool B_T, int EPI> static void launch_head_gemm(fwgpu_ctx *c, HeadGemmParams &p)
+template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_gemm_tile(fwgpu_ctx *c, HeadGemmParams &p)
 {
     uint32_t splits = 1;
     if (EPI == HEAD_EPI_SUMS) {
         // the reduction runs over the sub-batch: split it so that the grid fills the machine about twice
-        const uint32_t tiles = ((p.M + 63) / 64) * ((p.N + 63) / 64);
+        const uint32_t tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
         splits = std::max<uint32_t>(1, std::min<uint32_t>((2 * (uint32_t)c->num_sms + tiles - 1) / tiles, (p.K + 63) / 64));
         p.k_split = (((p.K + splits - 1) / splits) + 15) / 16 * 16;
         splits = (p.K + p.k_split - 1) / p.k_split;
     }
-    dim3 grid((p.N + 63) / 64, (p.M + 63) / 64, splits);
-    k_head_gemm<A_T, B_T, EPI><<<grid, 256, 0, c->stream>>>(p);
+    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
+    k_head_gemm<A_T, B_T, EPI, BM, BN><<<grid, 256, 0, c->stream>>>(p);
     c->launches++;
+}
+
+// tile choice: 128 x 128 (8 x 8 outputs per thread, FFMA-bound) when that still gives every SM a block, else 64 x 64;
+// the gradient-sum GEMM keeps two accumulators per output, so its largest tile is 128 x 64
+template <bool A_T, bool B_T, int EPI> static void launch_head_gemm(fwgpu_ctx *c, HeadGemmParams &p)
+{
+    const uint64_t big_tiles = (uint64_t)((p.M + 127) / 128) * ((p.N + 127) / 128);
+    const bool small = c->head_tile == 64 || (c->head_tile == 0 && (p.M <= 64 || p.N <= 64 || (EPI != HEAD_EPI_SUMS && big_tiles < (uint64_t)c->num_sms * 3 / 4)));
+    if (small) launch_head_gemm_tile<A_T, B_T, EPI, 64, 64>(c, p);
+    else if constexpr (EPI == HEAD_EPI_SUMS) launch_head_gemm_tile<A_T, B_T, EPI, 128, 64>(c, p);
+    else launch_head_gemm_tile<A_T, B_T, EPI, 128, 128>(c, p);
 }
 
 // forward (+ backward and optimizer step when update) of the head over `rows` examples whose inputs sit in hX
@@ -1225,6 +1327,34 @@ extern "C" fwgpu_status fwgpu_dataset_learn(fwgpu_ctx *c, fwgpu_dataset *ds, uin
 }
 
 // ---- weights ----------------------------------------------------------------------------------
+// Device -> host copy of the first `bytes` of a table; a sharded table is copied owner range by owner range (a copy never
+// spans two physical allocations), remote ranges coming over NVLink.
+static cudaError_t table_d2h(fwgpu_ctx *c, void *dst, const void *src, size_t bytes, const ShardedArray &a)
+{
+    if (!c->shard || !a.va) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    for (uint32_t s = 0; s < c->shard->world; s++) {
+        const size_t lo = a.offsets[s], hi = std::min(lo + a.sizes[s], bytes);
+        if (hi <= lo) continue;
+        cudaError_t e = cudaMemcpyAsync((char *)dst + lo, (const char *)src + lo, hi - lo, cudaMemcpyDeviceToHost, c->stream);
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+// Host -> device copy of a whole-table payload: every rank of a sharded model is handed the same payload and writes the
+// range it owns (collective call; follow it with fwgpu_shard_barrier before training).
+static void own_range(const fwgpu_ctx *c, const ShardedArray &a, size_t bytes, size_t &lo, size_t &hi)
+{
+    lo = 0; hi = bytes;
+    if (c->shard && a.va) { lo = std::min(a.offsets[c->shard->rank], bytes); hi = std::min(a.offsets[c->shard->rank] + a.sizes[c->shard->rank], bytes); }
+}
+static cudaError_t table_h2d(fwgpu_ctx *c, void *dst, const void *src, size_t bytes, const ShardedArray &a)
+{
+    size_t lo, hi;
+    own_range(c, a, bytes, lo, hi);
+    if (hi <= lo) return cudaSuccess;
+    return cudaMemcpyAsync((char *)dst + lo, (const char *)src + lo, hi - lo, cudaMemcpyHostToDevice, c->stream);
+}
+
 extern "C" fwgpu_status fwgpu_block_len(const fwgpu_ctx *c, int block, uint64_t *n_weights, uint64_t *n_bytes)
 {
     if (!c) return FWGPU_ERR_INVALID;
@@ -1251,7 +1381,7 @@ extern "C" fwgpu_status fwgpu_export_block(fwgpu_ctx *c, int block, void *dst, u
     const bool sgd = c->optimizer == FWGPU_OPT_SGD;
     if (block == FWGPU_BLOCK_LR) {
         if (!sgd) { // {f32 w, f32 acc} x len, block_helpers.rs:23-28
-            CUDA_TRY(c, cudaMemcpyAsync(dst, c->lr, bytes, cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(c, table_d2h(c, dst, c->lr, bytes, c->sh_lr));
         } else {
             fwgpu_status st;
             if ((st = ensure(c, c->csr, n * 4))) return st;
@@ -1265,8 +1395,8 @@ extern "C" fwgpu_status fwgpu_export_block(fwgpu_ctx *c, int block, void *dst, u
         if (!sgd) CUDA_TRY(c, cudaMemcpyAsync((char *)dst + n * 4, c->head_acc + L.off, n * 4, cudaMemcpyDeviceToHost, c->stream));
     } else {
         if (n == 0) return FWGPU_OK;
-        CUDA_TRY(c, cudaMemcpyAsync(dst, c->ffm_w, n * 4, cudaMemcpyDeviceToHost, c->stream)); // weights, then accumulators (block_ffm.rs:835-848)
-        if (!sgd) CUDA_TRY(c, cudaMemcpyAsync((char *)dst + n * 4, c->ffm_acc, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, table_d2h(c, dst, c->ffm_w, n * 4, c->sh_w)); // weights, then accumulators (block_ffm.rs:835-848)
+        if (!sgd) CUDA_TRY(c, table_d2h(c, (char *)dst + n * 4, c->ffm_acc, n * 4, c->sh_acc));
     }
     return fwgpu_sync(c);
 }
@@ -1282,14 +1412,18 @@ extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *
     if (src_bytes < need) { c->set_error("import payload too small"); return FWGPU_ERR_INVALID; }
     if (with_acc) { c->examples_seen = std::max<uint64_t>(c->examples_seen, 1ull << 40); c->ramp_finished = true; }
     if (block == FWGPU_BLOCK_LR) {
-        if (with_acc) CUDA_TRY(c, cudaMemcpyAsync(c->lr, src, n * 8, cudaMemcpyHostToDevice, c->stream));
+        if (with_acc) CUDA_TRY(c, table_h2d(c, c->lr, src, n * 8, c->sh_lr));
         else {
             fwgpu_status st;
             if ((st = ensure(c, c->csr, n * 4))) return st;
             CUDA_TRY(c, cudaMemcpyAsync(c->csr.p, src, n * 4, cudaMemcpyHostToDevice, c->stream));
             const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? c->d.init_acc_gradient : 0.0f;
-            k_lr_set_w<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr, (const float *)c->csr.p, n, acc0);
-            c->launches++;
+            size_t lo, hi;
+            own_range(c, c->sh_lr, n * 8, lo, hi);
+            if (hi > lo) {
+                k_lr_set_w<<<c->num_sms * 4, 256, 0, c->stream>>>(c->lr + lo / 8, (const float *)c->csr.p + lo / 8, (hi - lo) / 8, acc0);
+                c->launches++;
+            }
         }
     } else if (block >= FWGPU_BLOCK_NN0) { // block_neural.rs:440-470
         const auto &L = c->head[block - FWGPU_BLOCK_NN0];
@@ -1302,12 +1436,16 @@ extern "C" fwgpu_status fwgpu_import_block(fwgpu_ctx *c, int block, const void *
         }
     } else {
         if (n == 0) return FWGPU_OK;
-        CUDA_TRY(c, cudaMemcpyAsync(c->ffm_w, src, n * 4, cudaMemcpyHostToDevice, c->stream));
-        if (with_acc) CUDA_TRY(c, cudaMemcpyAsync(c->ffm_acc, (const char *)src + n * 4, n * 4, cudaMemcpyHostToDevice, c->stream));
+        CUDA_TRY(c, table_h2d(c, c->ffm_w, src, n * 4, c->sh_w));
+        if (with_acc) CUDA_TRY(c, table_h2d(c, c->ffm_acc, (const char *)src + n * 4, n * 4, c->sh_acc));
         else if (!sgd) {
             const float acc0 = c->optimizer == FWGPU_OPT_ADAGRAD_FLEX ? c->d.ffm_init_acc_gradient : 0.0f;
-            k_fill<<<c->num_sms * 4, 256, 0, c->stream>>>(c->ffm_acc, n, acc0);
-            c->launches++;
+            size_t lo, hi;
+            own_range(c, c->sh_acc, n * 4, lo, hi);
+            if (hi > lo) {
+                k_fill<<<c->num_sms * 4, 256, 0, c->stream>>>(c->ffm_acc + lo / 4, (hi - lo) / 4, acc0);
+                c->launches++;
+            }
         }
     }
     return fwgpu_sync(c);

@@ -31,6 +31,7 @@ struct HeadGemmParams {
     float *C; uint32_t ldc;         // C[m*ldc + n]
     uint32_t M, N, K;
     uint32_t k_split;               // HEAD_EPI_SUMS: rows of K handled per blockIdx.z
+    uint32_t pad_;
     // epilogues
     const float *bias; int relu;    // BIAS_ACT: C = act(acc + bias[n]); a ReLU-clamped output is stored as -0.0f (its mask bit)
     const float *mask_src; uint32_t ld_mask; int mask_on; // MASK: C = mask_src[m][n] is -0.0f ? 0 : acc    (block_relu.rs:101-108)
@@ -38,54 +39,75 @@ struct HeadGemmParams {
     float *G1, *G2; float *G1_bias, *G2_bias;             // SUMS: atomicAdd into G1/G2[m*ldc + n]; bias sums from A alone
 };
 
-// 64 x 64 x 16 tiles, 256 threads, 4 x 4 outputs per thread.
-template <bool A_T, bool B_T, int EPI>
-__global__ void __launch_bounds__(256) k_head_gemm(const HeadGemmParams p)
+// BM x BN x 16 tiles, 256 threads (16 x 16).  Each thread owns (BM/16) x (BN/16) outputs arranged as 4-wide groups that are
+// BM/2 (BN/2) apart, so the 128-bit shared-memory reads of a quarter-warp fall into distinct banks.  The next k-tile is
+// fetched into registers while the current one is multiplied (one barrier pair per tile).
+template <bool A_T, bool B_T, int EPI, int BM, int BN>
+__global__ void __launch_bounds__(256, (BM * BN > 64 * 128) ? 1 : 2) k_head_gemm(const HeadGemmParams p)
 {
-    constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+    constexpr int BK = 16, PAD = 4;
+    constexpr int TM = BM / 16, TN = BN / 16;       // outputs per thread: 4 or 8 in each direction
+    constexpr int GM = TM / 4, GN = TN / 4;         // 4-wide groups
+    constexpr int LA = BM * BK / 256, LB = BN * BK / 256; // tile elements fetched per thread
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
     const uint32_t tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
     const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
     uint32_t k_begin = 0, k_end = p.K;
     if (EPI == HEAD_EPI_SUMS) { k_begin = blockIdx.z * p.k_split; k_end = min(p.K, k_begin + p.k_split); }
-    float acc[4][4], acc2[4][4], bsum[4], bsum2[4];
+    float acc[TM][TN], acc2[EPI == HEAD_EPI_SUMS ? TM : 1][EPI == HEAD_EPI_SUMS ? TN : 1], bsum[TM], bsum2[TM];
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
+    for (int i = 0; i < TM; i++) {
         bsum[i] = bsum2[i] = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 4; j++) acc[i][j] = acc2[i][j] = 0.0f;
+        for (int j = 0; j < TN; j++) { acc[i][j] = 0.0f; if (EPI == HEAD_EPI_SUMS) acc2[i][j] = 0.0f; }
     }
-    for (uint32_t k0 = k_begin; k0 < k_end; k0 += BK) {
+    float ra[LA], rb[LB];
+    auto fetch = [&](uint32_t k0) {
 #pragma unroll
-        for (int r = 0; r < 4; r++) {
+        for (int r = 0; r < LA; r++) {
             const uint32_t e = tid + 256 * r;
-            {
-                const uint32_t kk = A_T ? e / BM : e % BK, mm = A_T ? e % BM : e / BK;
-                const uint32_t gm = m0 + mm, gk = k0 + kk;
-                float v = 0.0f;
-                if (gm < p.M && gk < k_end) v = A_T ? p.A[(size_t)gk * p.lda + gm] : p.A[(size_t)gm * p.lda + gk];
-                As[kk][mm] = v;
-            }
-            {
-                const uint32_t kk = B_T ? e / BN : e % BK, nn = B_T ? e % BN : e / BK;
-                const uint32_t gn = n0 + nn, gk = k0 + kk;
-                float v = 0.0f;
-                if (gn < p.N && gk < k_end) v = B_T ? p.B[(size_t)gk * p.ldb + gn] : p.B[(size_t)gn * p.ldb + gk];
-                Bs[kk][nn] = v;
-            }
+            const uint32_t kk = A_T ? e / BM : e % BK, mm = A_T ? e % BM : e / BK;
+            const uint32_t gm = m0 + mm, gk = k0 + kk;
+            ra[r] = (gm < p.M && gk < k_end) ? (A_T ? p.A[(size_t)gk * p.lda + gm] : p.A[(size_t)gm * p.lda + gk]) : 0.0f;
         }
+#pragma unroll
+        for (int r = 0; r < LB; r++) {
+            const uint32_t e = tid + 256 * r;
+            const uint32_t kk = B_T ? e / BN : e % BK, nn = B_T ? e % BN : e / BK;
+            const uint32_t gn = n0 + nn, gk = k0 + kk;
+            rb[r] = (gn < p.N && gk < k_end) ? (B_T ? p.B[(size_t)gk * p.ldb + gn] : p.B[(size_t)gn * p.ldb + gk]) : 0.0f;
+        }
+    };
+    auto stage = [&]() {
+#pragma unroll
+        for (int r = 0; r < LA; r++) { const uint32_t e = tid + 256 * r; As[A_T ? e / BM : e % BK][A_T ? e % BM : e / BK] = ra[r]; }
+#pragma unroll
+        for (int r = 0; r < LB; r++) { const uint32_t e = tid + 256 * r; Bs[B_T ? e / BN : e % BK][B_T ? e % BN : e / BK] = rb[r]; }
+    };
+    if (k_begin < k_end) fetch(k_begin);
+    for (uint32_t k0 = k_begin; k0 < k_end; k0 += BK) {
+        stage();
         __syncthreads();
+        if (k0 + BK < k_end) fetch(k0 + BK);
 #pragma unroll
         for (int kk = 0; kk < BK; kk++) {
-            const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
-            const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
-            const float a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            float a[TM], b[TN];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
+            for (int g = 0; g < GM; g++) {
+                const float4 v = *reinterpret_cast<const float4 *>(&As[kk][g * (BM / GM) + ty * 4]);
+                a[4 * g] = v.x; a[4 * g + 1] = v.y; a[4 * g + 2] = v.z; a[4 * g + 3] = v.w;
+            }
+#pragma unroll
+            for (int g = 0; g < GN; g++) {
+                const float4 v = *reinterpret_cast<const float4 *>(&Bs[kk][g * (BN / GN) + tx * 4]);
+                b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; i++) {
                 if (EPI == HEAD_EPI_SUMS) { bsum[i] += a[i]; bsum2[i] = fmaf(a[i], a[i], bsum2[i]); }
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
+                for (int j = 0; j < TN; j++) {
                     if (EPI == HEAD_EPI_SUMS) {
                         const float g = __fmul_rn(a[i], b[j]); // the per-example gradient g_j * x_i (block_neural.rs:268-269)
                         acc[i][j] += g;
@@ -99,15 +121,15 @@ __global__ void __launch_bounds__(256) k_head_gemm(const HeadGemmParams p)
         __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t gm = m0 + ty * 4 + i;
+    for (int i = 0; i < TM; i++) {
+        const uint32_t gm = m0 + (i / 4) * (BM / GM) + ty * 4 + (i & 3);
         if (gm >= p.M) continue;
         if (EPI == HEAD_EPI_SUMS && blockIdx.x == 0 && tx == 0 && p.G1_bias) {
             if (bsum[i] != 0.0f || bsum2[i] != 0.0f) { atomicAdd(p.G1_bias + gm, bsum[i]); atomicAdd(p.G2_bias + gm, bsum2[i]); }
         }
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const uint32_t gn = n0 + tx * 4 + j;
+        for (int j = 0; j < TN; j++) {
+            const uint32_t gn = n0 + (j / 4) * (BN / GN) + tx * 4 + (j & 3);
             if (gn >= p.N) continue;
             const size_t o = (size_t)gm * p.ldc + gn;
             if (EPI == HEAD_EPI_BIAS_ACT) {

@@ -1156,10 +1156,11 @@ __device__ __forceinline__ float merand48(uint64_t seed)
     uint64_t s = a * seed + c;
     return __uint_as_float((uint32_t)((s >> 25) & 0x7FFFFFu) | 0x3F800000u) - 1.0f;
 }
-__global__ void k_init_ffm(float *w, float *acc, uint32_t len, uint32_t alloc_len, float one_over_k_root, float init_acc,
+__global__ void k_init_ffm(float *w, float *acc, uint32_t len, uint32_t first, uint32_t last, float one_over_k_root, float init_acc,
                            float init_width, float zero_band, float center)
 {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < alloc_len; i += (size_t)gridDim.x * blockDim.x) {
+    // elements [first, last) of the table (a sharded table is initialised range by range, each by its owner); index >= len is padding
+    for (size_t i = first + blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < last; i += (size_t)gridDim.x * blockDim.x) {
         float wv = 0.0f;
         if (i < len) {
             if (init_width == 0.0f) wv = __fmul_rn(__fsub_rn(1.0f * merand48((uint64_t)len + i), 0.5f), one_over_k_root);

@@ -1,0 +1,302 @@
+// fwgpu_shard.cu -- sharded-table plumbing: CUDA virtual-memory API + unix-socket rendezvous (see fwgpu_shard.hpp).
+#include "fwgpu_shard.hpp"
+
+#include <chrono>
+#include <cstring>
+#include <poll.h>
+#include <sys/socket.h>
+#include <sys/un.h>
+#include <unistd.h>
+
+namespace fwgpu {
+
+// ---- driver entry points, resolved at run time (the library links against the runtime only) ----
+struct Drv {
+    CUresult (*MemCreate)(CUmemGenericAllocationHandle *, size_t, const CUmemAllocationProp *, unsigned long long) = nullptr;
+    CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+    CUresult (*MemAddressReserve)(CUdeviceptr *, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+    CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+    CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+    CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc *, size_t) = nullptr;
+    CUresult (*MemExportToShareableHandle)(void *, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+    CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle *, void *, CUmemAllocationHandleType) = nullptr;
+    CUresult (*MemGetAllocationGranularity)(size_t *, const CUmemAllocationProp *, CUmemAllocationGranularity_flags) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char **) = nullptr;
+    bool ok = false;
+    std::string err;
+    Drv()
+    {
+        auto get = [&](const char *name, void **fn) {
+            cudaDriverEntryPointQueryResult q;
+            cudaError_t e = cudaGetDriverEntryPoint(name, fn, cudaEnableDefault, &q);
+            if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !*fn) { err = std::string("driver entry point ") + name + " unavailable"; return false; }
+            return true;
+        };
+        ok = get("cuMemCreate", (void **)&MemCreate) && get("cuMemRelease", (void **)&MemRelease) &&
+             get("cuMemAddressReserve", (void **)&MemAddressReserve) && get("cuMemAddressFree", (void **)&MemAddressFree) &&
+             get("cuMemMap", (void **)&MemMap) && get("cuMemUnmap", (void **)&MemUnmap) && get("cuMemSetAccess", (void **)&MemSetAccess) &&
+             get("cuMemExportToShareableHandle", (void **)&MemExportToShareableHandle) &&
+             get("cuMemImportFromShareableHandle", (void **)&MemImportFromShareableHandle) &&
+             get("cuMemGetAllocationGranularity", (void **)&MemGetAllocationGranularity) && get("cuGetErrorString", (void **)&GetErrorString);
+    }
+};
+static Drv &drv()
+{
+    static Drv d;
+    return d;
+}
+static std::string cu_err(const char *what, CUresult r)
+{
+    const char *s = nullptr;
+    if (drv().GetErrorString) drv().GetErrorString(r, &s);
+    return std::string(what) + ": " + (s ? s : "CUDA driver error ") + " (" + std::to_string((int)r) + ")";
+}
+static CUmemAllocationProp alloc_prop(int device)
+{
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = device;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    return prop;
+}
+
+// ---- unix-socket helpers ----
+static bool send_all(int fd, const void *buf, size_t n)
+{
+    const char *p = (const char *)buf;
+    while (n) { ssize_t w = ::send(fd, p, n, MSG_NOSIGNAL); if (w <= 0) return false; p += w; n -= (size_t)w; }
+    return true;
+}
+static bool recv_all(int fd, void *buf, size_t n, int timeout_ms)
+{
+    char *p = (char *)buf;
+    while (n) {
+        pollfd pf{fd, POLLIN, 0};
+        if (::poll(&pf, 1, timeout_ms) <= 0) return false;
+        ssize_t r = ::recv(fd, p, n, 0);
+        if (r <= 0) return false;
+        p += r; n -= (size_t)r;
+    }
+    return true;
+}
+static bool send_fd(int sock, int fd)
+{
+    char dummy = 'F', ctrl[CMSG_SPACE(sizeof(int))];
+    memset(ctrl, 0, sizeof(ctrl));
+    iovec io{&dummy, 1};
+    msghdr msg{};
+    msg.msg_iov = &io; msg.msg_iovlen = 1; msg.msg_control = ctrl; msg.msg_controllen = sizeof(ctrl);
+    cmsghdr *cm = CMSG_FIRSTHDR(&msg);
+    cm->cmsg_level = SOL_SOCKET; cm->cmsg_type = SCM_RIGHTS; cm->cmsg_len = CMSG_LEN(sizeof(int));
+    memcpy(CMSG_DATA(cm), &fd, sizeof(int));
+    return ::sendmsg(sock, &msg, MSG_NOSIGNAL) == 1;
+}
+static int recv_fd(int sock, int timeout_ms)
+{
+    pollfd pf{sock, POLLIN, 0};
+    if (::poll(&pf, 1, timeout_ms) <= 0) return -1;
+    char dummy = 0, ctrl[CMSG_SPACE(sizeof(int))];
+    iovec io{&dummy, 1};
+    msghdr msg{};
+    msg.msg_iov = &io; msg.msg_iovlen = 1; msg.msg_control = ctrl; msg.msg_controllen = sizeof(ctrl);
+    if (::recvmsg(sock, &msg, 0) != 1) return -1;
+    cmsghdr *cm = CMSG_FIRSTHDR(&msg);
+    if (!cm || cm->cmsg_level != SOL_SOCKET || cm->cmsg_type != SCM_RIGHTS) return -1;
+    int fd = -1;
+    memcpy(&fd, CMSG_DATA(cm), sizeof(int));
+    return fd;
+}
+static bool sock_addr(const std::string &path, sockaddr_un &a)
+{
+    memset(&a, 0, sizeof(a));
+    a.sun_family = AF_UNIX;
+    if (path.size() + 1 > sizeof(a.sun_path)) return false;
+    memcpy(a.sun_path, path.c_str(), path.size() + 1);
+    return true;
+}
+static int connect_retry(const std::string &path, uint32_t timeout_ms)
+{
+    sockaddr_un a;
+    if (!sock_addr(path, a)) return -1;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        int s = ::socket(AF_UNIX, SOCK_STREAM, 0);
+        if (s < 0) return -1;
+        if (::connect(s, (sockaddr *)&a, sizeof(a)) == 0) return s;
+        ::close(s);
+        if (std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - t0).count() > (long)timeout_ms) return -1;
+        ::usleep(20000);
+    }
+}
+
+enum { REQ_FD = 1, REQ_BARRIER = 2 };
+
+static void serve_connection(ShardGroup *g, int s)
+{
+    uint32_t req[2];
+    if (recv_all(s, req, sizeof(req), (int)g->timeout_ms)) {
+        std::unique_lock<std::mutex> lk(g->mu);
+        const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(g->timeout_ms);
+        if (req[0] == REQ_FD) {
+            const bool ready = g->cv.wait_until(lk, deadline, [&] { return g->stop.load() || g->arrays.size() > req[1]; });
+            const int fd = (ready && !g->stop.load()) ? g->arrays[req[1]]->own_fd : -1;
+            lk.unlock();
+            if (fd >= 0) send_fd(s, fd);
+        } else if (req[0] == REQ_BARRIER) {
+            const bool ready = g->cv.wait_until(lk, deadline, [&] { return g->stop.load() || g->phase >= req[1]; });
+            lk.unlock();
+            const char ok = (ready && !g->stop.load()) ? 1 : 0;
+            send_all(s, &ok, 1);
+        }
+    }
+    ::close(s);
+}
+
+bool ShardGroup::start(uint32_t rank_, uint32_t world_, int device_, const char *prefix_, uint32_t timeout_ms_)
+{
+    rank = rank_; world = world_; device = device_; prefix = prefix_ ? prefix_ : ""; if (timeout_ms_) timeout_ms = timeout_ms_;
+    if (world == 0 || rank >= world || prefix.empty()) { error = "bad shard group arguments"; return false; }
+    if (!drv().ok) { error = drv().err; return false; }
+    CUmemAllocationProp prop = alloc_prop(device);
+    CUresult r = drv().MemGetAllocationGranularity(&granularity, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED);
+    if (r != CUDA_SUCCESS || granularity == 0) { error = cu_err("cuMemGetAllocationGranularity", r); return false; }
+    const std::string path = prefix + "." + std::to_string(rank);
+    sockaddr_un a;
+    if (!sock_addr(path, a)) { error = "rendezvous path too long"; return false; }
+    ::unlink(path.c_str());
+    listen_fd = ::socket(AF_UNIX, SOCK_STREAM, 0);
+    if (listen_fd < 0 || ::bind(listen_fd, (sockaddr *)&a, sizeof(a)) != 0 || ::listen(listen_fd, 64) != 0) {
+        error = "cannot listen on " + path + ": " + strerror(errno);
+        return false;
+    }
+    server = std::thread([this] {
+        std::vector<std::thread> workers;
+        while (!stop.load()) {
+            pollfd pf{listen_fd, POLLIN, 0};
+            if (::poll(&pf, 1, 100) <= 0) continue;
+            int s = ::accept(listen_fd, nullptr, nullptr);
+            if (s >= 0) workers.emplace_back(serve_connection, this, s);
+        }
+        for (auto &w : workers) w.join();
+    });
+    return true;
+}
+
+ShardGroup::~ShardGroup()
+{
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        stop.store(true);
+    }
+    cv.notify_all();
+    if (server.joinable()) server.join();
+    if (listen_fd >= 0) { ::close(listen_fd); ::unlink((prefix + "." + std::to_string(rank)).c_str()); }
+}
+
+void shard_plan(size_t bytes, size_t tail_bytes, uint32_t world, size_t granularity, std::vector<size_t> &sizes)
+{
+    auto up = [&](size_t x) { return (x + granularity - 1) / granularity * granularity; };
+    sizes.assign(world, 0);
+    if (world > 1 && bytes % world == 0 && (bytes / world) % granularity == 0) {
+        for (uint32_t s = 0; s < world; s++) sizes[s] = bytes / world;
+        sizes[world - 1] += up(tail_bytes);
+    } else {
+        sizes[0] = up(bytes + tail_bytes);
+    }
+}
+
+bool ShardGroup::create_array(ShardedArray &a, const std::vector<size_t> &sizes)
+{
+    Drv &d = drv();
+    if (sizes.size() != world) { error = "shard plan does not match the group size"; return false; }
+    a.sizes = sizes;
+    a.offsets.assign(world, 0);
+    a.total_bytes = 0;
+    for (uint32_t s = 0; s < world; s++) {
+        if (sizes[s] % granularity) { error = "shard sizes must be multiples of the allocation granularity"; return false; }
+        a.offsets[s] = a.total_bytes;
+        a.total_bytes += sizes[s];
+    }
+    a.handles.assign(world, 0);
+    CUresult r;
+    if (sizes[rank]) {
+        CUmemAllocationProp prop = alloc_prop(device);
+        r = d.MemCreate(&a.handles[rank], sizes[rank], &prop, 0);
+        if (r != CUDA_SUCCESS) { error = cu_err("cuMemCreate", r); return false; }
+        r = d.MemExportToShareableHandle(&a.own_fd, a.handles[rank], CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0);
+        if (r != CUDA_SUCCESS) { error = cu_err("cuMemExportToShareableHandle", r); return false; }
+    }
+    uint32_t index;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        index = (uint32_t)arrays.size();
+        arrays.push_back(&a);
+    }
+    cv.notify_all();
+    r = d.MemAddressReserve(&a.va, a.total_bytes, granularity, 0, 0);
+    if (r != CUDA_SUCCESS) { error = cu_err("cuMemAddressReserve", r); return false; }
+    for (uint32_t s = 0; s < world; s++) {
+        if (!sizes[s]) continue;
+        if (s != rank) {
+            int sock = connect_retry(prefix + "." + std::to_string(s), timeout_ms);
+            if (sock < 0) { error = "cannot reach rank " + std::to_string(s) + " at " + prefix; return false; }
+            const uint32_t req[2] = {REQ_FD, index};
+            int fd = send_all(sock, req, sizeof(req)) ? recv_fd(sock, (int)timeout_ms) : -1;
+            ::close(sock);
+            if (fd < 0) { error = "rank " + std::to_string(s) + " did not send its shard handle"; return false; }
+            r = d.MemImportFromShareableHandle(&a.handles[s], (void *)(uintptr_t)fd, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
+            ::close(fd);
+            if (r != CUDA_SUCCESS) { error = cu_err("cuMemImportFromShareableHandle", r); return false; }
+        }
+        r = d.MemMap(a.va + a.offsets[s], sizes[s], 0, a.handles[s], 0);
+        if (r != CUDA_SUCCESS) { error = cu_err("cuMemMap", r); return false; }
+    }
+    CUmemAccessDesc acc;
+    memset(&acc, 0, sizeof(acc));
+    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    acc.location.id = device;
+    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+    r = d.MemSetAccess(a.va, a.total_bytes, &acc, 1);
+    if (r != CUDA_SUCCESS) { error = cu_err("cuMemSetAccess (is peer access between the GPUs available?)", r); return false; }
+    return true;
+}
+
+void ShardGroup::destroy_array(ShardedArray &a)
+{
+    Drv &d = drv();
+    if (!d.ok) return;
+    if (a.va) {
+        d.MemUnmap(a.va, a.total_bytes);
+        d.MemAddressFree(a.va, a.total_bytes);
+        a.va = 0;
+    }
+    for (auto h : a.handles) if (h) d.MemRelease(h);
+    a.handles.clear();
+    if (a.own_fd >= 0) { ::close(a.own_fd); a.own_fd = -1; }
+}
+
+bool ShardGroup::barrier()
+{
+    uint64_t my;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        my = ++phase;
+    }
+    cv.notify_all();
+    for (uint32_t s = 0; s < world; s++) {
+        if (s == rank) continue;
+        int sock = connect_retry(prefix + "." + std::to_string(s), timeout_ms);
+        if (sock < 0) { error = "barrier: cannot reach rank " + std::to_string(s); return false; }
+        const uint32_t req[2] = {REQ_BARRIER, (uint32_t)my};
+        char ok = 0;
+        const bool got = send_all(sock, req, sizeof(req)) && recv_all(sock, &ok, 1, (int)timeout_ms) && ok == 1;
+        ::close(sock);
+        if (!got) { error = "barrier: rank " + std::to_string(s) + " did not arrive"; return false; }
+    }
+    return true;
+}
+
+} // namespace fwgpu

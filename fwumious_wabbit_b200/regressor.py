@@ -31,13 +31,19 @@ class Dataset:
 
 
 class Regressor:
-    def __init__(self, mi: ModelInstance, device: int = 0, immutable: bool = False):
+    def __init__(self, mi: ModelInstance, device: int = 0, immutable: bool = False, shard=None):
+        """shard = (rank, world, rendezvous_prefix): one model whose tables are hash-range-sharded over `world` GPUs
+        (one process per GPU, collective constructor; fwgpu_create_sharded)."""
         self.L = _lib.lib()
         self.mi = mi
         self.immutable = immutable
         desc, keep = mi.to_desc(immutable=immutable)
         h = C.c_void_p()
-        st = self.L.fwgpu_create(C.byref(desc), device, C.byref(h))
+        if shard is not None:
+            rank, world, prefix = shard
+            st = self.L.fwgpu_create_sharded(C.byref(desc), device, rank, world, str(prefix).encode(), 0, C.byref(h))
+        else:
+            st = self.L.fwgpu_create(C.byref(desc), device, C.byref(h))
         if st != 0:
             raise _lib.FwgpuError(st, self.L.fwgpu_last_error(None).decode())
         self.h = h
@@ -65,6 +71,14 @@ class Regressor:
 
     def sync(self):
         self._check(self.L.fwgpu_sync(self.h))
+
+    def shard_barrier(self):
+        self._check(self.L.fwgpu_shard_barrier(self.h))
+
+    def shard_info(self):
+        r, w, f, n = C.c_uint32(0), C.c_uint32(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.L.fwgpu_shard_info(self.h, C.byref(r), C.byref(w), C.byref(f), C.byref(n)))
+        return r.value, w.value, f.value, n.value
 
     # ---- Regressor::learn / predict (regressor.rs:356-395), one example ----
     def learn(self, fb: FeatureBuffer, update: bool = True) -> float:

@@ -130,6 +130,20 @@ typedef struct fwgpu_dataset fwgpu_dataset; /* records resident in HBM */
  * allocates the tables in HBM and initialises them like the reference (LR zeros block_lr.rs:97-105,
  * FFM merand48 block_ffm.rs:784-829), builds the AdaGrad look-up tables (optimizer.rs:121-144). */
 fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **out);
+/* The same regressor with its LR / FFM tables hash-range-sharded over the GPUs of one NVLink/NVSwitch box (BASELINE config 4).
+ * One process per GPU calls this collectively (rank in [0, world)); the reference's counterpart is the single table all
+ * Hogwild workers share (hogwild.rs:24-103).  Rank r owns indices [r*len/world, (r+1)*len/world) (+ the spill-over tail
+ * of block_ffm.rs:93-94 on the last rank); every rank maps all ranges into one contiguous virtual range (CUDA VMM +
+ * POSIX fd exchange over the unix sockets "<rendezvous>.<rank>"), so the learn kernels address remote rows like local
+ * ones: gathers and AdaGrad atomics travel over NVLink to the owner's L2 inside the fused kernel.  Every other entry
+ * point works unchanged on such a ctx; fwgpu_import_block is collective (each rank writes the range it owns).
+ * Tables too small to split into whole allocation granules live on rank 0.  timeout_ms 0 = 60 s. */
+fwgpu_status fwgpu_create_sharded(const fwgpu_model_desc *desc, int device, uint32_t rank, uint32_t world,
+                                  const char *rendezvous, uint32_t timeout_ms, fwgpu_ctx **out);
+/* fwgpu_sync + wait until every rank of the shard group has done the same (no-op group of one for unsharded ctxs). */
+fwgpu_status fwgpu_shard_barrier(fwgpu_ctx *ctx);
+/* rank / world of the ctx's shard group and the FFM index range [first, first+count) this rank's HBM holds. */
+fwgpu_status fwgpu_shard_info(const fwgpu_ctx *ctx, uint32_t *rank, uint32_t *world, uint64_t *ffm_first, uint64_t *ffm_count);
 void fwgpu_destroy(fwgpu_ctx *ctx);
 const char *fwgpu_last_error(const fwgpu_ctx *ctx); /* ctx may be NULL: last create() failure */
 fwgpu_status fwgpu_sync(fwgpu_ctx *ctx);
