@@ -164,7 +164,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_ours(args):
@@ -283,8 +283,8 @@ def run_ours(args):
         traffic = None
         tp = os.path.join(ROOT, "profiles", f"traffic_{w.name}.json")
         if os.path.exists(tp):
-            try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            try:  # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` launch, scaled to this run's launch size
+                traffic = json.load(open(tp)).get("dram_bytes_per_example") * ex_per_launch
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -324,7 +324,7 @@ def run_ours(args):
                        "optimizer": "AdagradLUT", "semantics": "Hogwild on device, chunked launches"},
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     ds.free()
     re.close()
     L.fwgpu_host_free(hp)
@@ -333,7 +333,24 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's real stdout; everything else any library prints on fd 1 (NCCL's version
+    banner, for instance) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     # NCCL prints its version banner on stdout when NCCL_DEBUG is VERSION/INFO; stdout carries exactly one JSON line
     if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE") and not os.environ.get("FWGPU_KEEP_NCCL_DEBUG"):
         os.environ["NCCL_DEBUG"] = "WARN"

@@ -105,8 +105,11 @@ int main(int argc, char **argv)
     if (fl.has("sequential")) desc.hogwild_ramp_div = 0x7fffffffu;
     fwgpu_ctx *ctx = nullptr;
     if (fwgpu_create(&desc, device, &ctx) != FWGPU_OK) die(std::string("fwgpu_create: ") + fwgpu_last_error(nullptr));
-    const int blocks[2] = {FWGPU_BLOCK_LR, FWGPU_BLOCK_FFM};
-    const int n_blocks = desc.ffm_k > 0 ? 2 : 1;
+    // blocks with weights in execution order (regressor.rs:426-442): LR, FFM, the head's neuron layers
+    std::vector<int> blocks{FWGPU_BLOCK_LR};
+    if (desc.ffm_k > 0) blocks.push_back(FWGPU_BLOCK_FFM);
+    if (desc.nn_num_layers > 0) for (uint32_t l = 0; l <= desc.nn_num_layers; l++) blocks.push_back(FWGPU_BLOCK_NN0 + (int)l);
+    const int n_blocks = (int)blocks.size();
     if (reader) { // overwrite_weights_from_buf (regressor.rs:444-469)
         uint64_t expect = 0;
         for (int b = 0; b < n_blocks; b++) { uint64_t n, by; check(ctx, fwgpu_block_len(ctx, blocks[b], &n, &by), "block_len"); expect += n; }
@@ -126,7 +129,7 @@ int main(int argc, char **argv)
     }
     auto save = [&](const char *path, bool as_sgd) {
         std::vector<std::vector<float>> payload(n_blocks);
-        const void *ptrs[2]; uint64_t sizes[2], total = 0;
+        std::vector<const void *> ptrs(n_blocks); std::vector<uint64_t> sizes(n_blocks); uint64_t total = 0;
         for (int b = 0; b < n_blocks; b++) {
             uint64_t n, by; fwgpu_block_len(ctx, blocks[b], &n, &by);
             payload[b].resize(by / 4);
@@ -137,7 +140,7 @@ int main(int argc, char **argv)
         if (as_sgd) { // main.rs:140-147: the inference regressor is written with optimizer SGD
             size_t p = mj.find("\"optimizer\": \""); if (p != std::string::npos) { size_t e = mj.find('"', p + 14); mj.replace(p + 14, e - (p + 14), "SGD"); }
         }
-        if (fwhost_regressor_write(path, vwmap_json.c_str(), mj.c_str(), total, ptrs, sizes, (uint32_t)n_blocks, err, sizeof(err))) die(err);
+        if (fwhost_regressor_write(path, vwmap_json.c_str(), mj.c_str(), total, ptrs.data(), sizes.data(), (uint32_t)n_blocks, err, sizeof(err))) die(err);
     };
     if (convert) { save(fl.get("convert_inference_regressor"), true); fwgpu_destroy(ctx); return 0; }
 

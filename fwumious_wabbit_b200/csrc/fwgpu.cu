@@ -808,13 +808,14 @@ static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
     if (!update) { CUDA_TRY(c, cudaGetLastError()); return FWGPU_OK; }
     // final neuron: gradient sums over its inputs [h, x] and its bias (block_neural.rs:266-305 with one neuron)
     {
-        HeadGemmParams g{};
-        g.A = dy; g.lda = 1; g.B = (const float *)c->hH[nl - 2].p; g.ldb = Ll.n_out; g.M = 1; g.N = Ll.n_out; g.K = rows; g.ldc = Lf.n_in;
-        g.G1 = c->head_G1 + Lf.off; g.G2 = c->head_G2 + Lf.off; g.G1_bias = c->head_G1 + Lf.off + Lf.n_in; g.G2_bias = c->head_G2 + Lf.off + Lf.n_in;
-        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, g);
-        HeadGemmParams h = g;
-        h.B = X; h.ldb = c->ldx; h.N = c->x_len; h.G1 = g.G1 + Ll.n_out; h.G2 = g.G2 + Ll.n_out; h.G1_bias = nullptr; h.G2_bias = nullptr;
-        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, h);
+        HeadFinalSumsParams f{};
+        f.H = (const float *)c->hH[nl - 2].p; f.ldh = Ll.n_out; f.n_h = Ll.n_out; f.X = X; f.ldx = c->ldx; f.n_x = c->x_len;
+        f.dy = dy; f.n_rows = rows; f.G1 = c->head_G1 + Lf.off; f.G2 = c->head_G2 + Lf.off;
+        const uint32_t col_blocks = (Lf.n_in + 1 + 255) / 256;
+        const uint32_t row_blocks = std::max<uint32_t>(1, std::min<uint32_t>((rows + 127) / 128, (2 * (uint32_t)c->num_sms + col_blocks - 1) / col_blocks));
+        f.rows_per_block = (rows + row_blocks - 1) / row_blocks;
+        k_head_final_sums<<<dim3(col_blocks, (rows + f.rows_per_block - 1) / f.rows_per_block), 256, 0, c->stream>>>(f);
+        c->launches++;
     }
     for (size_t li = nl - 1; li-- > 0;) { // hidden layers, last to first
         const auto &L = c->head[li];

@@ -104,17 +104,22 @@ __global__ void __launch_bounds__(256, (BM * BN > 64 * 128) ? 1 : 2) k_head_gemm
                 b[4 * g] = v.x; b[4 * g + 1] = v.y; b[4 * g + 2] = v.z; b[4 * g + 3] = v.w;
             }
 #pragma unroll
+            float a2[EPI == HEAD_EPI_SUMS ? TM : 1], b2[EPI == HEAD_EPI_SUMS ? TN : 1];
+            if (EPI == HEAD_EPI_SUMS) {
+#pragma unroll
+                for (int i = 0; i < TM; i++) a2[i] = __fmul_rn(a[i], a[i]);
+#pragma unroll
+                for (int j = 0; j < TN; j++) b2[j] = __fmul_rn(b[j], b[j]);
+            }
+#pragma unroll
             for (int i = 0; i < TM; i++) {
-                if (EPI == HEAD_EPI_SUMS) { bsum[i] += a[i]; bsum2[i] = fmaf(a[i], a[i], bsum2[i]); }
+                if (EPI == HEAD_EPI_SUMS) { bsum[i] += a[i]; bsum2[i] += a2[i]; }
 #pragma unroll
                 for (int j = 0; j < TN; j++) {
-                    if (EPI == HEAD_EPI_SUMS) {
-                        const float g = __fmul_rn(a[i], b[j]); // the per-example gradient g_j * x_i (block_neural.rs:268-269)
-                        acc[i][j] += g;
-                        acc2[i][j] += __fmul_rn(g, g);          // two roundings like optimizer.rs:148-151
-                    } else {
-                        acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-                    }
+                    acc[i][j] = fmaf(a[i], b[j], acc[i][j]); // sum of the per-example gradients g_j * x_i (block_neural.rs:268-269)
+                    // sum of their squares as (g_j^2)(x_i^2): one FMA per term instead of multiply, square, add
+                    // (optimizer.rs:148-151 squares the product; the two differ by one rounding of ~6e-8 relative)
+                    if (EPI == HEAD_EPI_SUMS) acc2[i][j] = fmaf(a2[i], b2[j], acc2[i][j]);
                 }
             }
         }
@@ -188,6 +193,41 @@ __global__ void __launch_bounds__(256) k_head_final(const HeadFinalParams p)
             }
         }
     }
+}
+
+// Gradient sums of the FINAL neuron (one output, inputs [h, x], block_neural.rs:266-305 with num_neurons = 1):
+//   G1[i] += sum_b g_b in_b[i],  G2[i] += sum_b (g_b in_b[i])^2,  and the bias sums from g alone.
+// A matrix-vector product: one thread per input column (coalesced rows), blockIdx.y takes a slice of the rows.
+struct HeadFinalSumsParams {
+    const float *H; uint32_t ldh, n_h; const float *X; uint32_t ldx, n_x;
+    const float *dy; uint32_t n_rows, rows_per_block;
+    float *G1, *G2; // [n_h + n_x] then the bias
+};
+__global__ void __launch_bounds__(256) k_head_final_sums(const HeadFinalSumsParams p)
+{
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x, n_in = p.n_h + p.n_x;
+    const uint32_t b0 = blockIdx.y * p.rows_per_block, b1 = min(p.n_rows, b0 + p.rows_per_block);
+    __shared__ float sdy[256];
+    float s1 = 0.0f, s2 = 0.0f, t1 = 0.0f, t2 = 0.0f;
+    const bool is_h = i < p.n_h;
+    const float *col = is_h ? p.H + i : p.X + (i - p.n_h);
+    const uint32_t ld = is_h ? p.ldh : p.ldx;
+    for (uint32_t base = b0; base < b1; base += 256) {
+        __syncthreads();
+        sdy[threadIdx.x] = base + threadIdx.x < b1 ? p.dy[base + threadIdx.x] : 0.0f;
+        __syncthreads();
+        const uint32_t cnt = min(256u, b1 - base);
+        if (i < n_in) {
+            for (uint32_t r = 0; r < cnt; r++) {
+                const float g = __fmul_rn(sdy[r], col[(size_t)(base + r) * ld]);
+                s1 += g; s2 = fmaf(g, g, s2);
+            }
+        } else if (i == n_in) {
+            for (uint32_t r = 0; r < cnt; r++) { t1 += sdy[r]; t2 = fmaf(sdy[r], sdy[r], t2); }
+        }
+    }
+    if (i < n_in) { if (s1 != 0.0f || s2 != 0.0f) { atomicAdd(p.G1 + i, s1); atomicAdd(p.G2 + i, s2); } }
+    else if (i == n_in) { if (t1 != 0.0f || t2 != 0.0f) { atomicAdd(p.G1 + i, t1); atomicAdd(p.G2 + i, t2); } }
 }
 
 // acc += G2 ; w -= G1 * step(acc)  over every head parameter at once; clears G1/G2 for the next sub-batch

@@ -223,10 +223,17 @@ def cache_read(path, vw: VwNamespaceMap = None):
 
 
 # ---------------------------------------------------------------- persistence.rs
+def _block_order(mi):
+    """Blocks with weights in execution order (regressor.rs:426-442): LR, FFM, then every neuron layer of the head
+    (hidden layers, final neuron); triangle / join / copy / relu / sigmoid hold nothing."""
+    nn = [_lib.BLOCK_NN0 + l for l in range(len(mi.nn_layers) + 1)] if mi.nn_layers else []
+    return [_lib.BLOCK_LR] + ([_lib.BLOCK_FFM] if mi.ffm_k > 0 else []) + nn
+
+
 def save_regressor_to_filename(filename, mi: ModelInstance, vw: VwNamespaceMap, re):
     """persistence.rs:76-92: header, vwmap JSON, ModelInstance JSON, total weight count, block payloads."""
     blocks, total = [], 0
-    order = [_lib.BLOCK_LR] + ([_lib.BLOCK_FFM] if mi.ffm_k > 0 else [])
+    order = _block_order(mi)
     for b in order:
         n, _ = re.block_len(b)
         total += n
@@ -264,12 +271,12 @@ def new_regressor_from_filename(filename, immutable=False, cmd_arguments=None, d
         mi = model_instance_from_json(mi_json, vw)
         file_has_state = mi.optimizer != Optimizer.SGD  # what the WRITER stored: accumulators unless it was SGD
         re = Regressor(mi, device=device, immutable=immutable)
-        expected = sum(re.block_len(b)[0] for b in [_lib.BLOCK_LR] + ([_lib.BLOCK_FFM] if mi.ffm_k > 0 else []))
+        expected = sum(re.block_len(b)[0] for b in _block_order(mi))
         got = L.fwhost_regressor_weights_len(r)
         if got != expected:
             raise IOError(f"Lenghts of weights array in regressor file differ: got {got}, expected {expected}")  # sic, regressor.rs:458-462
         want_state = file_has_state and not immutable
-        for b in [_lib.BLOCK_LR] + ([_lib.BLOCK_FFM] if mi.ffm_k > 0 else []):
+        for b in _block_order(mi):
             n, _ = re.block_len(b)
             if b == _lib.BLOCK_LR:
                 file_bytes = n * (8 if file_has_state else 4)

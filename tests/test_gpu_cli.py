@@ -92,3 +92,24 @@ def test_cli_flag_errors(tmp_path):
     assert r.returncode != 0 and "Unknown namespace" in r.stderr
     r = subprocess.run([FW, "--data", f"{d}/nothere/train.vw", "--keep", "A"], capture_output=True, text=True)
     assert r.returncode != 0 and "Could not find vw_namespace_map.csv" in r.stderr
+
+
+def test_cli_deep_head(tmp_path):
+    """The same round trip with a dense head (--nn_layers / --nn, model_instance.rs:430-470; regressor.rs:191-320):
+    train with AdaGrad, save, convert to inference weights, predict with both files -> identical lines; it learns."""
+    d = str(tmp_path)
+    generate(d, n_train=20000, n_eval=1000)
+    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B --nn_layers 2 --nn 0:width:16 --nn 0:activation:relu --nn 1:width:8 --nn 1:activation:relu".split()
+    rest = "-l 0.1 --ffm_learning_rate 0.05 --nn_learning_rate 0.02 -b 18 --ffm_bit_precision 18 --adaptive --sgd --power_t 0.4 --nn_power_t 0.45 --loss_function logistic --link logistic".split()
+    tr, full, inf = f"{d}/train.vw", f"{d}/full.fw", f"{d}/inference.fw"
+    run(ns + rest + ["--data", tr, "-p", f"{d}/training.txt", "-f", full, "--save_resume"])
+    run(ns + rest + ["-i", full, "--convert_inference_regressor", inf])
+    assert os.path.getsize(inf) < 0.6 * os.path.getsize(full)            # accumulators dropped from every block
+    run(ns + rest + ["-i", full, "--data", tr, "-p", f"{d}/eval_full.txt", "-t"])
+    run(ns + rest + ["-i", inf, "-d", tr, "-t", "-p", f"{d}/eval_inf.txt"])
+    assert open(f"{d}/eval_full.txt").read() == open(f"{d}/eval_inf.txt").read()
+    y = labels_of(tr)
+    p = np.loadtxt(f"{d}/eval_full.txt")
+    assert len(np.unique(p)) > 100 and balanced_accuracy(p, y) > 0.9
+    r = subprocess.run([FW] + ns + rest + ["--data", tr, "--nn", "0:dropout:0.5"], capture_output=True, text=True)
+    assert r.returncode != 0 and "not implemented" in r.stderr

@@ -225,3 +225,42 @@ def test_head_full_size_config5_properties():
         re3.import_block(blk, re2.export_block(blk), True)
     c = re3.learn_records(recs2[:5000].reshape(-1), n_examples=5000, update=False)
     assert np.array_equal(a, c)
+
+
+def test_head_regressor_file_roundtrip(tmp_path):
+    """Regressor file with a head (persistence.rs:55-97): LR, FFM, then every neuron layer as weights + accumulators
+    (block_neural.rs:426-438); mutable reload resumes with the same state, immutable reload (weights only) and the
+    converted inference file predict identically."""
+    from fwumious_wabbit_b200 import host
+
+    w = small_c5()
+    vw = host.VwNamespaceMap.new("".join(f"{c},feature{c}\n" for c in w.ns_names))
+    n = 20_000
+    recs = w.records(n)
+    re = fw.Regressor(w.mi)
+    re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    path = str(tmp_path / "c5s.fw")
+    host.save_regressor_to_filename(path, w.mi, vw, re)
+    raw = open(path, "rb").read()
+    l1 = int.from_bytes(raw[8:16], "little")
+    l2 = int.from_bytes(raw[16 + l1:24 + l1], "little")
+    body = 24 + l1 + l2
+    x_len = w.mi.num_combos + 10 * 11 // 2
+    nn_len = (x_len + 1) * 32 + (32 + 1) * 32 + (32 + x_len + 1)
+    assert int.from_bytes(raw[body:body + 8], "little") == (1 << 14) + (1 << 14) + 40 + nn_len
+    assert len(raw) == body + 8 + 8 * ((1 << 14) + (1 << 14) + 40 + nn_len)  # every block: weights + optimizer state
+    want = re.learn_records(recs[:3000].reshape(-1), n_examples=3000, update=False)
+    mi2, _, re2 = host.new_regressor_from_filename(path, False)
+    assert [dict(l) for l in mi2.nn_layers] == [dict(l) for l in w.mi.nn_layers]
+    assert np.array_equal(re2.learn_records(recs[:3000].reshape(-1), n_examples=3000, update=False), want)
+    for l in range(re.nn_layer_count()):
+        assert np.array_equal(re.get_nn(l)[0], re2.get_nn(l)[0]) and np.array_equal(re.get_nn(l)[1], re2.get_nn(l)[1])
+    _, _, re3 = host.new_regressor_from_filename(path, True)
+    assert re3.get_nn(0)[1] is None
+    assert np.array_equal(re3.learn_records(recs[:3000].reshape(-1), n_examples=3000, update=False), want)
+    inf = str(tmp_path / "c5s_inference.fw")
+    host.save_regressor_to_filename(inf, w.mi, vw, re3)
+    _, _, re4 = host.new_regressor_from_filename(inf, True)
+    assert np.array_equal(re4.learn_records(recs[:3000].reshape(-1), n_examples=3000, update=False), want)
+    with pytest.raises(fw._lib.FwgpuError):
+        re3.learn_records(recs[:10].reshape(-1), n_examples=10, update=True)  # regressor.rs:362-365
