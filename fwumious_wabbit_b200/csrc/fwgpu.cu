@@ -95,6 +95,8 @@ struct fwgpu_ctx {
     bool fast_ok = false;     // k_learn_fixed applies to this model (one namespace per field, k % 4 == 0, ...)
     bool fast_enabled = true; // FWGPU_FAST=0 turns the fused kernel off (measurement / debugging)
     uint32_t fast_nch = 1;
+    int fast_minb = 3;        // k_learn_fixed blocks per SM the register budget is set for (FWGPU_FIXED_MINB=2: 64 registers, 32 warps per SM)
+    bool fast_snap = false;   // k_learn_fixed steps from the accumulator values read at gather time (no ATOMG round trip); FWGPU_SNAP=0: from the atomics' return values
     bool fast_cta = false;    // wide model: one block per record (k_learn_fixed_cta) instead of one warp
     int fast_ub = 2;
     uint32_t *err_flag = nullptr;
@@ -419,6 +421,8 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         c->fast_ok = ok;
         c->fast_nch = n_chunks <= 32 ? 1 : n_chunks <= 64 ? 2 : n_chunks <= 96 ? 3 : 4;
         if (const char *t = getenv("FWGPU_FAST")) c->fast_enabled = atoi(t) != 0;
+        if (const char *t = getenv("FWGPU_SNAP")) c->fast_snap = atoi(t) != 0;
+        if (const char *t = getenv("FWGPU_FIXED_MINB")) c->fast_minb = atoi(t);
     }
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
     if (const char *t = getenv("FWGPU_MINB")) c->minb = atoi(t);
@@ -705,9 +709,9 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
 }
 
 // ---- fused fast path (k_learn_fixed) -----------------------------------------------------------
-template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+template <int NCH, bool SNAP, int MINB, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
 {
-    auto kern = k_learn_fixed<NCH>;
+    auto kern = k_learn_fixed<NCH, SNAP, MINB, OPTK>;
     constexpr int NW = FIXED_WARPS;
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -726,6 +730,13 @@ template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedPa
     kern<<<grid, NW * 32, smem, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
+}
+
+// AdagradLUT (the reference's default under --adaptive) gets its own instantiation; Flex / SGD share the generic one
+template <int NCH, bool SNAP, int MINB = 3> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+{
+    if (p.optimizer == OPT_LUT) return launch_fixed_k<NCH, SNAP, MINB, (int)OPT_LUT>(c, p, smem, full_groups);
+    return launch_fixed_k<NCH, SNAP, MINB, -1>(c, p, smem, full_groups);
 }
 
 template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
@@ -1093,7 +1104,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
         fp.optimizer = c->optimizer; fp.lr_lr = c->d.learning_rate; fp.lr_mpt = -c->d.power_t; fp.ffm_lr = c->d.ffm_learning_rate; fp.ffm_mpt = -c->d.ffm_power_t;
         fp.update = update; fp.preds = (float *)c->preds.p; fp.leftover_idx = left_idx; fp.leftover_cnt = left_cnt;
         fp.warp_smem_floats = c->F * (fp.cpr + 1) * 4;
-        const size_t smem = (size_t)fp.warp_smem_floats * 4 * FIXED_WARPS + (size_t)2 * FIXED_WARPS * FIXED_LR_MAX * 8;
+        const size_t smem = (size_t)fp.warp_smem_floats * 4 * FIXED_WARPS; // the warps' row transposes
         uint32_t done = 0;
         while (done < count) {
             uint32_t cnt = count - done, cap = 0;
@@ -1126,11 +1137,27 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 }
             } else {
                 ProfScope ps(c, 0);
-                switch (c->fast_nch) {
-                case 1: e = launch_fixed_n<1>(c, fp, smem, &full_groups); break;
-                case 2: e = launch_fixed_n<2>(c, fp, smem, &full_groups); break;
-                case 3: e = launch_fixed_n<3>(c, fp, smem, &full_groups); break;
-                default: e = launch_fixed_n<4>(c, fp, smem, &full_groups); break;
+                if (c->fast_snap && c->fast_minb == 2) {
+                    switch (c->fast_nch) {
+                    case 1: e = launch_fixed_n<1, true, 2>(c, fp, smem, &full_groups); break;
+                    case 2: e = launch_fixed_n<2, true, 2>(c, fp, smem, &full_groups); break;
+                    case 3: e = launch_fixed_n<3, true, 2>(c, fp, smem, &full_groups); break;
+                    default: e = launch_fixed_n<4, true, 2>(c, fp, smem, &full_groups); break;
+                    }
+                } else if (c->fast_snap) {
+                    switch (c->fast_nch) {
+                    case 1: e = launch_fixed_n<1, true>(c, fp, smem, &full_groups); break;
+                    case 2: e = launch_fixed_n<2, true>(c, fp, smem, &full_groups); break;
+                    case 3: e = launch_fixed_n<3, true>(c, fp, smem, &full_groups); break;
+                    default: e = launch_fixed_n<4, true>(c, fp, smem, &full_groups); break;
+                    }
+                } else {
+                    switch (c->fast_nch) {
+                    case 1: e = launch_fixed_n<1, false>(c, fp, smem, &full_groups); break;
+                    case 2: e = launch_fixed_n<2, false>(c, fp, smem, &full_groups); break;
+                    case 3: e = launch_fixed_n<3, false>(c, fp, smem, &full_groups); break;
+                    default: e = launch_fixed_n<4, false>(c, fp, smem, &full_groups); break;
+                    }
                 }
             }
             if (e != cudaSuccess) { c->set_error(std::string("k_learn_fixed launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }

@@ -613,33 +613,52 @@ struct FixedParams {
     uint32_t warp_smem_floats;     // F * (cpr + 1) * 4
 };
 
-// Block = FIXED_WARPS warps working in lock-step rounds (one record per warp and round).  After every round the
-// block combines its LR updates in shared memory: records that hit the same LR cell -- above all the constant
-// feature, which EVERY record hits (feature_buffer.rs:270-276) -- issue one accumulator atomic and one weight
-// reduction for the block instead of one per record.  Same-address atomics serialise in L2 (~4 ns each on B200,
-// tools/hotrow_microbench.cu), which capped the per-record version at ~180 M records/s.
-// The combined update is  acc += sum g_i^2 ;  w -= (sum g_i) * LUT[acc]  over the records of the round.
+// Block = FIXED_WARPS independent warps, one record per warp and round; nothing is exchanged between warps.
+//
+// LR updates (block_lr.rs:135-151) step from the accumulator value read at gather time -- the cell is loaded as one
+// float2 {w, acc} anyway -- so they are two fire-and-forget reductions and no warp waits for an atomic's return value.
+// The constant feature is special: EVERY record hits its cell (feature_buffer.rs:270-276), and same-address atomics
+// serialise in L2 (~4 ns each on B200, tools/hotrow_microbench.cu), which capped a version with one bias update per
+// record at ~180 M records/s.  Each warp therefore sums the bias gradients of FIXED_BIAS_PERIOD consecutive records
+// in a register and applies them as one update,  acc += sum g_i^2 ;  w -= (sum g_i) * LUT[acc]  (during the
+// concurrency ramp: every record).
+// History: two block-level schemes -- __syncthreads() every round with every warp scanning the others' pairs, then a
+// deferred mbarrier hand-over -- left the warps waiting for the slowest one of their block for 26 % / 45 % of the
+// stall samples (profiles/r01_c2_fixed_ncu_full.txt, profiles/r01_c2_fixed_mbar_top_stalls.txt).
 constexpr int FIXED_WARPS = 16;
-constexpr int FIXED_LR_MAX = 64; // LR entries per record the fast path supports (two per lane)
+constexpr int FIXED_LR_MAX = 64;       // LR entries per record the fast path supports (two per lane)
+constexpr int FIXED_BIAS_PERIOD = 16;  // records whose bias updates one warp combines
 
-template <int NCH>
-__global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const FixedParams p)
+__device__ __forceinline__ void red_add_f32(float *addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
+
+// one LR cell: acc += G2 ; w -= step(G, acc_seen + G2)
+__device__ __forceinline__ void fixed_lr_apply(const FixedParams &p, uint32_t optimizer, uint32_t h, float G, float G2, float acc_seen)
+{
+    float *cell = reinterpret_cast<float *>(p.lr + h);
+    float upd;
+    if (optimizer == OPT_SGD) upd = __fmul_rn(G, p.lr_lr);
+    else {
+        red_add_f32(cell + 1, G2);
+        upd = opt_step(optimizer, G, __fadd_rn(acc_seen, G2), p.lut_lr, p.lr_lr, p.lr_mpt);
+    }
+    red_add_f32(cell, -upd);
+}
+
+// OPTK: the optimizer as a compile-time constant (OPT_LUT: no powf code, no optimizer branches) or -1 = p.optimizer
+template <int NCH, bool SNAP, int MINB, int OPTK>
+__global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const FixedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIXED_WARPS;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     float4 *S = reinterpret_cast<float4 *>(smem_raw) + (size_t)wib * (p.warp_smem_floats / 4);
-    // LR exchange area, double-buffered by round parity: [2][NW][FIXED_LR_MAX] hashes then gradients
-    uint32_t *x_hash = reinterpret_cast<uint32_t *>(smem_raw + (size_t)NW * p.warp_smem_floats * 4);
-    float *x_grad = reinterpret_cast<float *>(x_hash + 2 * NW * FIXED_LR_MAX);
+    const uint32_t optimizer = OPTK < 0 ? p.optimizer : (uint32_t)OPTK;
     const uint32_t F = p.F, k = p.k, cpr = p.cpr, row_stride = cpr + 1, k4 = k >> 2;
     const uint32_t n_chunks = F * cpr;
     uint32_t n_warps = gridDim.x * NW;
     if (p.max_groups && p.max_groups < n_warps) n_warps = p.max_groups;
-    const uint32_t n_blocks = (n_warps + NW - 1) / NW;
-    if (blockIdx.x >= n_blocks) return;
     const uint32_t gw = blockIdx.x * NW + wib; // global warp index
-    const bool warp_on = gw < n_warps;          // the ramp may leave the last block partly idle
+    if (gw >= n_warps) return;                 // the ramp may leave the last block partly idle
 
     // static per-lane geometry: which chunk(s) I own and where my partner lives
     uint32_t my_e[NCH], my_c[NCH], part_off[NCH], my_off[NCH];
@@ -656,147 +675,151 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const Fixed
         diag[t] = (z == e);
     }
     const uint32_t my_field_ns = lane < F ? __ldg(p.field_ns + lane) : 0;
+    // the lane / register slot that holds the constant feature, and its combined update
+    const bool bias_lane = p.add_constant && lane == (int)(p.n_combos & 31u);
+    const int bias_r = (int)(p.n_combos >> 5);
+    const uint32_t bias_h = 11650396u & p.lr_mask; // feature_buffer.rs:270-276
+    const uint32_t bias_period = !p.update ? 0xffffffffu : p.max_groups ? 1u : (uint32_t)FIXED_BIAS_PERIOD; // predict: the cell never changes
+    float bias_G = 0.0f, bias_G2 = 0.0f;
+    float2 bias_cell = bias_lane ? __ldcg(p.lr + bias_h) : make_float2(0.f, 0.f); // {w, acc} as of the last refresh
+    uint32_t bias_n = 0;
 
-    for (uint32_t round = 0;; round++) {
-        const uint32_t base = round * n_warps; // round r handles records [r * n_warps, (r+1) * n_warps), one per active warp
-        if (base >= p.n_examples) break;       // uniform over the grid
-        const uint32_t ex = p.ex_begin + base + gw;
-        bool live = warp_on && base + gw < p.n_examples;
-        uint32_t *xh = x_hash + ((round & 1) * NW + wib) * FIXED_LR_MAX;
-        float *xg = x_grad + ((round & 1) * NW + wib) * FIXED_LR_MAX;
+    // the record's header slot of my field is fetched one round ahead: the record stream comes from HBM, and the load
+    // also pulls the record's sectors into L1 for the label / importance / LR reads of the round that uses it
+    auto rec_of = [&](uint32_t e_) -> const uint32_t * {
+        return p.records + (p.rec_off ? (size_t)(__ldg(p.rec_off + e_) - p.off_base) : (size_t)e_ * p.fixed_len);
+    };
+    uint32_t slot_next = 0x80000000u;
+    if (gw < p.n_examples && lane < F) slot_next = __ldg(rec_of(p.ex_begin + gw) + 3 + my_field_ns);
+
+    for (uint32_t base = gw; base < p.n_examples; base += n_warps) { // records gw, gw + n_warps, ...
+        const uint32_t ex = p.ex_begin + base;
+        const uint32_t slot = slot_next;
+        slot_next = 0x80000000u;
+        if (base + n_warps < p.n_examples && lane < F) slot_next = __ldg(rec_of(ex + n_warps) + 3 + my_field_ns);
+
+        const uint32_t *rec = rec_of(ex);
+        // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
+        bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
         uint32_t lr_h[2] = {0, 0};
-        float lr_g[2] = {0.0f, 0.0f}; // this record's LR gradients (0 = nothing to apply)
-
-        if (live) {
-            const uint32_t *rec = p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len);
-            // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
-            const uint32_t slot = lane < F ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
-            bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
-            float lr_v[2]; bool lr_ok[2];
+        float lr_v[2] = {0.0f, 0.0f};
+        bool lr_ok[2] = {false, false};
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
-                const uint32_t i = lane + 32 * r;
-                lr_ok[r] = false; lr_v[r] = 0.0f;
-                if (i < p.n_combos) {
-                    const uint32_t o0 = __ldg(p.combo_off + i), o1 = __ldg(p.combo_off + i + 1);
-                    uint32_t h = 0; bool ok = true;
-                    for (uint32_t o = o0; o < o1; o++) {
-                        const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
-                        if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
-                        h = (o == o0) ? sl : ((h * 16777619u) ^ sl); // feature_buffer.rs:239-251
-                    }
-                    lr_ok[r] = ok; lr_h[r] = h & p.lr_mask; lr_v[r] = __ldg(p.combo_weight + i); // value 1.0 * combo weight
-                } else if (i == p.n_combos && p.add_constant) {
-                    lr_ok[r] = true; lr_h[r] = 11650396u & p.lr_mask; lr_v[r] = 1.0f;       // feature_buffer.rs:270-276
+        for (int r = 0; r < 2; r++) {
+            const uint32_t i = lane + 32 * r;
+            if (i < p.n_combos) {
+                const uint32_t o0 = __ldg(p.combo_off + i), o1 = __ldg(p.combo_off + i + 1);
+                uint32_t h = 0; bool ok = true;
+                for (uint32_t o = o0; o < o1; o++) {
+                    const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
+                    if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
+                    h = (o == o0) ? sl : ((h * 16777619u) ^ sl); // feature_buffer.rs:239-251
                 }
-            }
-            if (__any_sync(0xffffffffu, bad)) {
-                if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
-                live = false;
-            } else {
-                const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
-
-                // ---- gather: one 128-bit load per chunk ----
-                float4 v[NCH];
-                uint32_t hbase[NCH]; bool pres[NCH];
-#pragma unroll
-                for (int t = 0; t < NCH; t++) {
-                    const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
-                    pres[t] = act[t] && sl != 0x80000000u;
-                    hbase[t] = (sl & p.ffm_mask) + 4 * my_c[t];
-                    v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-                float lrw[2];
-#pragma unroll
-                for (int r = 0; r < 2; r++) lrw[r] = lr_ok[r] ? __ldcg(p.lr + lr_h[r]).x : 0.0f;
-                __syncwarp(); // the previous round's partner reads are done
-#pragma unroll
-                for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
-                __syncwarp();
-
-                // ---- forward ----
-                float part = 0.0f;
-                float4 pv[NCH];
-#pragma unroll
-                for (int t = 0; t < NCH; t++) {
-                    pv[t] = act[t] ? S[part_off[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (act[t] && !diag[t]) {
-                        float sd = __fmul_rn(v[t].x, pv[t].x);
-                        sd = __fadd_rn(sd, __fmul_rn(v[t].y, pv[t].y));
-                        sd = __fadd_rn(sd, __fmul_rn(v[t].z, pv[t].z));
-                        sd = __fadd_rn(sd, __fmul_rn(v[t].w, pv[t].w));
-                        part += sd;
-                    }
-                }
-                part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
-#pragma unroll
-                for (int r = 0; r < 2; r++) if (lr_ok[r]) part += __fmul_rn(lrw[r], lr_v[r]);
-                const float wsum = warp_sum(part);
-
-                float pr, g;
-                if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
-                else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
-                else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
-                else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
-                if (lane == 0) p.preds[ex] = pr;
-
-                if (p.update && importance != 0.0f && g != 0.0f) {
-                    // ---- FFM update: grad of my chunk = g * partner chunk (values are 1.0); diagonal chunks get exactly 0 ----
-#pragma unroll
-                    for (int t = 0; t < NCH; t++) {
-                        if (!pres[t] || diag[t]) continue;
-                        const float gx = __fmul_rn(g, pv[t].x), gy = __fmul_rn(g, pv[t].y), gz = __fmul_rn(g, pv[t].z), gw = __fmul_rn(g, pv[t].w);
-                        if (gx == 0.0f && gy == 0.0f && gz == 0.0f && gw == 0.0f) continue; // partner field absent
-                        float4 upd;
-                        if (p.optimizer == OPT_SGD) {
-                            upd = make_float4(-__fmul_rn(gx, p.ffm_lr), -__fmul_rn(gy, p.ffm_lr), -__fmul_rn(gz, p.ffm_lr), -__fmul_rn(gw, p.ffm_lr));
-                        } else {
-                            const float4 gg = make_float4(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz), __fmul_rn(gw, gw));
-                            const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
-                            upd.x = -opt_step(p.optimizer, gx, acc_after(old.x, gx), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                            upd.y = -opt_step(p.optimizer, gy, acc_after(old.y, gy), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                            upd.z = -opt_step(p.optimizer, gz, acc_after(old.z, gz), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                            upd.w = -opt_step(p.optimizer, gw, acc_after(old.w, gw), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                        }
-                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + hbase[t]), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
-                    }
-#pragma unroll
-                    for (int r = 0; r < 2; r++) if (lr_ok[r]) lr_g[r] = __fmul_rn(g, lr_v[r]);
-                }
+                lr_ok[r] = ok; lr_h[r] = h & p.lr_mask; lr_v[r] = __ldg(p.combo_weight + i); // value 1.0 * combo weight
+            } else if (i == p.n_combos && p.add_constant) {
+                lr_ok[r] = true; lr_h[r] = bias_h; lr_v[r] = 1.0f;
             }
         }
+        if (__any_sync(0xffffffffu, bad)) {
+            if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+            continue;
+        }
+        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
 
-        // ---- LR update, combined over the block's records of this round (block_lr.rs:135-151) ----
-        if (p.update) {
+        // ---- gather: one 128-bit load per chunk (two with the accumulator snapshot) ----
+        float4 v[NCH], a[NCH];
+        uint32_t hbase[NCH]; bool pres[NCH];
 #pragma unroll
-            for (int r = 0; r < 2; r++) { xh[lane + 32 * r] = lr_h[r]; xg[lane + 32 * r] = lr_g[r]; }
-            __syncthreads();
-            const uint32_t *bh = x_hash + (round & 1) * NW * FIXED_LR_MAX;
-            const float *bg = x_grad + (round & 1) * NW * FIXED_LR_MAX;
+        for (int t = 0; t < NCH; t++) {
+            const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
+            pres[t] = act[t] && sl != 0x80000000u;
+            hbase[t] = (sl & p.ffm_mask) + 4 * my_c[t];
+            v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (SNAP) a[t] = (pres[t] && !diag[t] && p.update) ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_acc + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        float2 lrw[2];
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            // the bias cell is read by EVERY record: 5e8 loads/s of one address queue up in its L2 slice (they were the
+            // longest stall of the kernel, profiles/r01_c2_fixed_indep_top_stalls.txt), so a warp keeps the cell in a
+            // register and re-reads it when it applies its combined bias update
+            if (bias_lane && r == bias_r) lrw[r] = bias_cell;
+            else lrw[r] = lr_ok[r] ? __ldcg(p.lr + lr_h[r]) : make_float2(0.f, 0.f);
+        }
+        __syncwarp(); // the previous round's partner reads are done
+#pragma unroll
+        for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
+        __syncwarp();
+
+        // ---- forward ----
+        float part = 0.0f;
+        float4 pv[NCH];
+#pragma unroll
+        for (int t = 0; t < NCH; t++) {
+            pv[t] = act[t] ? S[part_off[t]] : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (act[t] && !diag[t]) {
+                float sd = __fmul_rn(v[t].x, pv[t].x);
+                sd = __fadd_rn(sd, __fmul_rn(v[t].y, pv[t].y));
+                sd = __fadd_rn(sd, __fmul_rn(v[t].z, pv[t].z));
+                sd = __fadd_rn(sd, __fmul_rn(v[t].w, pv[t].w));
+                part += sd;
+            }
+        }
+        part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
+#pragma unroll
+        for (int r = 0; r < 2; r++) if (lr_ok[r]) part += __fmul_rn(lrw[r].x, lr_v[r]);
+        const float wsum = warp_sum(part);
+
+        float pr, g;
+        if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+        else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+        else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+        else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
+        if (lane == 0) p.preds[ex] = pr;
+
+        if (p.update && importance != 0.0f && g != 0.0f) {
+            // ---- FFM update: grad of my chunk = g * partner chunk (values are 1.0); diagonal chunks get exactly 0 ----
+#pragma unroll
+            for (int t = 0; t < NCH; t++) {
+                if (!pres[t] || diag[t]) continue;
+                const float gx = __fmul_rn(g, pv[t].x), gy = __fmul_rn(g, pv[t].y), gz = __fmul_rn(g, pv[t].z), gw = __fmul_rn(g, pv[t].w);
+                if (gx == 0.0f && gy == 0.0f && gz == 0.0f && gw == 0.0f) continue; // partner field absent
+                float4 upd;
+                if (optimizer == OPT_SGD) {
+                    upd = make_float4(-__fmul_rn(gx, p.ffm_lr), -__fmul_rn(gy, p.ffm_lr), -__fmul_rn(gz, p.ffm_lr), -__fmul_rn(gw, p.ffm_lr));
+                } else {
+                    const float4 gg = make_float4(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz), __fmul_rn(gw, gw));
+                    float4 old;
+                    if (SNAP) {
+                        old = a[t];
+                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_acc + hbase[t]), "f"(gg.x), "f"(gg.y), "f"(gg.z), "f"(gg.w) : "memory");
+                    } else old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
+                    upd.x = -opt_step(optimizer, gx, __fadd_rn(old.x, gg.x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.y = -opt_step(optimizer, gy, __fadd_rn(old.y, gg.y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.z = -opt_step(optimizer, gz, __fadd_rn(old.z, gg.z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.w = -opt_step(optimizer, gw, __fadd_rn(old.w, gg.w), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                }
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + hbase[t]), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+            }
+            // ---- LR update; the bias is summed over bias_period records first ----
 #pragma unroll
             for (int r = 0; r < 2; r++) {
-                if (lr_g[r] == 0.0f) continue;
-                const uint32_t i = lane + 32 * r;
-                bool first = true;
-                for (int w2 = 0; w2 < wib; w2++)
-                    if (bg[w2 * FIXED_LR_MAX + i] != 0.0f && bh[w2 * FIXED_LR_MAX + i] == lr_h[r]) { first = false; break; }
-                if (!first) continue; // an earlier warp of the block applies this cell for all of us
-                float G = lr_g[r], G2 = __fmul_rn(lr_g[r], lr_g[r]);
-                for (int w2 = wib + 1; w2 < NW; w2++) {
-                    const float g2 = bg[w2 * FIXED_LR_MAX + i];
-                    if (g2 != 0.0f && bh[w2 * FIXED_LR_MAX + i] == lr_h[r]) { G += g2; G2 += g2 * g2; }
-                }
-                float *cell = reinterpret_cast<float *>(p.lr + lr_h[r]);
-                float upd;
-                if (p.optimizer == OPT_SGD) upd = __fmul_rn(G, p.lr_lr);
-                else {
-                    const float old = atomicAdd(cell + 1, G2);
-                    upd = opt_step(p.optimizer, G, __fadd_rn(old, G2), p.lut_lr, p.lr_lr, p.lr_mpt);
-                }
-                atomicAdd(cell, -upd);
+                if (!lr_ok[r]) continue;
+                const float gl = __fmul_rn(g, lr_v[r]);
+                if (bias_lane && r == bias_r) {
+                    bias_G = __fadd_rn(bias_G, gl); bias_G2 = __fadd_rn(bias_G2, __fmul_rn(gl, gl));
+                } else if (gl != 0.0f) fixed_lr_apply(p, optimizer, lr_h[r], gl, __fmul_rn(gl, gl), lrw[r].y);
             }
+        }
+        if (++bias_n >= bias_period) {
+            if (bias_lane) {
+                if (bias_G != 0.0f) fixed_lr_apply(p, optimizer, bias_h, bias_G, bias_G2, bias_cell.y);
+                bias_cell = __ldcg(p.lr + bias_h); // consumed a round later
+            }
+            bias_G = 0.0f; bias_G2 = 0.0f; bias_n = 0;
         }
     }
+    if (bias_lane && bias_G != 0.0f) fixed_lr_apply(p, optimizer, bias_h, bias_G, bias_G2, bias_cell.y);
 }
 
 // ---------------------------------------------------------------------------------------------
