@@ -95,8 +95,6 @@ struct fwgpu_ctx {
     bool fast_ok = false;     // k_learn_fixed applies to this model (one namespace per field, k % 4 == 0, ...)
     bool fast_enabled = true; // FWGPU_FAST=0 turns the fused kernel off (measurement / debugging)
     uint32_t fast_nch = 1;
-    int fast_minb = 3;        // k_learn_fixed blocks per SM the register budget is set for (FWGPU_FIXED_MINB=2: 64 registers, 32 warps per SM)
-    bool fast_snap = false;   // k_learn_fixed steps from the accumulator values read at gather time (no ATOMG round trip); FWGPU_SNAP=0: from the atomics' return values
     bool fast_cta = false;    // wide model: one block per record (k_learn_fixed_cta) instead of one warp
     int fast_ub = 2;
     uint32_t *err_flag = nullptr;
@@ -421,8 +419,6 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         c->fast_ok = ok;
         c->fast_nch = n_chunks <= 32 ? 1 : n_chunks <= 64 ? 2 : n_chunks <= 96 ? 3 : 4;
         if (const char *t = getenv("FWGPU_FAST")) c->fast_enabled = atoi(t) != 0;
-        if (const char *t = getenv("FWGPU_SNAP")) c->fast_snap = atoi(t) != 0;
-        if (const char *t = getenv("FWGPU_FIXED_MINB")) c->fast_minb = atoi(t);
     }
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
     if (const char *t = getenv("FWGPU_MINB")) c->minb = atoi(t);
@@ -709,9 +705,9 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
 }
 
 // ---- fused fast path (k_learn_fixed) -----------------------------------------------------------
-template <int NCH, bool SNAP, int MINB, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+template <int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
 {
-    auto kern = k_learn_fixed<NCH, SNAP, MINB, OPTK>;
+    auto kern = k_learn_fixed<NCH, NLR, OPTK>;
     constexpr int NW = FIXED_WARPS;
     static thread_local size_t configured = 0;
     if (smem > configured) {
@@ -732,11 +728,12 @@ template <int NCH, bool SNAP, int MINB, int OPTK> static cudaError_t launch_fixe
     return cudaGetLastError();
 }
 
-// AdagradLUT (the reference's default under --adaptive) gets its own instantiation; Flex / SGD share the generic one
-template <int NCH, bool SNAP, int MINB = 3> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+// AdagradLUT (the reference's default under --adaptive) and "at most 32 LR entries" get their own instantiations
+template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
 {
-    if (p.optimizer == OPT_LUT) return launch_fixed_k<NCH, SNAP, MINB, (int)OPT_LUT>(c, p, smem, full_groups);
-    return launch_fixed_k<NCH, SNAP, MINB, -1>(c, p, smem, full_groups);
+    const bool one = p.n_combos + (p.add_constant ? 1u : 0u) <= 32;
+    if (p.optimizer == OPT_LUT) return one ? launch_fixed_k<NCH, 1, (int)OPT_LUT>(c, p, smem, full_groups) : launch_fixed_k<NCH, 2, (int)OPT_LUT>(c, p, smem, full_groups);
+    return one ? launch_fixed_k<NCH, 1, -1>(c, p, smem, full_groups) : launch_fixed_k<NCH, 2, -1>(c, p, smem, full_groups);
 }
 
 template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
@@ -1137,27 +1134,11 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 }
             } else {
                 ProfScope ps(c, 0);
-                if (c->fast_snap && c->fast_minb == 2) {
-                    switch (c->fast_nch) {
-                    case 1: e = launch_fixed_n<1, true, 2>(c, fp, smem, &full_groups); break;
-                    case 2: e = launch_fixed_n<2, true, 2>(c, fp, smem, &full_groups); break;
-                    case 3: e = launch_fixed_n<3, true, 2>(c, fp, smem, &full_groups); break;
-                    default: e = launch_fixed_n<4, true, 2>(c, fp, smem, &full_groups); break;
-                    }
-                } else if (c->fast_snap) {
-                    switch (c->fast_nch) {
-                    case 1: e = launch_fixed_n<1, true>(c, fp, smem, &full_groups); break;
-                    case 2: e = launch_fixed_n<2, true>(c, fp, smem, &full_groups); break;
-                    case 3: e = launch_fixed_n<3, true>(c, fp, smem, &full_groups); break;
-                    default: e = launch_fixed_n<4, true>(c, fp, smem, &full_groups); break;
-                    }
-                } else {
-                    switch (c->fast_nch) {
-                    case 1: e = launch_fixed_n<1, false>(c, fp, smem, &full_groups); break;
-                    case 2: e = launch_fixed_n<2, false>(c, fp, smem, &full_groups); break;
-                    case 3: e = launch_fixed_n<3, false>(c, fp, smem, &full_groups); break;
-                    default: e = launch_fixed_n<4, false>(c, fp, smem, &full_groups); break;
-                    }
+                switch (c->fast_nch) {
+                case 1: e = launch_fixed_n<1>(c, fp, smem, &full_groups); break;
+                case 2: e = launch_fixed_n<2>(c, fp, smem, &full_groups); break;
+                case 3: e = launch_fixed_n<3>(c, fp, smem, &full_groups); break;
+                default: e = launch_fixed_n<4>(c, fp, smem, &full_groups); break;
                 }
             }
             if (e != cudaSuccess) { c->set_error(std::string("k_learn_fixed launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }

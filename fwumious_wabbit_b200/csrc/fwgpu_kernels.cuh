@@ -644,9 +644,12 @@ __device__ __forceinline__ void fixed_lr_apply(const FixedParams &p, uint32_t op
     red_add_f32(cell, -upd);
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
+// NCH : 16-byte chunks per lane (ceil(F*F*k/4 / 32));  NLR : LR entries per lane (1 when combos + constant <= 32);
 // OPTK: the optimizer as a compile-time constant (OPT_LUT: no powf code, no optimizer branches) or -1 = p.optimizer
-template <int NCH, bool SNAP, int MINB, int OPTK>
-__global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const FixedParams p)
+template <int NCH, int NLR, int OPTK>
+__global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const FixedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NW = FIXED_WARPS;
@@ -661,7 +664,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const Fi
     if (gw >= n_warps) return;                 // the ramp may leave the last block partly idle
 
     // static per-lane geometry: which chunk(s) I own and where my partner lives
-    uint32_t my_e[NCH], my_c[NCH], part_off[NCH], my_off[NCH];
+    uint32_t my_e[NCH], my_c4[NCH], part_off[NCH], my_off[NCH];
     bool act[NCH], diag[NCH];
 #pragma unroll
     for (int t = 0; t < NCH; t++) {
@@ -669,83 +672,87 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const Fi
         act[t] = j < n_chunks;
         const uint32_t e = act[t] ? fdiv(j, p.div_cpr) : 0, c = act[t] ? j - e * cpr : 0;
         const uint32_t z = fdiv(c, p.div_k4), q4 = c - z * k4; // chunk c = quarter q4 of the block towards field z
-        my_e[t] = e; my_c[t] = c;
+        my_e[t] = e; my_c4[t] = 4 * c;
         my_off[t] = e * row_stride + c;
         part_off[t] = z * row_stride + e * k4 + q4;              // row z, its block towards field e, same quarter
         diag[t] = (z == e);
     }
     const uint32_t my_field_ns = lane < F ? __ldg(p.field_ns + lane) : 0;
-    // the lane / register slot that holds the constant feature, and its combined update
-    const bool bias_lane = p.add_constant && lane == (int)(p.n_combos & 31u);
-    const int bias_r = (int)(p.n_combos >> 5);
+    // static per-lane LR entries: lane i (+32) owns combo i; the entry after the last combo is the constant feature
+    uint32_t c_o0[NLR], c_len[NLR]; // the combo's namespaces are combo_ns[c_o0 .. c_o0 + c_len); 0 = no entry, 0xffffffff = constant
+    float c_w[NLR];
+#pragma unroll
+    for (int r = 0; r < NLR; r++) {
+        const uint32_t i = lane + 32 * r;
+        c_o0[r] = 0; c_len[r] = 0; c_w[r] = 0.0f;
+        if (i < p.n_combos) { c_o0[r] = __ldg(p.combo_off + i); c_len[r] = __ldg(p.combo_off + i + 1) - c_o0[r]; c_w[r] = __ldg(p.combo_weight + i); }
+        else if (i == p.n_combos && p.add_constant) { c_len[r] = 0xffffffffu; c_w[r] = 1.0f; }
+    }
     const uint32_t bias_h = 11650396u & p.lr_mask; // feature_buffer.rs:270-276
+    // the combined bias update of this warp (see above) and the cell as of the last refresh
     const uint32_t bias_period = !p.update ? 0xffffffffu : p.max_groups ? 1u : (uint32_t)FIXED_BIAS_PERIOD; // predict: the cell never changes
+    const bool bias_lane = c_len[NLR - 1] == 0xffffffffu || c_len[0] == 0xffffffffu;
     float bias_G = 0.0f, bias_G2 = 0.0f;
-    float2 bias_cell = bias_lane ? __ldcg(p.lr + bias_h) : make_float2(0.f, 0.f); // {w, acc} as of the last refresh
+    float2 bias_cell = bias_lane ? __ldcg(p.lr + bias_h) : make_float2(0.f, 0.f);
     uint32_t bias_n = 0;
 
-    // the record's header slot of my field is fetched one round ahead: the record stream comes from HBM, and the load
-    // also pulls the record's sectors into L1 for the label / importance / LR reads of the round that uses it
+    // The record stream comes from HBM: every lane that reads a header slot prefetches its word of the NEXT record of
+    // this warp into L1 (no register, nothing waits), so the loads below hit L1.  With an offset array the offset of
+    // the record after next is prefetched as well.
     auto rec_of = [&](uint32_t e_) -> const uint32_t * {
         return p.records + (p.rec_off ? (size_t)(__ldg(p.rec_off + e_) - p.off_base) : (size_t)e_ * p.fixed_len);
     };
-    uint32_t slot_next = 0x80000000u;
-    if (gw < p.n_examples && lane < F) slot_next = __ldg(rec_of(p.ex_begin + gw) + 3 + my_field_ns);
+    if (gw < p.n_examples && lane < F) prefetch_l1(rec_of(p.ex_begin + gw) + 3 + my_field_ns);
 
     for (uint32_t base = gw; base < p.n_examples; base += n_warps) { // records gw, gw + n_warps, ...
         const uint32_t ex = p.ex_begin + base;
-        const uint32_t slot = slot_next;
-        slot_next = 0x80000000u;
-        if (base + n_warps < p.n_examples && lane < F) slot_next = __ldg(rec_of(ex + n_warps) + 3 + my_field_ns);
+        if (base + n_warps < p.n_examples && lane < F) prefetch_l1(rec_of(ex + n_warps) + 3 + my_field_ns);
+        if (p.rec_off && base + 2 * n_warps < p.n_examples && lane == 0) prefetch_l1(p.rec_off + ex + 2 * n_warps);
 
         const uint32_t *rec = rec_of(ex);
         // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
+        const uint32_t slot = lane < F ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
         bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
-        uint32_t lr_h[2] = {0, 0};
-        float lr_v[2] = {0.0f, 0.0f};
-        bool lr_ok[2] = {false, false};
+        uint32_t lr_h[NLR];
+        bool lr_ok[NLR];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const uint32_t i = lane + 32 * r;
-            if (i < p.n_combos) {
-                const uint32_t o0 = __ldg(p.combo_off + i), o1 = __ldg(p.combo_off + i + 1);
-                uint32_t h = 0; bool ok = true;
-                for (uint32_t o = o0; o < o1; o++) {
-                    const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
-                    if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
-                    h = (o == o0) ? sl : ((h * 16777619u) ^ sl); // feature_buffer.rs:239-251
+        for (int r = 0; r < NLR; r++) {
+            lr_h[r] = bias_h; lr_ok[r] = c_len[r] != 0;
+            if (c_len[r] - 1u < 0xfffffffeu) { // a combo: chain its namespaces' hashes (feature_buffer.rs:239-251)
+                uint32_t h = 0;
+                for (uint32_t o = 0; o < c_len[r]; o++) {
+                    const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + c_o0[r] + o));
+                    if (sl & 0x80000000u) { lr_ok[r] = false; if (sl != 0x80000000u) bad = true; }
+                    h = o ? ((h * 16777619u) ^ sl) : sl;
                 }
-                lr_ok[r] = ok; lr_h[r] = h & p.lr_mask; lr_v[r] = __ldg(p.combo_weight + i); // value 1.0 * combo weight
-            } else if (i == p.n_combos && p.add_constant) {
-                lr_ok[r] = true; lr_h[r] = bias_h; lr_v[r] = 1.0f;
+                lr_h[r] = h & p.lr_mask;
             }
         }
         if (__any_sync(0xffffffffu, bad)) {
             if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
             continue;
         }
-        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
 
-        // ---- gather: one 128-bit load per chunk (two with the accumulator snapshot) ----
-        float4 v[NCH], a[NCH];
+        // ---- gather: one 128-bit load per chunk ----
+        float4 v[NCH];
         uint32_t hbase[NCH]; bool pres[NCH];
 #pragma unroll
         for (int t = 0; t < NCH; t++) {
             const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
             pres[t] = act[t] && sl != 0x80000000u;
-            hbase[t] = (sl & p.ffm_mask) + 4 * my_c[t];
+            hbase[t] = (sl & p.ffm_mask) + my_c4[t];
             v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (SNAP) a[t] = (pres[t] && !diag[t] && p.update) ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_acc + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        float2 lrw[2];
+        float2 lrw[NLR];
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
+        for (int r = 0; r < NLR; r++) {
             // the bias cell is read by EVERY record: 5e8 loads/s of one address queue up in its L2 slice (they were the
             // longest stall of the kernel, profiles/r01_c2_fixed_indep_top_stalls.txt), so a warp keeps the cell in a
             // register and re-reads it when it applies its combined bias update
-            if (bias_lane && r == bias_r) lrw[r] = bias_cell;
+            if (c_len[r] == 0xffffffffu) lrw[r] = bias_cell;
             else lrw[r] = lr_ok[r] ? __ldcg(p.lr + lr_h[r]) : make_float2(0.f, 0.f);
         }
+        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
         __syncwarp(); // the previous round's partner reads are done
 #pragma unroll
         for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
@@ -767,7 +774,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const Fi
         }
         part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
 #pragma unroll
-        for (int r = 0; r < 2; r++) if (lr_ok[r]) part += __fmul_rn(lrw[r].x, lr_v[r]);
+        for (int r = 0; r < NLR; r++) if (lr_ok[r]) part += __fmul_rn(lrw[r].x, c_w[r]);
         const float wsum = warp_sum(part);
 
         float pr, g;
@@ -789,11 +796,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const Fi
                     upd = make_float4(-__fmul_rn(gx, p.ffm_lr), -__fmul_rn(gy, p.ffm_lr), -__fmul_rn(gz, p.ffm_lr), -__fmul_rn(gw, p.ffm_lr));
                 } else {
                     const float4 gg = make_float4(__fmul_rn(gx, gx), __fmul_rn(gy, gy), __fmul_rn(gz, gz), __fmul_rn(gw, gw));
-                    float4 old;
-                    if (SNAP) {
-                        old = a[t];
-                        asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_acc + hbase[t]), "f"(gg.x), "f"(gg.y), "f"(gg.z), "f"(gg.w) : "memory");
-                    } else old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
+                    const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + hbase[t]), gg);
                     upd.x = -opt_step(optimizer, gx, __fadd_rn(old.x, gg.x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
                     upd.y = -opt_step(optimizer, gy, __fadd_rn(old.y, gg.y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
                     upd.z = -opt_step(optimizer, gz, __fadd_rn(old.z, gg.z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
@@ -803,12 +806,11 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, MINB) k_learn_fixed(const Fi
             }
             // ---- LR update; the bias is summed over bias_period records first ----
 #pragma unroll
-            for (int r = 0; r < 2; r++) {
+            for (int r = 0; r < NLR; r++) {
                 if (!lr_ok[r]) continue;
-                const float gl = __fmul_rn(g, lr_v[r]);
-                if (bias_lane && r == bias_r) {
-                    bias_G = __fadd_rn(bias_G, gl); bias_G2 = __fadd_rn(bias_G2, __fmul_rn(gl, gl));
-                } else if (gl != 0.0f) fixed_lr_apply(p, optimizer, lr_h[r], gl, __fmul_rn(gl, gl), lrw[r].y);
+                const float gl = __fmul_rn(g, c_w[r]);
+                if (c_len[r] == 0xffffffffu) { bias_G = __fadd_rn(bias_G, gl); bias_G2 = __fadd_rn(bias_G2, __fmul_rn(gl, gl)); }
+                else if (gl != 0.0f) fixed_lr_apply(p, optimizer, lr_h[r], gl, __fmul_rn(gl, gl), lrw[r].y);
             }
         }
         if (++bias_n >= bias_period) {

@@ -129,9 +129,11 @@ def test_head_records_sequential_mode(fast, monkeypatch):
     re = fw.Regressor(w.mi)
     got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
     assert np.max(np.abs(got - want)) <= TOL, np.max(np.abs(got - want))
+    # weights: the head's gradient sums are split over blocks and added atomically, so their summation order varies from
+    # run to run; once in a few thousand steps that flips an AdaGrad-LUT bucket of one weight (a step ~3e-5 apart)
     for l in range(re.nn_layer_count()):
-        np.testing.assert_allclose(re.get_nn(l)[0], ora.nn_weights(l), rtol=0, atol=2e-5)
-    np.testing.assert_allclose(re.get_ffm()[0], ora.ffm_weights, rtol=0, atol=2e-5)
+        np.testing.assert_allclose(re.get_nn(l)[0], ora.nn_weights(l), rtol=0, atol=5e-5)
+    np.testing.assert_allclose(re.get_ffm()[0], ora.ffm_weights, rtol=0, atol=5e-5)
     # predict-only pass over the same records on the trained model
     want_p = ora.learn_batch(util.oracle_translate_batch(spec, recs[:500], fixed_len=w.record_len), update=False)
     got_p = re.learn_records(recs[:500].reshape(-1), n_examples=500, update=False)
