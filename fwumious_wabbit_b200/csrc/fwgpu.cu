@@ -94,7 +94,7 @@ struct fwgpu_ctx {
     DevBuf rec[2], rec_off_dev[2], meta, lr_ent, ffm_ent, preds, csr, leftover;
     bool fast_ok = false;     // k_learn_fixed applies to this model (one namespace per field, k % 4 == 0, ...)
     bool fast_enabled = true; // FWGPU_FAST=0 turns the fused kernel off (measurement / debugging)
-    uint32_t fast_nch = 1;
+    bool fast_g16 = true;     // narrow models: two records per warp (FWGPU_G16=0: always one)
     bool fast_cta = false;    // wide model: one block per record (k_learn_fixed_cta) instead of one warp
     int fast_ub = 2;
     uint32_t *err_flag = nullptr;
@@ -417,7 +417,7 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         }
         if (const char *t = getenv("FWGPU_UB")) c->fast_ub = atoi(t);
         c->fast_ok = ok;
-        c->fast_nch = n_chunks <= 32 ? 1 : n_chunks <= 64 ? 2 : n_chunks <= 96 ? 3 : 4;
+        if (const char *t = getenv("FWGPU_G16")) c->fast_g16 = atoi(t) != 0;
         if (const char *t = getenv("FWGPU_FAST")) c->fast_enabled = atoi(t) != 0;
     }
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
@@ -705,10 +705,11 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
 }
 
 // ---- fused fast path (k_learn_fixed) -----------------------------------------------------------
-template <int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+template <int G, int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups)
 {
-    auto kern = k_learn_fixed<NCH, NLR, OPTK>;
-    constexpr int NW = FIXED_WARPS;
+    auto kern = k_learn_fixed<G, NCH, NLR, OPTK>;
+    constexpr int NW = FIXED_WARPS, RPW = 32 / G;
+    const size_t smem = (size_t)p.rec_smem_floats * 4 * NW * RPW; // the records' row transposes
     static thread_local size_t configured = 0;
     if (smem > configured) {
         cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -719,21 +720,38 @@ template <int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ct
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    uint32_t grid = std::min<uint32_t>((p.n_examples + NW - 1) / NW, (uint32_t)(c->num_sms * per_sm));
-    if (p.max_groups) grid = std::min<uint32_t>(grid, (p.max_groups + NW - 1) / NW);
-    *full_groups = (uint32_t)(c->num_sms * per_sm) * NW;
+    const uint32_t per_block = NW * RPW; // records in flight per block
+    uint32_t grid = std::min<uint32_t>((p.n_examples + per_block - 1) / per_block, (uint32_t)(c->num_sms * per_sm));
+    if (p.max_groups) grid = std::min<uint32_t>(grid, (p.max_groups + per_block - 1) / per_block);
+    *full_groups = (uint32_t)(c->num_sms * per_sm) * per_block;
     if (grid == 0) return cudaSuccess;
     kern<<<grid, NW * 32, smem, c->stream>>>(p);
     c->launches++;
     return cudaGetLastError();
 }
 
-// AdagradLUT (the reference's default under --adaptive) and "at most 32 LR entries" get their own instantiations
-template <int NCH> static cudaError_t launch_fixed_n(fwgpu_ctx *c, const FixedParams &p, size_t smem, uint32_t *full_groups)
+// AdagradLUT (the reference's default under --adaptive) gets its own instantiation; narrow models (F <= 16, at most 64
+// chunks and 16 LR entries) run two records per warp
+template <int G, int NCH, int NLR> static cudaError_t launch_fixed_o(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups)
 {
-    const bool one = p.n_combos + (p.add_constant ? 1u : 0u) <= 32;
-    if (p.optimizer == OPT_LUT) return one ? launch_fixed_k<NCH, 1, (int)OPT_LUT>(c, p, smem, full_groups) : launch_fixed_k<NCH, 2, (int)OPT_LUT>(c, p, smem, full_groups);
-    return one ? launch_fixed_k<NCH, 1, -1>(c, p, smem, full_groups) : launch_fixed_k<NCH, 2, -1>(c, p, smem, full_groups);
+    if (p.optimizer == OPT_LUT) return launch_fixed_k<G, NCH, NLR, (int)OPT_LUT>(c, p, full_groups);
+    return launch_fixed_k<G, NCH, NLR, -1>(c, p, full_groups);
+}
+template <int G, int NLR> static cudaError_t launch_fixed_g(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups)
+{
+    const uint32_t nch = (p.F * p.cpr + G - 1) / G;
+    switch (nch) {
+    case 1: return launch_fixed_o<G, 1, NLR>(c, p, full_groups);
+    case 2: return launch_fixed_o<G, 2, NLR>(c, p, full_groups);
+    case 3: return launch_fixed_o<G, 3, NLR>(c, p, full_groups);
+    default: return launch_fixed_o<G, 4, NLR>(c, p, full_groups);
+    }
+}
+static cudaError_t launch_fixed(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups)
+{
+    const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u), n_chunks = p.F * p.cpr;
+    if (c->fast_g16 && p.F <= 16 && n_chunks <= 64 && n_lr <= 16) return launch_fixed_g<16, 1>(c, p, full_groups);
+    return n_lr <= 32 ? launch_fixed_g<32, 1>(c, p, full_groups) : launch_fixed_g<32, 2>(c, p, full_groups);
 }
 
 template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
@@ -1100,8 +1118,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
         fp.add_constant = c->d.add_constant; fp.lr_mask = tp.lr_mask; fp.ffm_mask = tp.ffm_mask;
         fp.optimizer = c->optimizer; fp.lr_lr = c->d.learning_rate; fp.lr_mpt = -c->d.power_t; fp.ffm_lr = c->d.ffm_learning_rate; fp.ffm_mpt = -c->d.ffm_power_t;
         fp.update = update; fp.preds = (float *)c->preds.p; fp.leftover_idx = left_idx; fp.leftover_cnt = left_cnt;
-        fp.warp_smem_floats = c->F * (fp.cpr + 1) * 4;
-        const size_t smem = (size_t)fp.warp_smem_floats * 4 * FIXED_WARPS; // the warps' row transposes
+        fp.rec_smem_floats = c->F * (fp.cpr + 1) * 4;
         uint32_t done = 0;
         while (done < count) {
             uint32_t cnt = count - done, cap = 0;
@@ -1134,12 +1151,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 }
             } else {
                 ProfScope ps(c, 0);
-                switch (c->fast_nch) {
-                case 1: e = launch_fixed_n<1>(c, fp, smem, &full_groups); break;
-                case 2: e = launch_fixed_n<2>(c, fp, smem, &full_groups); break;
-                case 3: e = launch_fixed_n<3>(c, fp, smem, &full_groups); break;
-                default: e = launch_fixed_n<4>(c, fp, smem, &full_groups); break;
-                }
+                e = launch_fixed(c, fp, &full_groups);
             }
             if (e != cudaSuccess) { c->set_error(std::string("k_learn_fixed launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
             if (update) {

@@ -610,7 +610,7 @@ struct FixedParams {
     float *preds;
     uint32_t *leftover_idx, *leftover_cnt;
     uint32_t max_groups;
-    uint32_t warp_smem_floats;     // F * (cpr + 1) * 4
+    uint32_t rec_smem_floats;      // F * (cpr + 1) * 4: the transpose area of one record
 };
 
 // Block = FIXED_WARPS independent warps, one record per warp and round; nothing is exchanged between warps.
@@ -646,91 +646,99 @@ __device__ __forceinline__ void fixed_lr_apply(const FixedParams &p, uint32_t op
 
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
-// NCH : 16-byte chunks per lane (ceil(F*F*k/4 / 32));  NLR : LR entries per lane (1 when combos + constant <= 32);
+// G   : lanes per record (32, or 16 = two records per warp and round when F <= 16, F*F*k/4 <= 64 chunks and at most 16
+//       LR entries: the per-record overhead -- translate, sigmoid, reductions -- is then shared by two records and
+//       every wait for L2 covers two records);
+// NCH : 16-byte chunks per lane (ceil(F*F*k/4 / G));  NLR : LR entries per lane (ceil((combos + constant) / G));
 // OPTK: the optimizer as a compile-time constant (OPT_LUT: no powf code, no optimizer branches) or -1 = p.optimizer
-template <int NCH, int NLR, int OPTK>
-__global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const FixedParams p)
+template <int G, int NCH, int NLR, int OPTK>
+__global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_fixed(const FixedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NW = FIXED_WARPS;
+    constexpr int NW = FIXED_WARPS, RPW = 32 / G; // records per warp and round
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float4 *S = reinterpret_cast<float4 *>(smem_raw) + (size_t)wib * (p.warp_smem_floats / 4);
+    const int sl = lane & (G - 1), sg = lane / G; // lane within the record's group, group within the warp
+    const int g0 = sg * G;                        // first lane of my group
+    const uint32_t gmask = G == 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << g0);
+    float4 *S = reinterpret_cast<float4 *>(smem_raw) + (size_t)(wib * RPW + sg) * (p.rec_smem_floats / 4);
     const uint32_t optimizer = OPTK < 0 ? p.optimizer : (uint32_t)OPTK;
     const uint32_t F = p.F, k = p.k, cpr = p.cpr, row_stride = cpr + 1, k4 = k >> 2;
     const uint32_t n_chunks = F * cpr;
-    uint32_t n_warps = gridDim.x * NW;
-    if (p.max_groups && p.max_groups < n_warps) n_warps = p.max_groups;
-    const uint32_t gw = blockIdx.x * NW + wib; // global warp index
-    if (gw >= n_warps) return;                 // the ramp may leave the last block partly idle
+    uint32_t n_groups = gridDim.x * NW * RPW;     // records in flight
+    if (p.max_groups && p.max_groups < n_groups) n_groups = p.max_groups;
+    const uint32_t wg0 = (blockIdx.x * NW + wib) * RPW; // this warp's first group
+    if (wg0 >= n_groups) return;                  // the ramp may leave the last block partly idle
+    const bool group_on = wg0 + sg < n_groups;
 
     // static per-lane geometry: which chunk(s) I own and where my partner lives
     uint32_t my_e[NCH], my_c4[NCH], part_off[NCH], my_off[NCH];
     bool act[NCH], diag[NCH];
 #pragma unroll
     for (int t = 0; t < NCH; t++) {
-        const uint32_t j = lane + 32 * t;
+        const uint32_t j = sl + G * t;
         act[t] = j < n_chunks;
         const uint32_t e = act[t] ? fdiv(j, p.div_cpr) : 0, c = act[t] ? j - e * cpr : 0;
         const uint32_t z = fdiv(c, p.div_k4), q4 = c - z * k4; // chunk c = quarter q4 of the block towards field z
-        my_e[t] = e; my_c4[t] = 4 * c;
+        my_e[t] = g0 + e; my_c4[t] = 4 * c;
         my_off[t] = e * row_stride + c;
         part_off[t] = z * row_stride + e * k4 + q4;              // row z, its block towards field e, same quarter
         diag[t] = (z == e);
     }
-    const uint32_t my_field_ns = lane < F ? __ldg(p.field_ns + lane) : 0;
-    // static per-lane LR entries: lane i (+32) owns combo i; the entry after the last combo is the constant feature
+    const uint32_t my_field_ns = sl < F ? __ldg(p.field_ns + sl) : 0;
+    // static per-lane LR entries: lane i (+G) owns combo i; the entry after the last combo is the constant feature
     uint32_t c_o0[NLR], c_len[NLR]; // the combo's namespaces are combo_ns[c_o0 .. c_o0 + c_len); 0 = no entry, 0xffffffff = constant
     float c_w[NLR];
+    bool bias_lane = false;
 #pragma unroll
     for (int r = 0; r < NLR; r++) {
-        const uint32_t i = lane + 32 * r;
+        const uint32_t i = sl + G * r;
         c_o0[r] = 0; c_len[r] = 0; c_w[r] = 0.0f;
         if (i < p.n_combos) { c_o0[r] = __ldg(p.combo_off + i); c_len[r] = __ldg(p.combo_off + i + 1) - c_o0[r]; c_w[r] = __ldg(p.combo_weight + i); }
-        else if (i == p.n_combos && p.add_constant) { c_len[r] = 0xffffffffu; c_w[r] = 1.0f; }
+        else if (i == p.n_combos && p.add_constant) { c_len[r] = 0xffffffffu; c_w[r] = 1.0f; bias_lane = true; }
     }
     const uint32_t bias_h = 11650396u & p.lr_mask; // feature_buffer.rs:270-276
-    // the combined bias update of this warp (see above) and the cell as of the last refresh
+    // the combined bias update of this group (see above) and the cell as of the last refresh
     const uint32_t bias_period = !p.update ? 0xffffffffu : p.max_groups ? 1u : (uint32_t)FIXED_BIAS_PERIOD; // predict: the cell never changes
-    const bool bias_lane = c_len[NLR - 1] == 0xffffffffu || c_len[0] == 0xffffffffu;
     float bias_G = 0.0f, bias_G2 = 0.0f;
     float2 bias_cell = bias_lane ? __ldcg(p.lr + bias_h) : make_float2(0.f, 0.f);
     uint32_t bias_n = 0;
 
     // The record stream comes from HBM: every lane that reads a header slot prefetches its word of the NEXT record of
-    // this warp into L1 (no register, nothing waits), so the loads below hit L1.  With an offset array the offset of
+    // its group into L1 (no register, nothing waits), so the loads below hit L1.  With an offset array the offset of
     // the record after next is prefetched as well.
     auto rec_of = [&](uint32_t e_) -> const uint32_t * {
         return p.records + (p.rec_off ? (size_t)(__ldg(p.rec_off + e_) - p.off_base) : (size_t)e_ * p.fixed_len);
     };
-    if (gw < p.n_examples && lane < F) prefetch_l1(rec_of(p.ex_begin + gw) + 3 + my_field_ns);
+    if (group_on && wg0 + sg < p.n_examples && sl < F) prefetch_l1(rec_of(p.ex_begin + wg0 + sg) + 3 + my_field_ns);
 
-    for (uint32_t base = gw; base < p.n_examples; base += n_warps) { // records gw, gw + n_warps, ...
-        const uint32_t ex = p.ex_begin + base;
-        if (base + n_warps < p.n_examples && lane < F) prefetch_l1(rec_of(ex + n_warps) + 3 + my_field_ns);
-        if (p.rec_off && base + 2 * n_warps < p.n_examples && lane == 0) prefetch_l1(p.rec_off + ex + 2 * n_warps);
+    for (uint32_t base0 = wg0; base0 < p.n_examples; base0 += n_groups) { // group g takes records g, g + n_groups, ...
+        const uint32_t base = base0 + sg, ex = p.ex_begin + base;
+        bool live = group_on && base < p.n_examples;
+        if (group_on && base + n_groups < p.n_examples && sl < F) prefetch_l1(rec_of(ex + n_groups) + 3 + my_field_ns);
+        if (p.rec_off && group_on && base + 2 * n_groups < p.n_examples && sl == 0) prefetch_l1(p.rec_off + ex + 2 * n_groups);
 
-        const uint32_t *rec = rec_of(ex);
+        const uint32_t *rec = live ? rec_of(ex) : p.records;
         // ---- translate (feature_buffer.rs:178-338) for in-place slots; anything else -> leftover ----
-        const uint32_t slot = lane < F ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
+        const uint32_t slot = (live && sl < F) ? __ldg(rec + 3 + my_field_ns) : 0x80000000u;
         bool bad = (slot & 0x80000000u) && slot != 0x80000000u;
         uint32_t lr_h[NLR];
         bool lr_ok[NLR];
 #pragma unroll
         for (int r = 0; r < NLR; r++) {
-            lr_h[r] = bias_h; lr_ok[r] = c_len[r] != 0;
-            if (c_len[r] - 1u < 0xfffffffeu) { // a combo: chain its namespaces' hashes (feature_buffer.rs:239-251)
+            lr_h[r] = bias_h; lr_ok[r] = live && c_len[r] != 0;
+            if (live && c_len[r] - 1u < 0xfffffffeu) { // a combo: chain its namespaces' hashes (feature_buffer.rs:239-251)
                 uint32_t h = 0;
                 for (uint32_t o = 0; o < c_len[r]; o++) {
-                    const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + c_o0[r] + o));
-                    if (sl & 0x80000000u) { lr_ok[r] = false; if (sl != 0x80000000u) bad = true; }
-                    h = o ? ((h * 16777619u) ^ sl) : sl;
+                    const uint32_t s_ = __ldg(rec + 3 + __ldg(p.combo_ns + c_o0[r] + o));
+                    if (s_ & 0x80000000u) { lr_ok[r] = false; if (s_ != 0x80000000u) bad = true; }
+                    h = o ? ((h * 16777619u) ^ s_) : s_;
                 }
                 lr_h[r] = h & p.lr_mask;
             }
         }
-        if (__any_sync(0xffffffffu, bad)) {
-            if (lane == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
-            continue;
+        if (__ballot_sync(0xffffffffu, bad) & gmask) { // my group's record does not fit the fast path
+            if (sl == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+            live = false;
         }
 
         // ---- gather: one 128-bit load per chunk ----
@@ -738,21 +746,22 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const Fixed
         uint32_t hbase[NCH]; bool pres[NCH];
 #pragma unroll
         for (int t = 0; t < NCH; t++) {
-            const uint32_t sl = __shfl_sync(0xffffffffu, slot, my_e[t]);
-            pres[t] = act[t] && sl != 0x80000000u;
-            hbase[t] = (sl & p.ffm_mask) + my_c4[t];
+            const uint32_t s_ = __shfl_sync(0xffffffffu, slot, my_e[t]);
+            pres[t] = live && act[t] && s_ != 0x80000000u;
+            hbase[t] = (s_ & p.ffm_mask) + my_c4[t];
             v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float2 lrw[NLR];
 #pragma unroll
         for (int r = 0; r < NLR; r++) {
             // the bias cell is read by EVERY record: 5e8 loads/s of one address queue up in its L2 slice (they were the
-            // longest stall of the kernel, profiles/r01_c2_fixed_indep_top_stalls.txt), so a warp keeps the cell in a
+            // longest stall of the kernel, profiles/r01_c2_fixed_indep_top_stalls.txt), so a group keeps the cell in a
             // register and re-reads it when it applies its combined bias update
+            lr_ok[r] = lr_ok[r] && live;
             if (c_len[r] == 0xffffffffu) lrw[r] = bias_cell;
             else lrw[r] = lr_ok[r] ? __ldcg(p.lr + lr_h[r]) : make_float2(0.f, 0.f);
         }
-        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
+        const float label = live ? (float)__ldg(rec + 1) : 0.0f, importance = live ? __uint_as_float(__ldg(rec + 2)) : 0.0f;
         __syncwarp(); // the previous round's partner reads are done
 #pragma unroll
         for (int t = 0; t < NCH; t++) if (act[t]) S[my_off[t]] = v[t];
@@ -775,16 +784,18 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, 3) k_learn_fixed(const Fixed
         part *= 0.5f; // every unordered field pair is seen from both sides; the triangle keeps 2*out[f][z], z < f
 #pragma unroll
         for (int r = 0; r < NLR; r++) if (lr_ok[r]) part += __fmul_rn(lrw[r].x, c_w[r]);
-        const float wsum = warp_sum(part);
+        float wsum = part;
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
 
         float pr, g;
         if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
         else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
         else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
         else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
-        if (lane == 0) p.preds[ex] = pr;
+        if (live && sl == 0) p.preds[ex] = pr;
 
-        if (p.update && importance != 0.0f && g != 0.0f) {
+        if (live && p.update && importance != 0.0f && g != 0.0f) {
             // ---- FFM update: grad of my chunk = g * partner chunk (values are 1.0); diagonal chunks get exactly 0 ----
 #pragma unroll
             for (int t = 0; t < NCH; t++) {
