@@ -749,7 +749,8 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
             const uint32_t s_ = __shfl_sync(0xffffffffu, slot, my_e[t]);
             pres[t] = live && act[t] && s_ != 0x80000000u;
             hbase[t] = (s_ & p.ffm_mask) + my_c4[t];
-            v[t] = pres[t] ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // own-field chunks are never read: a single-valued field has no interaction with itself (block_ffm.rs:236-244)
+            v[t] = (pres[t] && !diag[t]) ? __ldcg(reinterpret_cast<const float4 *>(p.ffm_w + hbase[t])) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         float2 lrw[NLR];
 #pragma unroll
