@@ -9,9 +9,12 @@ grep -E "AssertionError:|Mismatched|Max abs|^FAILED|passed|failed|^E  " gpurun_o
 (timeout 400 python bench.py --workload c3 --steps 5 --warmup 3 > gpurun_out/bench_c3_$TAG.json 2> gpurun_out/bench_c3_$TAG.err)
 (timeout 400 python bench.py --workload c5 --steps 5 --warmup 3 > gpurun_out/bench_c5_$TAG.json 2> gpurun_out/bench_c5_$TAG.err)
 (timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_c2_$TAG.json 2> gpurun_out/bench_ref_c2_$TAG.err)
+# launch lists of the bench command itself (all kernels, gpu time).  c2 / c3 keep the concurrency ramp (a dozen short launches at
+# the start), c5 skips its ramp (hundreds of tiny sub-batches) so that the list shows steady-state sub-batches
 for W in c2 c3 c5; do
   EX=2000000; [ $W = c3 ] && EX=400000; [ $W = c5 ] && EX=200000
-  (FWGPU_RAMP_DIV=4294967295 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${W}_$TAG.csv \
+  RD=32; [ $W = c5 ] && RD=4294967295
+  (FWGPU_RAMP_DIV=$RD timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${W}_$TAG.csv \
      python bench.py --workload $W --examples $EX --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_list_${W}_$TAG.log 2>&1)
 done
 python - <<PY
