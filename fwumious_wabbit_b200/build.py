@@ -9,6 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfwgpu.so")
 CLI_SRC = os.path.join(HERE, "cli", "fwgpu_main.cpp")
 CLI_OUT = os.path.join(HERE, "fwgpu")
+UMMA_TEST_SRC = os.path.join(os.path.dirname(HERE), "tools", "umma_gemm_test.cu")
+UMMA_TEST_OUT = os.path.join(HERE, "umma_gemm_test")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -35,11 +37,12 @@ def deps():
     out.append(os.path.join(os.path.dirname(HERE), "include", "fwgpu.h"))
     out.append(os.path.join(os.path.dirname(HERE), "include", "fwhost.h"))
     out.append(CLI_SRC)
+    out.append(UMMA_TEST_SRC)
     return out
 
 
 def up_to_date():
-    if not os.path.exists(OUT) or not os.path.exists(CLI_OUT):
+    if not os.path.exists(OUT) or not os.path.exists(CLI_OUT) or not os.path.exists(UMMA_TEST_OUT):
         return False
     t = os.path.getmtime(OUT)
     return all(os.path.getmtime(d) <= t for d in deps())
@@ -67,6 +70,14 @@ def build(force=False, verbose=False):
     if res2.returncode != 0:
         sys.stderr.write(res2.stdout + res2.stderr)
         raise RuntimeError("building the fwgpu command-line front end failed")
+    # stand-alone check of the tcgen05 GEMM tiles against a double-precision product (tests/test_gpu_head.py runs it on the GPU)
+    cmd3 = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-o", UMMA_TEST_OUT, UMMA_TEST_SRC]
+    res3 = subprocess.run(cmd3, capture_output=True, text=True)
+    with open(os.path.join(HERE, "build.log"), "a") as f:
+        f.write(" ".join(cmd3) + "\n" + res3.stdout + res3.stderr)
+    if res3.returncode != 0:
+        sys.stderr.write(res3.stdout + res3.stderr)
+        raise RuntimeError("building tools/umma_gemm_test.cu failed")
     if verbose:
         print(log)
     return OUT

@@ -3,6 +3,7 @@
 #include "../../include/fwgpu.h"
 #include "fwgpu_kernels.cuh"
 #include "fwgpu_head.cuh"
+#include "fwgpu_umma.cuh"
 #include "fwgpu_shard.hpp"
 
 #include <algorithm>
@@ -122,6 +123,8 @@ struct fwgpu_ctx {
     uint32_t x_len = 0, ldx = 0;  // head input: num_combos + F(F+1)/2 (regressor.rs:185-189), padded leading dimension
     uint32_t head_batch = 4096;   // examples per pass around the head's GEMMs = examples in flight
     int head_tile = 0;            // FWGPU_HEAD_TILE: 0 = choose per GEMM, 64 = always 64 x 64 tiles
+    uint32_t head_umma_rows = 512; // sub-batches of at least this many rows run the head's GEMMs on the tensor cores (tcgen05, 3xTF32); 0 = never.
+                                   // Smaller ones (the sequential / parity mode is 1 row) keep the fp32 FFMA tiles, whose arithmetic is the reference's
     double head_ramp_mul = 2.0;   // sub-batches grow as head_ramp_mul * sqrt(examples_seen) (0 = only the linear ramp)
     uint32_t head_rows_cap = 0;
     DevBuf hX, hdX, hH[FWGPU_MAX_NN_LAYERS], hdZ[FWGPU_MAX_NN_LAYERS], h_label, h_imp, h_outidx, h_dy;
@@ -393,6 +396,7 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         if (const char *t = getenv("FWGPU_HEAD_BATCH")) c->head_batch = std::max(1, atoi(t));
         if (const char *t = getenv("FWGPU_HEAD_RAMP_MUL")) c->head_ramp_mul = atof(t);
         if (const char *t = getenv("FWGPU_HEAD_TILE")) c->head_tile = atoi(t);
+        if (const char *t = getenv("FWGPU_HEAD_UMMA_ROWS")) c->head_umma_rows = (uint32_t)strtoul(t, nullptr, 10);
     }
 
     fwgpu_status st;
@@ -794,8 +798,29 @@ template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_g
 
 // tile choice: 128 x 128 (8 x 8 outputs per thread, FFMA-bound) when that still gives every SM a block, else 64 x 64;
 // the gradient-sum GEMM keeps two accumulators per output, so its largest tile is 128 x 64
+// the same GEMM on the tensor cores (fwgpu_umma.cuh): one 128 x 128 tile per block, the update GEMM split over K so that
+// the grid covers the machine
+template <bool A_T, bool B_T, int EPI> static void launch_head_umma(fwgpu_ctx *c, HeadGemmParams &p)
+{
+    auto kern = k_umma_gemm<A_T, B_T, EPI>;
+    static thread_local bool configured = false;
+    if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_BYTES); configured = true; }
+    const uint32_t n_cols = p.N + ((EPI == HEAD_EPI_SUMS && p.G1_bias) ? 1u : 0u); // the bias sums ride along as one more column
+    const uint32_t tiles = ((p.M + UMMA_BM - 1) / UMMA_BM) * ((n_cols + UMMA_BN - 1) / UMMA_BN);
+    uint32_t splits = 1;
+    if (EPI == HEAD_EPI_SUMS) {
+        splits = std::max<uint32_t>(1, std::min<uint32_t>(((uint32_t)c->num_sms + tiles - 1) / tiles, (p.K + 127) / 128));
+        p.k_split = (((p.K + splits - 1) / splits) + 15) / 16 * 16;
+        splits = (p.K + p.k_split - 1) / p.k_split;
+    }
+    dim3 grid((n_cols + UMMA_BN - 1) / UMMA_BN, (p.M + UMMA_BM - 1) / UMMA_BM, splits);
+    kern<<<grid, UMMA_THREADS, UMMA_SMEM_BYTES, c->stream>>>(p);
+    c->launches++;
+}
+
 template <bool A_T, bool B_T, int EPI> static void launch_head_gemm(fwgpu_ctx *c, HeadGemmParams &p)
 {
+    if (c->head_umma_rows && (EPI == HEAD_EPI_SUMS ? p.K : p.M) >= c->head_umma_rows) { launch_head_umma<A_T, B_T, EPI>(c, p); return; }
     const uint64_t big_tiles = (uint64_t)((p.M + 127) / 128) * ((p.N + 127) / 128);
     const bool small = c->head_tile == 64 || (c->head_tile == 0 && (p.M <= 64 || p.N <= 64 || (EPI != HEAD_EPI_SUMS && big_tiles < (uint64_t)c->num_sms * 3 / 4)));
     if (small) launch_head_gemm_tile<A_T, B_T, EPI, 64, 64>(c, p);

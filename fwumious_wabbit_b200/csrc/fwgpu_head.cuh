@@ -16,8 +16,9 @@
 //             acc_ji += G2_ji ; w_ji -= G1_ji * LUT[acc_ji]               (per-example squared gradients, as AdaGrad
 //                                                                          would have accumulated them one by one)
 // For B = 1 every sum has one term and the arithmetic is the reference's, rounding included.
-// All contractions are fp32 FFMA on purpose: predictions must stay within 1e-5 of the reference, which single-pass TF32
-// does not give; a 3xTF32 tcgen05 version is the planned replacement for these tiles.
+// The contractions in THIS file are fp32 FFMA: for small sub-batches (and the one-example parity mode) the arithmetic is
+// the reference's.  Sub-batches of >= 512 rows run the same four GEMM kinds on the tensor cores (fwgpu_umma.cuh,
+// tcgen05 with 3xTF32 split operands: single-pass TF32 does not keep predictions within 1e-5).
 #pragma once
 #include "fwgpu_kernels.cuh"
 

@@ -266,3 +266,14 @@ def test_head_regressor_file_roundtrip(tmp_path):
     assert np.array_equal(re4.learn_records(recs[:3000].reshape(-1), n_examples=3000, update=False), want)
     with pytest.raises(fw._lib.FwgpuError):
         re3.learn_records(recs[:10].reshape(-1), n_examples=10, update=True)  # regressor.rs:362-365
+
+
+def test_umma_gemm_tiles_against_double_precision():
+    """The tcgen05 3xTF32 GEMM tiles the head uses for sub-batches >= 512 rows (csrc/fwgpu_umma.cuh): all operand layouts and
+    epilogue kinds against a double-precision CPU product, ragged shapes included (tools/umma_gemm_test.cu prints one line per
+    case and the measured error; tolerance 2e-5 of the largest output, i.e. fp32-sum level)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(fw.__file__)), "umma_gemm_test")
+    assert os.path.exists(exe), "umma_gemm_test is built by fwumious_wabbit_b200/build.py"
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and "all cases ok" in res.stdout, res.stdout + res.stderr
