@@ -292,8 +292,10 @@ def run_ours(args):
                 "examples_per_launch": ex_per_launch, "avg_launch_ms": k_ms / k_n, "launches_timed": int(k_n),
                 "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1)), "translate_ms_per_launch": (t_ms / t_n) if t_n else None}
         if h_n:
-            # dense head (config 5): fp32 FFMA GEMMs, reported against the kernel's own flop count (forward + the two backward
-            # GEMMs + the squared-gradient sums of every layer), not against the HBM roofline of the gather/scatter kernel
+            # dense head (config 5): GEMMs on the tensor cores (tcgen05, 3xTF32 split operands, fp32 accumulation in TMEM) for
+            # sub-batches >= 512 rows, fp32 FFMA tiles below that; reported against the head's own fp32-equivalent flop count
+            # (forward + the two backward GEMMs + the squared-gradient sums of every layer), not against the HBM roofline of
+            # the gather/scatter kernel
             mi = w.mi
             x_len = mi.num_combos + len(mi.ffm_fields) * (len(mi.ffm_fields) + 1) // 2
             dims, n_in = [], x_len
@@ -302,7 +304,9 @@ def run_ours(args):
             dims.append((n_in + x_len, 1))
             fma = sum(a * b * (1 + 1 + 2) for a, b in dims)  # forward, input gradient, sum g and sum g^2
             roof["head"] = {"ms_per_pass": h_ms / h_n, "passes": int(h_n), "share_of_step": h_ms / ev0.elapsed_time(ev1),
-                            "fp32_tflops": 2 * fma * n * args.steps / (h_ms * 1e-3) * 1e-12, "fma_per_example": fma}
+                            "fp32_tflops": 2 * fma * n * args.steps / (h_ms * 1e-3) * 1e-12, "fma_per_example": fma,
+                            "engine": "fp32 FFMA tiles" if os.environ.get("FWGPU_HEAD_UMMA_ROWS") == "0" else
+                                      "tcgen05.mma kind::tf32, 3xTF32 split, TMEM accumulators (sub-batches >= 512 rows)"}
 
     # ---------------- cpu baseline (rank 0, N = 1 only) ----------------
     cpu = None
