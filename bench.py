@@ -291,6 +291,14 @@ def run_ours(args):
                 "kernel": "k_learn", "peak_source": peak_src, "algorithmic_bytes_per_example": alg_bytes,
                 "examples_per_launch": ex_per_launch, "avg_launch_ms": k_ms / k_n, "launches_timed": int(k_n),
                 "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1)), "translate_ms_per_launch": (t_ms / t_n) if t_n else None}
+        sp = os.path.join(ROOT, "profiles", f"skeleton_{w.name}.json")
+        if os.path.exists(sp) and not args.predict_only:
+            try:  # the kernel's memory operations alone (tools/skeleton_microbench.cu): what the memory system sustains for this access pattern
+                sk = json.load(open(sp))
+                ref_rate = sk["records_per_s_uniform_ids"] if args.uniform_ids else sk["records_per_s_bench_id_law"]
+                roof["memory_skeleton"] = {"records_per_s": ref_rate, "frac": (ex_per_launch / (k_ms / k_n * 1e-3)) / ref_rate, "source": sk["source"]}
+            except Exception:
+                pass
         if h_n:
             # dense head (config 5): GEMMs on the tensor cores (tcgen05, 3xTF32 split operands, fp32 accumulation in TMEM) for
             # sub-batches >= 512 rows, fp32 FFMA tiles below that; reported against the head's own fp32-equivalent flop count
