@@ -88,9 +88,14 @@ struct fwgpu_ctx {
     uint8_t *d_ns_is_f32 = nullptr;
     uint32_t *d_combo_off = nullptr, *d_combo_ns = nullptr, *d_field_off = nullptr, *d_field_ns = nullptr;
     float *d_combo_weight = nullptr;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_ready[2]{}, ev_free[2]{};
     bool ev_free_recorded[2] = {false, false};
+    // predictions leave through their own stream: a chunk's predictions are staged device-to-device on the compute stream
+    // (microseconds) and copied to the host while the next chunk is being learned
+    cudaEvent_t ev_pred_ready[2]{}, ev_pred_out[2]{};
+    bool ev_pred_out_recorded[2] = {false, false};
+    DevBuf pred_stage[2];
     // staging
     DevBuf rec[2], rec_off_dev[2], meta, lr_ent, ffm_ent, preds, csr, leftover;
     bool fast_ok = false;     // k_learn_fixed applies to this model (one namespace per field, k % 4 == 0, ...)
@@ -143,6 +148,7 @@ static fwgpu_status ensure(fwgpu_ctx *c, DevBuf &b, size_t bytes)
     if (b.p) {
         CUDA_TRY(c, cudaStreamSynchronize(c->stream));
         CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+        CUDA_TRY(c, cudaStreamSynchronize(c->d2h_stream));
         CUDA_TRY(c, cudaFree(b.p));
         b.p = nullptr;
         b.bytes = 0;
@@ -180,6 +186,7 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     if (c->shard) {
         c->shard->destroy_array(c->sh_lr); c->shard->destroy_array(c->sh_w); c->shard->destroy_array(c->sh_acc);
         delete c->shard;
@@ -188,7 +195,7 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     cudaFree(c->lr); cudaFree(c->ffm_w); cudaFree(c->ffm_acc); cudaFree(c->lut_dev);
     cudaFree(c->d_ns_is_f32); cudaFree(c->d_combo_off); cudaFree(c->d_combo_ns); cudaFree(c->d_field_off);
     cudaFree(c->d_field_ns); cudaFree(c->d_combo_weight);
-    for (DevBuf *b : {&c->rec[0], &c->rec[1], &c->rec_off_dev[0], &c->rec_off_dev[1], &c->meta, &c->lr_ent, &c->ffm_ent, &c->preds, &c->csr, &c->leftover})
+    for (DevBuf *b : {&c->rec[0], &c->rec[1], &c->rec_off_dev[0], &c->rec_off_dev[1], &c->meta, &c->lr_ent, &c->ffm_ent, &c->preds, &c->csr, &c->leftover, &c->pred_stage[0], &c->pred_stage[1]})
         if (b->p) cudaFree(b->p);
     cudaFree(c->head_w); cudaFree(c->head_acc); cudaFree(c->head_G1); cudaFree(c->head_G2);
     for (DevBuf *b : {&c->hX, &c->hdX, &c->h_label, &c->h_imp, &c->h_outidx, &c->h_dy}) if (b->p) cudaFree(b->p);
@@ -196,10 +203,12 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     cudaFree(c->err_flag);
     if (c->err_host) cudaFreeHost(c->err_host);
     for (int i = 0; i < 2; i++) { if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]); if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]); }
+    for (int i = 0; i < 2; i++) { if (c->ev_pred_ready[i]) cudaEventDestroy(c->ev_pred_ready[i]); if (c->ev_pred_out[i]) cudaEventDestroy(c->ev_pred_out[i]); }
     for (int kk = 0; kk < 3; kk++) for (auto &pr : c->prof[kk]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (auto e : c->ev_pool) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     delete c;
 }
 
@@ -276,9 +285,12 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
 
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_pred_ready[i], cudaEventDisableTiming));
+        CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_pred_out[i], cudaEventDisableTiming));
     }
     CUDA_TRY(c, cudaMalloc((void **)&c->err_flag, 4));
     CUDA_TRY(c, cudaMemset(c->err_flag, 0, 4));
@@ -520,6 +532,7 @@ extern "C" fwgpu_status fwgpu_sync(fwgpu_ctx *c)
     CUDA_TRY(c, cudaMemcpyAsync(c->err_host, c->err_flag, 4, cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->d2h_stream));
     return check_err_flag(c);
 }
 
@@ -1232,6 +1245,7 @@ extern "C" fwgpu_status fwgpu_learn_records(fwgpu_ctx *c, const uint32_t *record
     const uint32_t max_len = rec_off ? host_max_len(rec_off, 0, n_examples) : fixed_len;
     if (max_len < hdr && !rec_off) { c->set_error("records shorter than header + namespace slots"); return FWGPU_ERR_INVALID; }
     const uint32_t dyn_pairs = max_len > hdr ? (max_len - hdr + 1) / 2 : 0;
+    // ~1.3 M records per chunk on c2 (57 MB of records): measured best for the host-record pipeline; 16 MB chunks lose 9 % to launch tails
     const size_t chunk = chunk_examples(c, derive_lr_stride(c, dyn_pairs), c->F ? derive_ffm_stride(c, dyn_pairs) : 1);
     fwgpu_status st;
     uint64_t done = 0;
@@ -1252,10 +1266,23 @@ extern "C" fwgpu_status fwgpu_learn_records(fwgpu_ctx *c, const uint32_t *record
         if ((st = translate_and_learn(c, rv, cnt, nullptr, update, true))) return st;
         CUDA_TRY(c, cudaEventRecord(c->ev_free[bi], c->stream)); // translate (and learn) of this chunk are ordered before it
         c->ev_free_recorded[bi] = true;
-        if (preds_out) CUDA_TRY(c, cudaMemcpyAsync(preds_out + done, c->preds.p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->stream));
+        if (preds_out) {
+            if ((st = ensure(c, c->pred_stage[bi], (size_t)cnt * 4))) return st;
+            if (c->ev_pred_out_recorded[bi]) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_pred_out[bi], 0)); // staging buffer free again
+            CUDA_TRY(c, cudaMemcpyAsync(c->pred_stage[bi].p, c->preds.p, (size_t)cnt * 4, cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(c, cudaEventRecord(c->ev_pred_ready[bi], c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_pred_ready[bi], 0));
+            CUDA_TRY(c, cudaMemcpyAsync(preds_out + done, c->pred_stage[bi].p, (size_t)cnt * 4, cudaMemcpyDeviceToHost, c->d2h_stream));
+            CUDA_TRY(c, cudaEventRecord(c->ev_pred_out[bi], c->d2h_stream));
+            c->ev_pred_out_recorded[bi] = true;
+        }
         done += cnt;
         bi ^= 1;
     }
+    // the call is complete, in stream order, when its last predictions have left: whoever waits for (or records an event on) the
+    // compute stream afterwards also waits for them
+    if (preds_out)
+        for (int i = 0; i < 2; i++) if (c->ev_pred_out_recorded[i]) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_pred_out[i], 0));
     return FWGPU_OK;
 }
 
