@@ -14,6 +14,7 @@
 #include <mutex>
 #include <stdexcept>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 using namespace fwgpu;
@@ -89,6 +90,7 @@ struct fwgpu_ctx {
     uint32_t *d_combo_off = nullptr, *d_combo_ns = nullptr, *d_field_off = nullptr, *d_field_ns = nullptr;
     float *d_combo_weight = nullptr;
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    std::unordered_map<const void *, size_t> smem_optin_set; // kernels whose dynamic shared-memory limit was raised on THIS device (the attribute is per device)
     cudaEvent_t ev_ready[2]{}, ev_free[2]{};
     bool ev_free_recorded[2] = {false, false};
     // predictions leave through their own stream: a chunk's predictions are staged device-to-device on the compute stream
@@ -141,6 +143,16 @@ struct fwgpu_ctx {
 };
 
 struct ShardCfg { uint32_t rank, world; const char *rendezvous; uint32_t timeout_ms; };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device, per-function attribute: remember per ctx what was set
+template <class K> static cudaError_t ensure_dyn_smem(fwgpu_ctx *c, K kern, size_t smem)
+{
+    size_t &have = c->smem_optin_set[(const void *)kern];
+    if (smem <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) have = smem;
+    return e;
+}
 
 static fwgpu_status ensure(fwgpu_ctx *c, DevBuf &b, size_t bytes)
 {
@@ -585,14 +597,10 @@ extern "C" fwgpu_status fwgpu_kernel_time(fwgpu_ctx *c, int kind, double *total_
 template <int T, int VEC, int MINB> static cudaError_t launch_learn_tvm(fwgpu_ctx *c, const LearnParams &p, size_t smem, uint32_t *full_groups)
 {
     auto kern = k_learn<T, VEC, MINB>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = smem;
-    }
+    cudaError_t e = ensure_dyn_smem(c, kern, smem);
+    if (e != cudaSuccess) return e;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     constexpr int GROUPS = 256 / T;
@@ -727,12 +735,8 @@ template <int G, int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(f
     auto kern = k_learn_fixed<G, NCH, NLR, OPTK>;
     constexpr int NW = FIXED_WARPS, RPW = 32 / G;
     const size_t smem = (size_t)p.rec_smem_floats * 4 * NW * RPW; // the records' row transposes
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e0 != cudaSuccess) return e0;
-        configured = smem;
-    }
+    cudaError_t e0 = ensure_dyn_smem(c, kern, smem);
+    if (e0 != cudaSuccess) return e0;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NW * 32, smem);
     if (e != cudaSuccess) return e;
@@ -774,12 +778,8 @@ static cudaError_t launch_fixed(fwgpu_ctx *c, const FixedParams &p, uint32_t *fu
 template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *c, const FixedCtaParams &p, size_t smem, uint32_t *full_groups)
 {
     auto kern = k_learn_fixed_cta<UB, PHASE>;
-    static thread_local size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e0 = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e0 != cudaSuccess) return e0;
-        configured = smem;
-    }
+    cudaError_t e0 = ensure_dyn_smem(c, kern, smem);
+    if (e0 != cudaSuccess) return e0;
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (e != cudaSuccess) return e;
@@ -816,8 +816,7 @@ template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_g
 template <bool A_T, bool B_T, int EPI> static void launch_head_umma(fwgpu_ctx *c, HeadGemmParams &p)
 {
     auto kern = k_umma_gemm<A_T, B_T, EPI>;
-    static thread_local bool configured = false;
-    if (!configured) { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, UMMA_SMEM_BYTES); configured = true; }
+    if (ensure_dyn_smem(c, kern, UMMA_SMEM_BYTES) != cudaSuccess) { c->set_error("k_umma_gemm: cannot raise the dynamic shared-memory limit"); return; }
     const uint32_t n_cols = p.N + ((EPI == HEAD_EPI_SUMS && p.G1_bias) ? 1u : 0u); // the bias sums ride along as one more column
     const uint32_t tiles = ((p.M + UMMA_BM - 1) / UMMA_BM) * ((n_cols + UMMA_BN - 1) / UMMA_BN);
     uint32_t splits = 1;
