@@ -89,7 +89,8 @@ struct fwgpu_ctx {
     uint8_t *d_ns_is_f32 = nullptr;
     uint32_t *d_combo_off = nullptr, *d_combo_ns = nullptr, *d_field_off = nullptr, *d_field_ns = nullptr;
     float *d_combo_weight = nullptr;
-    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr, head_side_stream = nullptr;
+    cudaEvent_t ev_head_fork = nullptr, ev_head_join = nullptr;
     std::unordered_map<const void *, size_t> smem_optin_set; // kernels whose dynamic shared-memory limit was raised on THIS device (the attribute is per device)
     cudaEvent_t ev_ready[2]{}, ev_free[2]{};
     bool ev_free_recorded[2] = {false, false};
@@ -199,6 +200,7 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
+    if (c->head_side_stream) cudaStreamSynchronize(c->head_side_stream);
     if (c->shard) {
         c->shard->destroy_array(c->sh_lr); c->shard->destroy_array(c->sh_w); c->shard->destroy_array(c->sh_acc);
         delete c->shard;
@@ -221,6 +223,9 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
+    if (c->head_side_stream) cudaStreamDestroy(c->head_side_stream);
+    if (c->ev_head_fork) cudaEventDestroy(c->ev_head_fork);
+    if (c->ev_head_join) cudaEventDestroy(c->ev_head_join);
     delete c;
 }
 
@@ -298,6 +303,9 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    if (!getenv("FWGPU_HEAD_NO_FORK")) CUDA_TRY(c, cudaStreamCreateWithFlags(&c->head_side_stream, cudaStreamNonBlocking));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_head_fork, cudaEventDisableTiming));
+    CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_head_join, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
         CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_ready[i], cudaEventDisableTiming));
         CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_free[i], cudaEventDisableTiming));
@@ -794,7 +802,7 @@ template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *
 }
 
 // ---- dense head (fwgpu_head.cuh) ----------------------------------------------------------------
-template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_gemm_tile(fwgpu_ctx *c, HeadGemmParams &p)
+template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_gemm_tile(fwgpu_ctx *c, HeadGemmParams &p, cudaStream_t stream)
 {
     uint32_t splits = 1;
     if (EPI == HEAD_EPI_SUMS) {
@@ -805,7 +813,7 @@ template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_g
         splits = (p.K + p.k_split - 1) / p.k_split;
     }
     dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, splits);
-    k_head_gemm<A_T, B_T, EPI, BM, BN><<<grid, 256, 0, c->stream>>>(p);
+    k_head_gemm<A_T, B_T, EPI, BM, BN><<<grid, 256, 0, stream>>>(p);
     c->launches++;
 }
 
@@ -813,7 +821,7 @@ template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_g
 // the gradient-sum GEMM keeps two accumulators per output, so its largest tile is 128 x 64
 // the same GEMM on the tensor cores (fwgpu_umma.cuh): one 128 x 128 tile per block, the update GEMM split over K so that
 // the grid covers the machine
-template <bool A_T, bool B_T, int EPI> static void launch_head_umma(fwgpu_ctx *c, HeadGemmParams &p)
+template <bool A_T, bool B_T, int EPI> static void launch_head_umma(fwgpu_ctx *c, HeadGemmParams &p, cudaStream_t stream)
 {
     auto kern = k_umma_gemm<A_T, B_T, EPI>;
     if (ensure_dyn_smem(c, kern, UMMA_SMEM_BYTES) != cudaSuccess) { c->set_error("k_umma_gemm: cannot raise the dynamic shared-memory limit"); return; }
@@ -826,18 +834,19 @@ template <bool A_T, bool B_T, int EPI> static void launch_head_umma(fwgpu_ctx *c
         splits = (p.K + p.k_split - 1) / p.k_split;
     }
     dim3 grid((n_cols + UMMA_BN - 1) / UMMA_BN, (p.M + UMMA_BM - 1) / UMMA_BM, splits);
-    kern<<<grid, UMMA_THREADS, UMMA_SMEM_BYTES, c->stream>>>(p);
+    kern<<<grid, UMMA_THREADS, UMMA_SMEM_BYTES, stream>>>(p);
     c->launches++;
 }
 
-template <bool A_T, bool B_T, int EPI> static void launch_head_gemm(fwgpu_ctx *c, HeadGemmParams &p)
+template <bool A_T, bool B_T, int EPI> static void launch_head_gemm(fwgpu_ctx *c, HeadGemmParams &p, cudaStream_t stream = nullptr)
 {
-    if (c->head_umma_rows && (EPI == HEAD_EPI_SUMS ? p.K : p.M) >= c->head_umma_rows) { launch_head_umma<A_T, B_T, EPI>(c, p); return; }
+    if (!stream) stream = c->stream;
+    if (c->head_umma_rows && (EPI == HEAD_EPI_SUMS ? p.K : p.M) >= c->head_umma_rows) { launch_head_umma<A_T, B_T, EPI>(c, p, stream); return; }
     const uint64_t big_tiles = (uint64_t)((p.M + 127) / 128) * ((p.N + 127) / 128);
     const bool small = c->head_tile == 64 || (c->head_tile == 0 && (p.M <= 64 || p.N <= 64 || (EPI != HEAD_EPI_SUMS && big_tiles < (uint64_t)c->num_sms * 3 / 4)));
-    if (small) launch_head_gemm_tile<A_T, B_T, EPI, 64, 64>(c, p);
-    else if constexpr (EPI == HEAD_EPI_SUMS) launch_head_gemm_tile<A_T, B_T, EPI, 128, 64>(c, p);
-    else launch_head_gemm_tile<A_T, B_T, EPI, 128, 128>(c, p);
+    if (small) launch_head_gemm_tile<A_T, B_T, EPI, 64, 64>(c, p, stream);
+    else if constexpr (EPI == HEAD_EPI_SUMS) launch_head_gemm_tile<A_T, B_T, EPI, 128, 64>(c, p, stream);
+    else launch_head_gemm_tile<A_T, B_T, EPI, 128, 128>(c, p, stream);
 }
 
 // forward (+ backward and optimizer step when update) of the head over `rows` examples whose inputs sit in hX
@@ -880,10 +889,18 @@ static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
         k_head_final_sums<<<dim3(col_blocks, (rows + f.rows_per_block - 1) / f.rows_per_block), 256, 0, c->stream>>>(f);
         c->launches++;
     }
+    // The update GEMM of a layer (gradient sums, reads dZ_l and the layer's input) and the GEMM that carries the error to the
+    // layer below (reads dZ_l and W_l) are independent and each fills less than half of the machine at these sizes: the
+    // update GEMMs go to a side stream, forked after dZ_l exists and joined before the optimizer step.
+    const bool fork = c->head_side_stream != nullptr && rows >= c->head_umma_rows && c->head_umma_rows;
     for (size_t li = nl - 1; li-- > 0;) { // hidden layers, last to first
         const auto &L = c->head[li];
         const float *dZ = (const float *)c->hdZ[li].p;
         const float *W = c->head_w + L.off;
+        if (fork) { // dZ_l is complete in main-stream order here; the error GEMM enqueued below is not waited for
+            CUDA_TRY(c, cudaEventRecord(c->ev_head_fork, c->stream));
+            CUDA_TRY(c, cudaStreamWaitEvent(c->head_side_stream, c->ev_head_fork, 0));
+        }
         // errors for the layer below from the PRE-update weights (block_neural.rs:283-284); the step is applied at the end
         HeadGemmParams g{};
         g.A = dZ; g.lda = L.n_out; g.B = W; g.ldb = L.n_in; g.M = rows; g.N = L.n_in; g.K = L.n_out;
@@ -900,7 +917,11 @@ static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
         u.M = L.n_out; u.N = L.n_in; u.K = rows; u.ldc = L.n_in;
         u.G1 = c->head_G1 + L.off; u.G2 = c->head_G2 + L.off;
         u.G1_bias = c->head_G1 + L.off + (size_t)L.n_in * L.n_out; u.G2_bias = c->head_G2 + L.off + (size_t)L.n_in * L.n_out;
-        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, u);
+        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, u, fork ? c->head_side_stream : c->stream);
+    }
+    if (fork) {
+        CUDA_TRY(c, cudaEventRecord(c->ev_head_join, c->head_side_stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_head_join, 0));
     }
     k_head_apply<<<(uint32_t)std::min<size_t>((c->head_params + 255) / 256, (size_t)c->num_sms * 8), 256, 0, c->stream>>>(
         c->head_w, c->head_acc, c->head_G1, c->head_G2, c->head_params, c->optimizer, c->lut_dev + 2 * FWGPU_LUT_SIZE, c->d.nn_learning_rate, -c->d.nn_power_t);
