@@ -878,6 +878,15 @@ static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
         c->launches++;
     }
     if (!update) { CUDA_TRY(c, cudaGetLastError()); return FWGPU_OK; }
+    // The gradient-sum kernels (this one and the update GEMM of every layer: they read dZ_l / dy and the layer's input) are
+    // independent of the GEMMs that carry the error to the layer below (dZ_l and W_l), and each fills less than half of the
+    // machine at these sizes: they go to a side stream, forked once their inputs exist and joined before the optimizer step.
+    const bool fork = c->head_side_stream != nullptr && c->head_umma_rows && rows >= c->head_umma_rows;
+    cudaStream_t sums_stream = fork ? c->head_side_stream : c->stream;
+    if (fork) { // dy and the last layer's dZ are complete in main-stream order here
+        CUDA_TRY(c, cudaEventRecord(c->ev_head_fork, c->stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(c->head_side_stream, c->ev_head_fork, 0));
+    }
     // final neuron: gradient sums over its inputs [h, x] and its bias (block_neural.rs:266-305 with one neuron)
     {
         HeadFinalSumsParams f{};
@@ -886,18 +895,14 @@ static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
         const uint32_t col_blocks = (Lf.n_in + 1 + 255) / 256;
         const uint32_t row_blocks = std::max<uint32_t>(1, std::min<uint32_t>((rows + 127) / 128, (2 * (uint32_t)c->num_sms + col_blocks - 1) / col_blocks));
         f.rows_per_block = (rows + row_blocks - 1) / row_blocks;
-        k_head_final_sums<<<dim3(col_blocks, (rows + f.rows_per_block - 1) / f.rows_per_block), 256, 0, c->stream>>>(f);
+        k_head_final_sums<<<dim3(col_blocks, (rows + f.rows_per_block - 1) / f.rows_per_block), 256, 0, sums_stream>>>(f);
         c->launches++;
     }
-    // The update GEMM of a layer (gradient sums, reads dZ_l and the layer's input) and the GEMM that carries the error to the
-    // layer below (reads dZ_l and W_l) are independent and each fills less than half of the machine at these sizes: the
-    // update GEMMs go to a side stream, forked after dZ_l exists and joined before the optimizer step.
-    const bool fork = c->head_side_stream != nullptr && rows >= c->head_umma_rows && c->head_umma_rows;
     for (size_t li = nl - 1; li-- > 0;) { // hidden layers, last to first
         const auto &L = c->head[li];
         const float *dZ = (const float *)c->hdZ[li].p;
         const float *W = c->head_w + L.off;
-        if (fork) { // dZ_l is complete in main-stream order here; the error GEMM enqueued below is not waited for
+        if (fork && li + 2 < nl) { // dZ_l (written by the previous iteration's error GEMM) is complete in main-stream order here
             CUDA_TRY(c, cudaEventRecord(c->ev_head_fork, c->stream));
             CUDA_TRY(c, cudaStreamWaitEvent(c->head_side_stream, c->ev_head_fork, 0));
         }
@@ -917,7 +922,7 @@ static fwgpu_status head_pass(fwgpu_ctx *c, uint32_t rows, int update)
         u.M = L.n_out; u.N = L.n_in; u.K = rows; u.ldc = L.n_in;
         u.G1 = c->head_G1 + L.off; u.G2 = c->head_G2 + L.off;
         u.G1_bias = c->head_G1 + L.off + (size_t)L.n_in * L.n_out; u.G2_bias = c->head_G2 + L.off + (size_t)L.n_in * L.n_out;
-        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, u, fork ? c->head_side_stream : c->stream);
+        launch_head_gemm<true, true, HEAD_EPI_SUMS>(c, u, sums_stream);
     }
     if (fork) {
         CUDA_TRY(c, cudaEventRecord(c->ev_head_join, c->head_side_stream));
