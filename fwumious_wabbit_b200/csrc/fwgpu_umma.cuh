@@ -5,7 +5,7 @@
 // The head's contractions (block_neural.rs:196-341, restated for a sub-batch in fwgpu_head.cuh) must keep predictions
 // within 1e-5 of the reference, which a single TF32 pass (10-bit mantissa) does not.  Every operand element v is
 // therefore split while it is staged into shared memory,
-//   hi = tf32(v)  (cvt.rna),   lo = tf32(v - hi),
+//   hi = v rounded to TF32 (10 mantissa bits),   lo = v - hi  (exact; the tensor core reads its upper 19 bits),
 // and each k-step issues three MMAs into the same accumulator:  hi*hi + lo*hi + hi*lo  (the lo*lo term is < 2^-22 |ab|).
 //
 // Structure of one CTA (1024 threads, one 128 x 128 output tile, BK = 32; BK = 16 for the update GEMM, which stages the
@@ -35,7 +35,10 @@ constexpr int UMMA_SMEM_BYTES = UMMA_STAGES * UMMA_STAGE_BYTES + 128; // stages 
 constexpr int UMMA_PREFETCH = 3;                                // k-blocks of operand chunks in flight per thread
 
 __device__ __forceinline__ uint32_t umma_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ float umma_tf32(float v) { uint32_t r; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v)); return __uint_as_float(r); }
+// hi part of the split: v rounded to TF32's 10 mantissa bits, with integer arithmetic.  cvt.rna.tf32.f32 does the same but
+// issues at the conversion unit's quarter rate: two of them per element made the producers, not the tensor core, the bound
+// of the k-loop (0.97 us of staging per k-block against 0.51 us of MMA work, tools/umma_gemm_test.cu experiment builds).
+__device__ __forceinline__ float umma_tf32(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xffffe000u); }
 
 // Operand tiles are K-major with one row = BK floats = 128 bytes (BK = 32, SWIZZLE_128B) or 64 bytes (BK = 16, SWIZZLE_64B):
 // swizzle atoms of 8 rows, the 16-byte chunk c of row r stored at chunk position c ^ (r & 7)  [128B]  /  c ^ ((r >> 1) & 3)  [64B]
@@ -132,7 +135,8 @@ __device__ __forceinline__ void umma_store_chunk(uint32_t idx, float4 v, float4 
     if (SQUARE) { v.x = __fmul_rn(v.x, v.x); v.y = __fmul_rn(v.y, v.y); v.z = __fmul_rn(v.z, v.z); v.w = __fmul_rn(v.w, v.w); }
     float4 h, l;
     h.x = umma_tf32(v.x); h.y = umma_tf32(v.y); h.z = umma_tf32(v.z); h.w = umma_tf32(v.w);
-    l.x = umma_tf32(v.x - h.x); l.y = umma_tf32(v.y - h.y); l.z = umma_tf32(v.z - h.z); l.w = umma_tf32(v.w - h.w);
+    // lo = v - hi is exact in fp32 and |lo| <= 2^-11 |v|; the tensor core reads its upper 19 bits, i.e. drops < 2^-21 |v|
+    l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
     const uint32_t chunk = umma_chunk_index<BK>(rg * 8 + r8, kc);
     hi[chunk] = h; lo[chunk] = l;
 }
@@ -221,6 +225,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_umma_gemm(const HeadGemmPar
                 const uint32_t s = it % UMMA_STAGES;
                 if (it >= UMMA_STAGES) umma_bar_wait(empty + s, ((it / UMMA_STAGES) - 1) & 1); // the MMAs that read this buffer are done
                 unsigned char *st = umma_smem + s * UMMA_STAGE_BYTES;
+#ifndef UMMA_EXPERIMENT_NO_STORE
 #pragma unroll
                 for (uint32_t c = 0; c < CPT; c++) {
                     const uint32_t idx = threadIdx.x + c * PRODUCERS;
@@ -231,6 +236,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_umma_gemm(const HeadGemmPar
                         umma_store_chunk<BK, B_T, true>(idx, cb[j][c], reinterpret_cast<float4 *>(st + 6 * TILE), reinterpret_cast<float4 *>(st + 7 * TILE));
                     }
                 }
+#endif
                 const uint32_t kn = k0 + UMMA_PREFETCH * BK;
                 if (kn < k_end) {
 #pragma unroll
@@ -253,8 +259,10 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_umma_gemm(const HeadGemmPar
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
                 const uint32_t sb = umma_smem_u32(umma_smem + s * UMMA_STAGE_BYTES);
+#ifndef UMMA_EXPERIMENT_NO_MMA // (tools/umma_gemm_test.cu: which side bounds the k-loop)
                 umma_issue_block<BK>(tmem, sb, sb + TILE, sb + 2 * TILE, sb + 3 * TILE, it == 0);
                 if (SUMS) umma_issue_block<BK>(tmem + 128, sb + 4 * TILE, sb + 5 * TILE, sb + 6 * TILE, sb + 7 * TILE, it == 0);
+#endif
                 umma_commit(empty + s);
                 if (it + 1 == n_kb) umma_commit(done); // MMAs complete in order: this commit covers all of them
             }
