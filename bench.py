@@ -288,7 +288,10 @@ def run_ours(args):
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "kernel": "k_learn", "peak_source": peak_src, "algorithmic_bytes_per_example": alg_bytes,
+                "kernel": {"c2": "k_learn_fixed<16,4,1,OPT_LUT> (16 lanes per record, two records per warp)",
+                           "c3": "k_learn_fixed_cta<2,0> (block per record)", "c4": "k_learn_fixed_cta<2,0> (block per record)",
+                           "c5": "k_learn_fixed_cta<2,1> + <2,2> (block per record, forward / update phases around the head)"}.get(w.name, "k_learn"),
+                "peak_source": peak_src, "algorithmic_bytes_per_example": alg_bytes,
                 "examples_per_launch": ex_per_launch, "avg_launch_ms": k_ms / k_n, "launches_timed": int(k_n),
                 "kernel_share_of_step": k_ms / (ev0.elapsed_time(ev1)), "translate_ms_per_launch": (t_ms / t_n) if t_n else None}
         sp = os.path.join(ROOT, "profiles", f"skeleton_{w.name}.json")
