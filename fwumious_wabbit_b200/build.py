@@ -63,7 +63,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
     # the command-line front end (fwgpu): plain C++ against the two C ABIs, finds the library next to itself
-    cmd2 = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI_OUT, CLI_SRC, "-L" + HERE, "-lfwgpu", "-Wl,-rpath,$ORIGIN"]
+    cmd2 = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI_OUT, CLI_SRC, "-L" + HERE, "-lfwgpu", "-lz", "-Wl,-rpath,$ORIGIN"]
     res2 = subprocess.run(cmd2, capture_output=True, text=True)
     with open(os.path.join(HERE, "build.log"), "a") as f:
         f.write(" ".join(cmd2) + "\n" + res2.stdout + res2.stderr)

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <zlib.h>
 
 namespace {
 [[noreturn]] void die(const std::string &m) { fprintf(stderr, "fwgpu: %s\n", m.c_str()); exit(1); }
@@ -25,6 +26,23 @@ std::string read_file(const std::string &p) {
     return s;
 }
 bool exists(const std::string &p) { FILE *f = fopen(p.c_str(), "rb"); if (f) fclose(f); return f != nullptr; }
+// text input by file extension, like buffer_handler.rs:8-36: .vw plain, .gz gzip (all members, MultiGzDecoder), .zst zstd
+std::string read_input(const std::string &p) {
+    const size_t dot = p.rfind('.');
+    const std::string ext = dot == std::string::npos ? "" : p.substr(dot + 1);
+    if (ext == "vw") return read_file(p);
+    if (ext == "gz") {
+        gzFile g = gzopen(p.c_str(), "rb");
+        if (!g) die("Could not open the input file.");
+        std::string s; std::vector<char> buf(1 << 20); int n;
+        while ((n = gzread(g, buf.data(), (unsigned)buf.size())) > 0) s.append(buf.data(), (size_t)n);
+        if (n < 0) { int e = 0; const char *m = gzerror(g, &e); die(std::string("gzip input: ") + (m ? m : "read error")); }
+        gzclose(g);
+        return s;
+    }
+    if (ext == "zst") die("zstd input is not supported by this build (no libzstd in the image); use .vw or .gz");
+    die("Please specify a valid input format (.vw, .zst, .gz)"); // buffer_handler.rs:33-35
+}
 struct Flags {
     std::vector<std::pair<std::string, std::string>> kv;
     std::vector<std::string> raw;
@@ -154,7 +172,7 @@ int main(int argc, char **argv)
         if (n_examples < 0 && !quiet) fprintf(stderr, "fwgpu: couldn't use the existing cache file: %s\n", err); // cache.rs:99-105: fall back to text
     }
     if (n_examples < 0) {
-        std::string text = read_file(data);
+        std::string text = read_input(data);
         void *parser = fwhost_parser_new(vwmap_json.c_str(), err, sizeof(err));
         if (!parser) die(err);
         uint64_t lines = std::count(text.begin(), text.end(), '\n') + 1;

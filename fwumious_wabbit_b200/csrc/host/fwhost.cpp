@@ -3,6 +3,7 @@
 // (model_instance.rs:296-495).  CPU code, C ABI outside; nothing here calls oracle/.
 #include "../../../include/fwhost.h"
 #include "model.hpp"
+#include "lz4frame.hpp"
 #include "murmur3.hpp"
 
 #include <atomic>
@@ -423,7 +424,14 @@ int64_t fwhost_parser_parse_text(void *parser, const char *text, size_t len, uin
     return (int64_t)n;
 }
 
-// ---- .fwcache (cache.rs:12-26, 133-161, 187-232); uncompressed variant only (LZ4 applies to *.gz inputs, cache.rs:71)
+// ---- .fwcache (cache.rs:12-26, 133-161, 187-232).  The cache of an input whose name ends in "gz" is the same byte stream
+// inside an LZ4 frame (cache.rs:71, 89-125); lz4frame.hpp is the codec.
+static bool cache_is_compressed(const std::string &path)
+{
+    const std::string suffix = "gz.fwcache"; // final_filename = input_filename + ".fwcache", gz = input_filename.ends_with("gz")
+    return path.size() >= suffix.size() && path.compare(path.size() - suffix.size(), suffix.size(), suffix) == 0;
+}
+
 int fwhost_cache_write(const char *path, const char *vwmap_json, const uint32_t *records, uint64_t n_words, char *err, size_t errcap)
 {
     try {
@@ -432,8 +440,18 @@ int fwhost_cache_write(const char *path, const char *vwmap_json, const uint32_t 
         FILE *f = fopen(tmp.c_str(), "wb");
         if (!f) throw std::runtime_error("cannot create " + tmp);
         uint64_t len = blob.size();
-        bool ok = fwrite("FWCA", 1, 4, f) == 4 && fwrite(&CACHE_VERSION, 4, 1, f) == 1 && fwrite(&len, 8, 1, f) == 1 && fwrite(blob.data(), 1, len, f) == len &&
-                  (n_words == 0 || fwrite(records, 4, n_words, f) == n_words);
+        bool ok;
+        if (cache_is_compressed(path)) {
+            std::vector<uint8_t> image;
+            image.reserve(16 + len + n_words * 4);
+            auto put = [&](const void *p_, size_t n_) { image.insert(image.end(), (const uint8_t *)p_, (const uint8_t *)p_ + n_); };
+            put("FWCA", 4); put(&CACHE_VERSION, 4); put(&len, 8); put(blob.data(), len); put(records, n_words * 4);
+            const std::vector<uint8_t> z = lz4::encode_frame(image.data(), image.size());
+            ok = fwrite(z.data(), 1, z.size(), f) == z.size();
+        } else {
+            ok = fwrite("FWCA", 1, 4, f) == 4 && fwrite(&CACHE_VERSION, 4, 1, f) == 1 && fwrite(&len, 8, 1, f) == 1 && fwrite(blob.data(), 1, len, f) == len &&
+                 (n_words == 0 || fwrite(records, 4, n_words, f) == n_words);
+        }
         ok = (fclose(f) == 0) && ok;
         if (!ok) throw std::runtime_error("write failed");
         if (rename(tmp.c_str(), path)) throw std::runtime_error("rename failed");
@@ -448,23 +466,32 @@ int64_t fwhost_cache_read(const char *path, const char *expect_vwmap_json, uint3
     try {
         f = fopen(path, "rb");
         if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+        std::vector<uint8_t> image;
+        {
+            fseek(f, 0, SEEK_END);
+            const long sz = ftell(f);
+            fseek(f, 0, SEEK_SET);
+            image.resize(sz > 0 ? (size_t)sz : 0);
+            if (!image.empty() && !read_exact(f, image.data(), image.size())) throw std::runtime_error("short read");
+            fclose(f);
+            f = nullptr;
+        }
+        if (cache_is_compressed(path)) image = lz4::decode_frames(image.data(), image.size());
+        size_t pos = 0;
+        auto take = [&](void *dst, size_t n_) { if (image.size() - pos < n_) return false; memcpy(dst, image.data() + pos, n_); pos += n_; return true; };
         char magic[4];
         uint32_t version = 0;
-        if (!read_exact(f, magic, 4) || memcmp(magic, "FWCA", 4)) throw std::runtime_error("Cache header does not begin with magic bytes FWFW"); // sic, cache.rs:167
-        if (!read_exact(f, &version, 4) || version != CACHE_VERSION) throw std::runtime_error("Cache file version of this binary: 11, version of the cache file: " + std::to_string(version));
-        std::string blob;
-        if (!read_blob(f, blob)) throw std::runtime_error("truncated cache header");
+        if (!take(magic, 4) || memcmp(magic, "FWCA", 4)) throw std::runtime_error("Cache header does not begin with magic bytes FWFW"); // sic, cache.rs:167
+        if (!take(&version, 4) || version != CACHE_VERSION) throw std::runtime_error("Cache file version of this binary: 11, version of the cache file: " + std::to_string(version));
+        uint64_t blen = 0;
+        if (!take(&blen, 8) || blen > image.size() - pos) throw std::runtime_error("truncated cache header");
+        std::string blob((const char *)image.data() + pos, blen);
+        pos += blen;
         VwMap in_file = vwmap_from_json(json_parse(blob));
         if (expect_vwmap_json && !(in_file == vwmap_from_json(json_parse(expect_vwmap_json)))) throw std::runtime_error("vw_namespace_map.csv and the one from cache file differ");
-        long start = ftell(f);
-        fseek(f, 0, SEEK_END);
-        long end = ftell(f);
-        fseek(f, start, SEEK_SET);
-        uint64_t n_words = (uint64_t)(end - start) / 4;
+        uint64_t n_words = (uint64_t)(image.size() - pos) / 4;
         uint32_t *recs = (uint32_t *)malloc(std::max<uint64_t>(n_words, 1) * 4);
-        if (n_words && !read_exact(f, recs, n_words * 4)) { free(recs); throw std::runtime_error("short read"); }
-        fclose(f);
-        f = nullptr;
+        if (n_words) memcpy(recs, image.data() + pos, n_words * 4);
         std::vector<uint32_t> offs;
         uint64_t w = 0;
         while (w < n_words) {

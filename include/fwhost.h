@@ -62,7 +62,8 @@ int fwhost_parser_parse_line(void *parser, const char *line, size_t len, uint32_
 int64_t fwhost_parser_parse_text(void *parser, const char *text, size_t len, uint32_t *out, uint64_t cap_words, uint32_t *rec_off,
                                  uint64_t cap_examples, int n_threads, uint64_t *n_words_out, char *err, size_t errcap);
 
-/* .fwcache (cache.rs:12-26): "FWCA", u32 11, u64 + JSON vwmap, records.  Uncompressed form only. */
+/* .fwcache (cache.rs:12-26): "FWCA", u32 11, u64 + JSON vwmap, records.  A path that ends in "gz.fwcache" (the cache of a
+ * *.gz input, cache.rs:68-71) holds the same bytes inside an LZ4 frame. */
 int fwhost_cache_write(const char *path, const char *vwmap_json, const uint32_t *records, uint64_t n_words, char *err, size_t errcap);
 int64_t fwhost_cache_read(const char *path, const char *expect_vwmap_json /* or NULL */, uint32_t **records_out, uint64_t *n_words_out,
                           uint32_t **rec_off_out, char **vwmap_json_out /* or NULL */, char *err, size_t errcap);

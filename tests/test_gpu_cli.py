@@ -113,3 +113,32 @@ def test_cli_deep_head(tmp_path):
     assert len(np.unique(p)) > 100 and balanced_accuracy(p, y) > 0.9
     r = subprocess.run([FW] + ns + rest + ["--data", tr, "--nn", "0:dropout:0.5"], capture_output=True, text=True)
     assert r.returncode != 0 and "not implemented" in r.stderr
+
+
+def test_cli_gz_input_and_lz4_cache(tmp_path):
+    """`*.gz` text input (all gzip members, buffer_handler.rs:19-23) and its LZ4-framed cache (cache.rs:68-71, 89-125): the
+    same model trained in sequential mode from train.vw and from train.vw.gz predicts identically, the second pass reads the
+    compressed cache, and an unknown extension is refused like the reference does (buffer_handler.rs:33-35)."""
+    import gzip
+    import shutil
+
+    d = str(tmp_path)
+    generate(d, n_train=4000, n_eval=10)
+    lines = open(f"{d}/train.vw", "rb").read().splitlines(keepends=True)
+    with open(f"{d}/packed.vw.gz", "wb") as f:   # two gzip members
+        f.write(gzip.compress(b"".join(lines[:1500])))
+        f.write(gzip.compress(b"".join(lines[1500:])))
+    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 -b 18 --ffm_bit_precision 18 --adaptive --sgd --sequential -c".split()
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_plain.txt"])
+    run(ns + rest + ["--data", f"{d}/packed.vw.gz", "-p", f"{d}/p_gz.txt"])
+    assert open(f"{d}/p_plain.txt").read() == open(f"{d}/p_gz.txt").read()
+    z = open(f"{d}/packed.vw.gz.fwcache", "rb").read()
+    assert z[:4] == bytes([0x04, 0x22, 0x4D, 0x18]) and len(z) < os.path.getsize(f"{d}/train.vw.fwcache")
+    os.remove(f"{d}/packed.vw.gz")               # the cache alone is enough now (cache.rs:98: "ignoring text input")
+    open(f"{d}/packed.vw.gz", "wb").close()
+    run(ns + rest + ["--data", f"{d}/packed.vw.gz", "-p", f"{d}/p_cache.txt"])
+    assert open(f"{d}/p_cache.txt").read() == open(f"{d}/p_plain.txt").read()
+    shutil.copy(f"{d}/train.vw", f"{d}/train.txt")
+    r = subprocess.run([FW] + ns + ["--data", f"{d}/train.txt"], capture_output=True, text=True)
+    assert r.returncode != 0 and "Please specify a valid input format (.vw, .zst, .gz)" in r.stderr

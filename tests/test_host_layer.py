@@ -112,6 +112,46 @@ def test_cache_roundtrip_and_header(tmp_path):  # cache.rs:12-26, 133-182
         host.cache_read(path, vw)
 
 
+def test_cache_of_gz_input_is_an_lz4_frame(tmp_path):  # cache.rs:68-71, 89-125
+    """The cache of a `*.gz` input is the same byte stream inside an LZ4 frame.  Our codec (csrc/host/lz4frame.hpp, written from
+    the format description) is checked against an independent implementation of the frame format (Arrow's): Arrow reads what
+    we write, we read what Arrow writes, and damaged frames are rejected."""
+    pa = pytest.importorskip("pyarrow")
+    w = synth.workload("c2")
+    vw = host.VwNamespaceMap.new("".join(f"{c},feature{c}\n" for c in w.ns_names))
+    recs = w.records(30000).reshape(-1)
+    plain, packed = str(tmp_path / "train.vw.fwcache"), str(tmp_path / "train.vw.gz.fwcache")
+    host.cache_write(plain, vw, recs)
+    host.cache_write(packed, vw, recs)
+    image, z = open(plain, "rb").read(), open(packed, "rb").read()
+    assert z[:4] == bytes([0x04, 0x22, 0x4D, 0x18]) and len(z) < 0.8 * len(image)   # a frame, and it does compress
+    assert pa.Codec("lz4").decompress(z, decompressed_size=len(image)).to_pybytes() == image
+    r, off, js = host.cache_read(packed, vw)
+    assert np.array_equal(r, recs) and off.tolist() == list(range(0, 330001, 11)) and json.loads(js) == vw.source
+    # a frame from the other implementation (its own block size / flags / checksums)
+    foreign = str(tmp_path / "other.vw.gz.fwcache")
+    open(foreign, "wb").write(pa.Codec("lz4").compress(image).to_pybytes())
+    r2, off2, _ = host.cache_read(foreign, vw)
+    assert np.array_equal(r2, recs) and np.array_equal(off2, off)
+    # edge cases: empty cache body, incompressible payload, damaged frames
+    empty = str(tmp_path / "empty.vw.gz.fwcache")
+    host.cache_write(empty, vw, np.zeros(0, np.uint32))
+    assert host.cache_read(empty, vw)[0].size == 0
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 1 << 32, size=22 * 1000, dtype=np.uint64).astype(np.uint32)
+    noise[::22] = 22  # valid record lengths, random payload
+    hard = str(tmp_path / "noise.vw.gz.fwcache")
+    host.cache_write(hard, vw, noise)
+    assert np.array_equal(host.cache_read(hard, vw)[0], noise)
+    bad = bytearray(z); bad[5] ^= 0x10   # descriptor byte: header checksum no longer matches
+    open(packed, "wb").write(bytes(bad))
+    with pytest.raises(IOError, match="lz4"):
+        host.cache_read(packed, vw)
+    open(packed, "wb").write(z[: len(z) // 2])
+    with pytest.raises(IOError, match="lz4"):
+        host.cache_read(packed, vw)
+
+
 def test_batch_parser_equals_line_parser_and_oracle():
     """Multi-threaded whole-buffer parse == line-by-line parse == the oracle's independent parser, on synthetic lines and,
     when the reference tree is present, on its real-shape example file (58 namespaces, weights, multi-valued namespaces)."""
