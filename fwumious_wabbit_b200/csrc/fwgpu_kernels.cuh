@@ -583,13 +583,13 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
 
 
 // ---------------------------------------------------------------------------------------------
-// k_learn_fixed<NCH>: the fused fast path for the cache's in-place encoding.
+// k_learn_fixed<G, NCH, NLR, OPTK>: the fused fast path for the cache's in-place encoding.
 //
 // The parser stores a namespace with one feature of weight 1.0 directly in its header slot
 // (parser.rs:396-404) -- the case the reference itself special-cases ("value == 1.0", block_ffm.rs:978,
-// SPEED.md).  When every field is one namespace and k % 4 == 0, one WARP takes one raw record and does
-// translate + forward + backward + update with the latent rows in registers:
-//   lane j (+32t) owns the 16-byte chunk c of row e:  W[h_e + 4c .. 4c+4)  = w_e towards field z = 4c/k
+// SPEED.md).  When every field is one namespace and k % 4 == 0, a group of G lanes (a warp, or half a warp for narrow
+// models) takes one raw record and does translate + forward + backward + update with the latent rows in registers:
+//   lane j (+G t) owns the 16-byte chunk c of row e:  W[h_e + 4c .. 4c+4)  = w_e towards field z = 4c/k
 //   its partner chunk  w_z towards field e  is fetched through a padded shared-memory transpose,
 //   dot(mine, partner) is both the forward term and (times g) the gradient of my chunk,
 //   so a lane issues one LDG.128, one ATOMG.128 and one REDG.128 per chunk and nothing else touches HBM.
@@ -613,21 +613,22 @@ struct FixedParams {
     uint32_t rec_smem_floats;      // F * (cpr + 1) * 4: the transpose area of one record
 };
 
-// Block = FIXED_WARPS independent warps, one record per warp and round; nothing is exchanged between warps.
+// Block = FIXED_WARPS independent warps, one record per G-lane group and round; nothing is exchanged between groups.
 //
 // LR updates (block_lr.rs:135-151) step from the accumulator value read at gather time -- the cell is loaded as one
 // float2 {w, acc} anyway -- so they are two fire-and-forget reductions and no warp waits for an atomic's return value.
-// The constant feature is special: EVERY record hits its cell (feature_buffer.rs:270-276), and same-address atomics
-// serialise in L2 (~4 ns each on B200, tools/hotrow_microbench.cu), which capped a version with one bias update per
-// record at ~180 M records/s.  Each warp therefore sums the bias gradients of FIXED_BIAS_PERIOD consecutive records
-// in a register and applies them as one update,  acc += sum g_i^2 ;  w -= (sum g_i) * LUT[acc]  (during the
-// concurrency ramp: every record).
+// The constant feature is special: EVERY record hits its cell (feature_buffer.rs:270-276).  Same-address atomics
+// serialise in L2 (~4 ns each on B200, tools/hotrow_microbench.cu: one bias update per record capped an early version at
+// ~180 M records/s), and so do same-address LOADS: 5e8 ld.cg per second of that one cell were the cap of every later
+// version until the cell moved into a register (profiles/r01_c2_fixed_indep_top_stalls.txt).  Each group therefore keeps
+// the cell in a register, sums the bias gradients of FIXED_BIAS_PERIOD consecutive records and applies them as one update,
+//   acc += sum g_i^2 ;  w -= (sum g_i) * LUT[acc],   re-reading the cell then (during the concurrency ramp: every record).
 // History: two block-level schemes -- __syncthreads() every round with every warp scanning the others' pairs, then a
 // deferred mbarrier hand-over -- left the warps waiting for the slowest one of their block for 26 % / 45 % of the
 // stall samples (profiles/r01_c2_fixed_ncu_full.txt, profiles/r01_c2_fixed_mbar_top_stalls.txt).
 constexpr int FIXED_WARPS = 16;
 constexpr int FIXED_LR_MAX = 64;       // LR entries per record the fast path supports (two per lane)
-constexpr int FIXED_BIAS_PERIOD = 16;  // records whose bias updates one warp combines
+constexpr int FIXED_BIAS_PERIOD = 16;  // records whose bias updates one group combines
 
 __device__ __forceinline__ void red_add_f32(float *addr, float v) { asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory"); }
 
