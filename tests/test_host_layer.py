@@ -133,6 +133,16 @@ def test_cache_of_gz_input_is_an_lz4_frame(tmp_path):  # cache.rs:68-71, 89-125
     open(foreign, "wb").write(pa.Codec("lz4").compress(image).to_pybytes())
     r2, off2, _ = host.cache_read(foreign, vw)
     assert np.array_equal(r2, recs) and np.array_equal(off2, off)
+    # more than one 4 MiB block, and Arrow's multi-block (linked) frames of the same image
+    big = w.records(250000).reshape(-1)   # 11 MB
+    bigp, bigz = str(tmp_path / "big.vw.fwcache"), str(tmp_path / "big.vw.gz.fwcache")
+    host.cache_write(bigp, vw, big)
+    host.cache_write(bigz, vw, big)
+    big_image = open(bigp, "rb").read()
+    assert pa.Codec("lz4").decompress(open(bigz, "rb").read(), decompressed_size=len(big_image)).to_pybytes() == big_image
+    assert np.array_equal(host.cache_read(bigz, vw)[0], big)
+    open(bigz, "wb").write(pa.Codec("lz4").compress(big_image).to_pybytes())
+    assert np.array_equal(host.cache_read(bigz, vw)[0], big)
     # edge cases: empty cache body, incompressible payload, damaged frames
     empty = str(tmp_path / "empty.vw.gz.fwcache")
     host.cache_write(empty, vw, np.zeros(0, np.uint32))
