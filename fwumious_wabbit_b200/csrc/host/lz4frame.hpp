@@ -63,9 +63,11 @@ inline void decode_block(const uint8_t *src, size_t n, std::vector<uint8_t> &out
         if (mlen == 15) { uint8_t b; do { if (ip >= iend) throw std::runtime_error("lz4: truncated match length"); b = *ip++; mlen += b; } while (b == 255); }
         mlen += 4;
         if (offset == 0 || offset > out.size()) throw std::runtime_error("lz4: match offset outside the window");
-        size_t from = out.size() - offset;
-        out.reserve(out.size() + mlen);
-        for (size_t i = 0; i < mlen; i++) out.push_back(out[from + i]); // byte by byte: overlapping matches repeat the pattern
+        const size_t at = out.size(), from = at - offset;
+        out.resize(at + mlen);
+        uint8_t *o = out.data();
+        if (offset >= mlen) memcpy(o + at, o + from, mlen);                      // source and destination do not overlap
+        else for (size_t i = 0; i < mlen; i++) o[at + i] = o[from + i];          // overlapping match: the pattern repeats
     }
 }
 
