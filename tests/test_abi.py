@@ -44,6 +44,28 @@ def test_sass_has_vector_atomics():
     assert "sm_100a" in sass
 
 
+def test_sass_has_tensor_core_instructions():
+    """The head's GEMMs really are tcgen05: UTCHMMA (tcgen05.mma), UTCBAR (tcgen05.commit) and LDTM (tcgen05.ld) in the cubin."""
+    import shutil
+    import subprocess
+
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTCBAR" in sass and "LDTM" in sass
+
+
+def test_product_never_touches_the_oracle():
+    """oracle/ is test infrastructure: nothing under the package (Python or C++/CUDA) imports, links or opens it."""
+    pkg = os.path.dirname(os.path.abspath(fw.__file__))
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                text = open(os.path.join(root, f), errors="ignore").read()
+                assert not re.search(r"(from|import)\s+oracle|fw_oracle|libfworacle|#include[^\n]*oracle", text), os.path.join(root, f)
+
+
 @pytest.mark.skipif(has_cuda(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     with pytest.raises(_lib.FwgpuError) as ei:
