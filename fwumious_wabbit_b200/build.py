@@ -9,6 +9,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libfwgpu.so")
 CLI_SRC = os.path.join(HERE, "cli", "fwgpu_main.cpp")
 CLI_OUT = os.path.join(HERE, "fwgpu")
+SYNTH_SRC = os.path.join(HERE, "synth_src", "fwsynth.cpp")  # bench / test data generator: its own library, not product code
+SYNTH_OUT = os.path.join(HERE, "libfwsynth.so")
 UMMA_TEST_SRC = os.path.join(os.path.dirname(HERE), "tools", "umma_gemm_test.cu")
 UMMA_TEST_OUT = os.path.join(HERE, "umma_gemm_test")
 
@@ -17,6 +19,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unused-function",
     "-Xptxas", "-v",
+    "-split-compile", "0", "-t", "0",  # device code of one translation unit optimised on all cores
     "-shared",
 ]
 
@@ -38,11 +41,12 @@ def deps():
     out.append(os.path.join(os.path.dirname(HERE), "include", "fwhost.h"))
     out.append(CLI_SRC)
     out.append(UMMA_TEST_SRC)
+    out.append(SYNTH_SRC)
     return out
 
 
 def up_to_date():
-    if not os.path.exists(OUT) or not os.path.exists(CLI_OUT) or not os.path.exists(UMMA_TEST_OUT):
+    if not all(os.path.exists(p) for p in (OUT, CLI_OUT, UMMA_TEST_OUT, SYNTH_OUT)):
         return False
     t = os.path.getmtime(OUT)
     return all(os.path.getmtime(d) <= t for d in deps())
@@ -62,6 +66,13 @@ def build(force=False, verbose=False):
     if res.returncode != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed")
+    cmd1 = ["g++", "-O3", "-std=c++17", "-fPIC", "-shared", "-pthread", "-Wall", "-o", SYNTH_OUT, SYNTH_SRC]
+    res1 = subprocess.run(cmd1, capture_output=True, text=True)
+    with open(os.path.join(HERE, "build.log"), "a") as f:
+        f.write(" ".join(cmd1) + "\n" + res1.stdout + res1.stderr)
+    if res1.returncode != 0:
+        sys.stderr.write(res1.stdout + res1.stderr)
+        raise RuntimeError("building libfwsynth.so failed")
     # the command-line front end (fwgpu): plain C++ against the two C ABIs, finds the library next to itself
     cmd2 = ["g++", "-O2", "-std=c++17", "-Wall", "-o", CLI_OUT, CLI_SRC, "-L" + HERE, "-lfwgpu", "-lz", "-Wl,-rpath,$ORIGIN"]
     res2 = subprocess.run(cmd2, capture_output=True, text=True)

@@ -50,7 +50,7 @@ struct Flags {
     bool has(const char *k) const { for (auto &p : kv) if (p.first == k) return true; return false; }
 };
 const char *VALUE[] = {"data", "predictions", "final_regressor", "initial_regressor", "predictions_after", "holdout_after", "convert_inference_regressor",
-                       "batch_size", "device", "hogwild_threads", nullptr};
+                       "batch_size", "device", "hogwild_threads", "prediction_model_delay", nullptr};
 const char *BOOLS[] = {"cache", "testonly", "save_resume", "quiet", "predictions_stdout", "build_cache_without_training", "sequential", "hogwild_training", nullptr};
 bool in(const char **l, const std::string &s) { for (; *l; l++) if (s == *l) return true; return false; }
 std::string long_name(const std::string &t) {
@@ -117,7 +117,9 @@ int main(int argc, char **argv)
     }
     const bool immutable = testonly || convert;
     // what the file holds: accumulators unless its ModelInstance says SGD
-    const bool file_sgd = reader && std::string(fwhost_regressor_mi_json(reader)).find("\"optimizer\": \"SGD\"") != std::string::npos;
+    const bool file_sgd = reader && fwhost_regressor_optimizer(reader) == FWGPU_OPT_SGD;
+    // persistence.rs:144-161: a file written with --weight_quantization holds the FFM block as 16-bit buckets (never when converting)
+    const bool file_quantized = reader && fwhost_regressor_dequantize(reader) && !convert;
     fwgpu_model_desc desc; void *keep = nullptr;
     if (fwhost_model_desc_from_json(mi_json.c_str(), vwmap_json.c_str(), immutable ? 1 : 0, &desc, &keep, err, sizeof(err))) die(err);
     if (fl.has("sequential")) desc.hogwild_ramp_div = 0x7fffffffu;
@@ -136,7 +138,10 @@ int main(int argc, char **argv)
             uint64_t n, by; fwgpu_block_len(ctx, blocks[b], &n, &by);
             const bool want_state = !file_sgd && !immutable;
             std::vector<float> buf((size_t)n * (file_sgd ? 1 : 2));
-            if (fwhost_regressor_read(reader, buf.data(), buf.size() * 4)) die("truncated regressor file");
+            if (file_quantized && blocks[b] == FWGPU_BLOCK_FFM) {
+                if (!file_sgd) die("a quantized regressor file must be an inference (SGD) regressor");
+                if (fwhost_regressor_read_quantized(reader, buf.data(), n)) die("truncated regressor file");
+            } else if (fwhost_regressor_read(reader, buf.data(), buf.size() * 4)) die("truncated regressor file");
             if (!file_sgd && !want_state) { // drop the accumulators (read_weights_from_buf_into_forward_only)
                 if (blocks[b] == FWGPU_BLOCK_LR) { for (uint64_t i = 0; i < n; i++) buf[i] = buf[2 * i]; }
                 buf.resize(n);
@@ -194,7 +199,28 @@ int main(int argc, char **argv)
     float *preds = nullptr;
     if (fwgpu_host_alloc((void **)&preds, std::max<uint64_t>(batch, 1) * 4) != FWGPU_OK) die("pinned allocation failed");
     auto t0 = std::chrono::steady_clock::now();
-    for (uint64_t done = 0; done < (uint64_t)n_examples;) {
+    // --prediction_model_delay D (main.rs:200-258): example i is scored by a model that has learned examples 1 .. i-D-1; the
+    // example D places back is learned right after.  In mini-batch form: score [done, done+cnt) with cnt <= D, then learn
+    // [done-D, done+cnt-D): every example sees at least the reference's delay, the first of each batch exactly it.  The last
+    // D examples are never learned, as in the reference.
+    const uint64_t delay = fl.get("prediction_model_delay") ? strtoull(fl.get("prediction_model_delay"), nullptr, 10) : 0;
+    for (uint64_t done = 0; delay && done < (uint64_t)n_examples;) {
+        const uint64_t cnt = std::min<uint64_t>(std::min<uint64_t>(batch, delay), (uint64_t)n_examples - done);
+        check(ctx, fwgpu_learn_records(ctx, records, n_words, rec_off + done, (uint32_t)cnt, preds, 0), "learn_records");
+        if (!testonly && done + cnt > delay) { // examples (done - D, done + cnt - D] in 1-based numbering
+            const uint64_t a = done > delay ? done - delay : 0, b = done + cnt - delay;
+            check(ctx, fwgpu_learn_records(ctx, records, n_words, rec_off + a, (uint32_t)(b - a), nullptr, 1), "learn_records");
+        }
+        check(ctx, fwgpu_sync(ctx), "sync");
+        for (uint64_t i = 0; i < cnt; i++) {
+            if (done + i + 1 > predictions_after) {
+                if (fl.has("predictions_stdout")) printf("%.6f\n", preds[i]);
+                if (pf) fprintf(pf, "%.6f\n", preds[i]);
+            }
+        }
+        done += cnt;
+    }
+    for (uint64_t done = 0; !delay && done < (uint64_t)n_examples;) {
         uint64_t cnt = std::min<uint64_t>(batch, (uint64_t)n_examples - done);
         // example numbers are 1-based in the reference: update while example_num < holdout_after (main.rs:241-244)
         bool update = !testonly;
@@ -203,7 +229,8 @@ int main(int argc, char **argv)
             if (first_num >= holdout_after) update = false;
             else cnt = std::min<uint64_t>(cnt, holdout_after - first_num);
         }
-        check(ctx, fwgpu_learn_records(ctx, records + rec_off[done], rec_off[done + cnt] - rec_off[done], rec_off + done, (uint32_t)cnt, preds, update ? 1 : 0), "learn_records");
+        // rec_off holds absolute word offsets into `records`: pass the unshifted base together with the offset window
+        check(ctx, fwgpu_learn_records(ctx, records, n_words, rec_off + done, (uint32_t)cnt, preds, update ? 1 : 0), "learn_records");
         check(ctx, fwgpu_sync(ctx), "sync");
         for (uint64_t i = 0; i < cnt; i++) {
             if (done + i + 1 > predictions_after) {
@@ -216,7 +243,7 @@ int main(int argc, char **argv)
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!quiet) fprintf(stderr, "fwgpu: Elapsed: %.2fs rows: %lld (%.0f rows/s)\n", secs, (long long)n_examples, n_examples / std::max(secs, 1e-9));
     if (pf) fclose(pf);
-    if (final_regressor) save(final_regressor, false);
+    if (final_regressor) save(final_regressor, /*as_sgd=*/immutable); // an immutable ctx holds weights only: the file says SGD (persistence.rs:163-172)
     fwgpu_host_free(preds);
     fwhost_free(records); fwhost_free(rec_off);
     fwhost_model_desc_free(keep);

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <poll.h>
 #include <sys/socket.h>
+#include <sys/stat.h>
 #include <sys/un.h>
 #include <unistd.h>
 
@@ -142,9 +143,12 @@ static void serve_connection(ShardGroup *g, int s)
         const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(g->timeout_ms);
         if (req[0] == REQ_FD) {
             const bool ready = g->cv.wait_until(lk, deadline, [&] { return g->stop.load() || g->arrays.size() > req[1]; });
-            const int fd = (ready && !g->stop.load()) ? g->arrays[req[1]]->own_fd : -1;
+            // a destroyed array leaves a null slot (indices are the protocol); duplicate the fd under the lock so that a
+            // concurrent destroy_array cannot close it between the look-up and the send
+            const ShardedArray *arr = (ready && !g->stop.load()) ? g->arrays[req[1]] : nullptr;
+            const int fd = (arr && arr->own_fd >= 0) ? ::dup(arr->own_fd) : -1;
             lk.unlock();
-            if (fd >= 0) send_fd(s, fd);
+            if (fd >= 0) { send_fd(s, fd); ::close(fd); }
         } else if (req[0] == REQ_BARRIER) {
             const bool ready = g->cv.wait_until(lk, deadline, [&] { return g->stop.load() || g->phase >= req[1]; });
             lk.unlock();
@@ -153,6 +157,11 @@ static void serve_connection(ShardGroup *g, int s)
         }
     }
     ::close(s);
+    {
+        std::lock_guard<std::mutex> lk(g->mu);
+        g->active_workers--;
+    }
+    g->cv.notify_all();
 }
 
 bool ShardGroup::start(uint32_t rank_, uint32_t world_, int device_, const char *prefix_, uint32_t timeout_ms_)
@@ -168,19 +177,28 @@ bool ShardGroup::start(uint32_t rank_, uint32_t world_, int device_, const char 
     if (!sock_addr(path, a)) { error = "rendezvous path too long"; return false; }
     ::unlink(path.c_str());
     listen_fd = ::socket(AF_UNIX, SOCK_STREAM, 0);
-    if (listen_fd < 0 || ::bind(listen_fd, (sockaddr *)&a, sizeof(a)) != 0 || ::listen(listen_fd, 64) != 0) {
+    // whoever can connect can obtain the exported GPU-memory handles: the socket is created owner-only
+    const mode_t old_mask = ::umask(0177);
+    const bool bound = listen_fd >= 0 && ::bind(listen_fd, (sockaddr *)&a, sizeof(a)) == 0;
+    ::umask(old_mask);
+    if (!bound || ::chmod(path.c_str(), 0600) != 0 || ::listen(listen_fd, 64) != 0) {
         error = "cannot listen on " + path + ": " + strerror(errno);
         return false;
     }
     server = std::thread([this] {
-        std::vector<std::thread> workers;
+        // one short-lived detached thread per request (a barrier request blocks until this rank arrives); the destructor
+        // waits for active_workers to drain, so nothing accumulates however many barriers a run performs
         while (!stop.load()) {
             pollfd pf{listen_fd, POLLIN, 0};
             if (::poll(&pf, 1, 100) <= 0) continue;
             int s = ::accept(listen_fd, nullptr, nullptr);
-            if (s >= 0) workers.emplace_back(serve_connection, this, s);
+            if (s < 0) continue;
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                active_workers++;
+            }
+            std::thread(serve_connection, this, s).detach();
         }
-        for (auto &w : workers) w.join();
     });
     return true;
 }
@@ -193,6 +211,10 @@ ShardGroup::~ShardGroup()
     }
     cv.notify_all();
     if (server.joinable()) server.join();
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait_for(lk, std::chrono::milliseconds(timeout_ms + 1000), [&] { return active_workers == 0; });
+    }
     if (listen_fd >= 0) { ::close(listen_fd); ::unlink((prefix + "." + std::to_string(rank)).c_str()); }
 }
 
@@ -267,6 +289,10 @@ bool ShardGroup::create_array(ShardedArray &a, const std::vector<size_t> &sizes)
 void ShardGroup::destroy_array(ShardedArray &a)
 {
     Drv &d = drv();
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        for (auto &p : arrays) if (p == &a) p = nullptr; // the slot stays (indices are the protocol), the pointer goes
+    }
     if (!d.ok) return;
     if (a.va) {
         d.MemUnmap(a.va, a.total_bytes);

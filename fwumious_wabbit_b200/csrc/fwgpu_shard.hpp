@@ -52,6 +52,7 @@ struct ShardGroup {
     std::mutex mu;
     std::condition_variable cv;
     uint64_t phase = 0;                // barrier phases this rank has reached
+    int active_workers = 0;            // request threads in flight (guarded by mu)
     std::string error;
 
     ~ShardGroup();

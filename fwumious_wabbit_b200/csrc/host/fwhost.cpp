@@ -158,7 +158,7 @@ int parse_line(const Parser &P, const char *p, size_t size, uint32_t *out, size_
 // ---------------------------------------------------------------- files
 constexpr uint32_t CACHE_VERSION = 11, REGRESSOR_VERSION = 6; // cache.rs:12-13, persistence.rs:17-18
 
-struct RegReader { FILE *f = nullptr; std::string vwmap_json, mi_json; uint64_t weights_len = 0; };
+struct RegReader { FILE *f = nullptr; std::string vwmap_json, mi_json; uint64_t weights_len = 0; uint32_t optimizer = 0; int dequantize = 0; };
 
 bool read_exact(FILE *f, void *dst, size_t n) { return fread(dst, 1, n, f) == n; }
 bool read_blob(FILE *f, std::string &out)
@@ -310,6 +310,8 @@ ModelInstanceH mi_from_args(const Args &a, const VwMap &vw)
 } // namespace
 
 // ================================================================ C ABI
+extern "C" uint32_t fwhost_murmur3_32(const void *key, size_t len, uint32_t seed) { return fwhost::murmur3_32(key, len, seed); }
+
 extern "C" {
 
 void fwhost_free(void *p) { free(p); }
@@ -412,6 +414,11 @@ int64_t fwhost_parser_parse_text(void *parser, const char *text, size_t len, uin
     for (auto &t : th) t.join();
     for (int t = 0; t < nt; t++) if (bad[t] >= 0) { set_err(err, errcap, errs[t] + " (line " + std::to_string(bad[t] + 1) + ")"); return -1; }
     uint64_t words = 0, n = 0;
+    {   // rec_off holds u32 word offsets
+        uint64_t total = 0;
+        for (int t = 0; t < nt; t++) total += slabs[t].size();
+        if (total > 0xffffffffull) { set_err(err, errcap, "input exceeds 2^32 record words (16 GiB): split it"); return -1; }
+    }
     for (int t = 0; t < nt; t++) {
         if (words + slabs[t].size() > cap_words) { set_err(err, errcap, "record buffer too small"); return -1; }
         if (!slabs[t].empty()) memcpy(out + words, slabs[t].data(), slabs[t].size() * 4);
@@ -490,6 +497,7 @@ int64_t fwhost_cache_read(const char *path, const char *expect_vwmap_json, uint3
         VwMap in_file = vwmap_from_json(json_parse(blob));
         if (expect_vwmap_json && !(in_file == vwmap_from_json(json_parse(expect_vwmap_json)))) throw std::runtime_error("vw_namespace_map.csv and the one from cache file differ");
         uint64_t n_words = (uint64_t)(image.size() - pos) / 4;
+        if (n_words > 0xffffffffull) throw std::runtime_error("cache exceeds 2^32 record words (16 GiB): rec_off holds u32 word offsets");
         uint32_t *recs = (uint32_t *)malloc(std::max<uint64_t>(n_words, 1) * 4);
         if (n_words) memcpy(recs, image.data() + pos, n_words * 4);
         std::vector<uint32_t> offs;
@@ -544,7 +552,12 @@ void *fwhost_regressor_open(const char *path, char *err, size_t errcap)
         if (!read_exact(r->f, &version, 4) || version != REGRESSOR_VERSION) throw std::runtime_error("Regressor file version of this binary: 6, version of the regressor file: " + std::to_string(version));
         if (!read_blob(r->f, r->vwmap_json) || !read_blob(r->f, r->mi_json) || !read_exact(r->f, &r->weights_len, 8)) throw std::runtime_error("truncated regressor header");
         json_parse(r->vwmap_json);
-        json_parse(r->mi_json);
+        {   // what the writer stored: the optimizer decides whether accumulators follow the weights, dequantize_weights
+            // whether the FFM block is the 16-bit form of quantization.rs:41-95
+            ModelInstanceH m = mi_from_json(json_parse(r->mi_json));
+            r->optimizer = m.optimizer;
+            r->dequantize = m.dequantize_weights > 0 ? 1 : 0;
+        }
         return r;
     } catch (const std::exception &e) {
         if (r->f) fclose(r->f);
@@ -557,6 +570,37 @@ const char *fwhost_regressor_vwmap_json(void *r) { return ((RegReader *)r)->vwma
 const char *fwhost_regressor_mi_json(void *r) { return ((RegReader *)r)->mi_json.c_str(); }
 uint64_t fwhost_regressor_weights_len(void *r) { return ((RegReader *)r)->weights_len; }
 int fwhost_regressor_read(void *r, void *dst, uint64_t bytes) { return read_exact(((RegReader *)r)->f, dst, bytes) ? 0 : -1; }
+uint32_t fwhost_regressor_optimizer(void *r) { return ((RegReader *)r)->optimizer; }
+int fwhost_regressor_dequantize(void *r) { return ((RegReader *)r)->dequantize; }
+// quantization.rs:77-95 dequantize_ffm_weights: 8-byte header {f32 increment, f32 min}, then one IEEE half per weight holding the
+// bucket number; weight = min + bucket * increment
+int fwhost_regressor_read_quantized(void *r, float *dst, uint64_t n)
+{
+    FILE *f = ((RegReader *)r)->f;
+    float hdr[2];
+    if (!read_exact(f, hdr, 8)) return -1;
+    std::vector<uint16_t> buf(1 << 16);
+    for (uint64_t done = 0; done < n;) {
+        const uint64_t cnt = std::min<uint64_t>(buf.size(), n - done);
+        if (!read_exact(f, buf.data(), cnt * 2)) return -1;
+        for (uint64_t i = 0; i < cnt; i++) {
+            const uint16_t h = buf[i];
+            const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, ex = (h >> 10) & 0x1fu, man = h & 0x3ffu;
+            uint32_t bits;
+            if (ex == 0) {
+                const float sub = (float)man * 5.9604644775390625e-08f; // man * 2^-24, exact
+                memcpy(&bits, &sub, 4);
+                bits |= sign;
+            } else if (ex == 31) bits = sign | 0x7f800000u | (man << 13);
+            else bits = sign | ((ex + 112u) << 23) | (man << 13);
+            float v;
+            memcpy(&v, &bits, 4);
+            dst[done + i] = hdr[1] + v * hdr[0];
+        }
+        done += cnt;
+    }
+    return 0;
+}
 int fwhost_regressor_skip(void *r, uint64_t bytes) { return fseek(((RegReader *)r)->f, (long)bytes, SEEK_CUR) == 0 ? 0 : -1; }
 void fwhost_regressor_close(void *r) { RegReader *rr = (RegReader *)r; if (rr) { if (rr->f) fclose(rr->f); delete rr; } }
 

@@ -44,6 +44,9 @@ def _L():
     L.fwhost_regressor_weights_len.argtypes, L.fwhost_regressor_weights_len.restype = [vp], C.c_uint64
     L.fwhost_regressor_read.argtypes, L.fwhost_regressor_read.restype = [vp, vp, C.c_uint64], C.c_int
     L.fwhost_regressor_skip.argtypes, L.fwhost_regressor_skip.restype = [vp, C.c_uint64], C.c_int
+    L.fwhost_regressor_optimizer.argtypes, L.fwhost_regressor_optimizer.restype = [vp], C.c_uint32
+    L.fwhost_regressor_dequantize.argtypes, L.fwhost_regressor_dequantize.restype = [vp], C.c_int
+    L.fwhost_regressor_read_quantized.argtypes, L.fwhost_regressor_read_quantized.restype = [vp, vp, C.c_uint64], C.c_int
     L.fwhost_regressor_close.argtypes, L.fwhost_regressor_close.restype = [vp], None
     L._host_bound = True
     return L
@@ -269,7 +272,11 @@ def new_regressor_from_filename(filename, immutable=False, cmd_arguments=None, d
             arr = (C.c_char_p * len(cmd_arguments))(*[a.encode() for a in cmd_arguments])
             mi_json = _take(L.fwhost_model_instance_update_from_cmdline(mi_json.encode(), len(cmd_arguments), arr, err, _ERR), err)
         mi = model_instance_from_json(mi_json, vw)
-        file_has_state = mi.optimizer != Optimizer.SGD  # what the WRITER stored: accumulators unless it was SGD
+        file_has_state = L.fwhost_regressor_optimizer(r) != Optimizer.SGD  # what the WRITER stored: accumulators unless it was SGD
+        # persistence.rs:144-161: --weight_quantization files hold the FFM block as 8-byte header + one half per weight
+        quantized = bool(L.fwhost_regressor_dequantize(r))
+        if quantized and file_has_state:
+            raise IOError("a quantized regressor file must be an inference (SGD) regressor")
         re = Regressor(mi, device=device, immutable=immutable)
         expected = sum(re.block_len(b)[0] for b in _block_order(mi))
         got = L.fwhost_regressor_weights_len(r)
@@ -288,7 +295,10 @@ def new_regressor_from_filename(filename, immutable=False, cmd_arguments=None, d
                 re.import_block(b, buf, with_optimizer_state=want_state)
             else:
                 w = np.empty(n, dtype=np.float32)
-                if L.fwhost_regressor_read(r, w.ctypes.data_as(C.c_void_p), n * 4) != 0:
+                if quantized and b == _lib.BLOCK_FFM:
+                    if L.fwhost_regressor_read_quantized(r, w.ctypes.data_as(C.c_void_p), n) != 0:
+                        raise IOError("truncated regressor file")
+                elif L.fwhost_regressor_read(r, w.ctypes.data_as(C.c_void_p), n * 4) != 0:
                     raise IOError("truncated regressor file")
                 if want_state:
                     acc = np.empty(n, dtype=np.float32)

@@ -1,33 +1,39 @@
 """Synthetic workloads of BASELINE.json's configs: records in the reference's cache format
-(parser.rs:57-74) produced by the C++ generator in csrc/host/synth.cpp, plus the matching
-ModelInstance (the flags SURVEY.md section 8d lists for each config)."""
+(parser.rs:57-74) produced by the C++ generator in synth_src/fwsynth.cpp (libfwsynth.so -- its own
+library, so that bench.py's reference arm generates its input without loading libfwgpu.so), plus the
+matching ModelInstance (the flags SURVEY.md section 8d lists for each config)."""
 import ctypes as C
 import string
 
 import numpy as np
 
-from . import _lib
+import os
+
 from .model_instance import ModelInstance, Optimizer
 
 NS_LETTERS = string.ascii_uppercase + string.ascii_lowercase
+_SYNTH_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libfwsynth.so")
+_synth = None
 
 
 def _host():
-    L = _lib.lib()
-    if not getattr(L, "_synth_bound", False):
-        L.fwhost_murmur3_32.restype = C.c_uint32
-        L.fwhost_murmur3_32.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
-        L.fwhost_synth_records.restype = C.c_int
-        L.fwhost_synth_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_char_p, C.c_void_p,
-                                           C.c_uint64, C.c_int]
-        L.fwhost_synth_line.restype = C.c_int
-        L.fwhost_synth_line.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_char_p, C.c_void_p, C.c_uint64]
-        L._synth_bound = True
-    return L
+    global _synth
+    if _synth is None:
+        if not os.path.exists(_SYNTH_PATH):
+            raise ImportError(f"{_SYNTH_PATH} is missing: build it with `python -m fwumious_wabbit_b200.build`")
+        L = C.CDLL(_SYNTH_PATH)
+        L.fwsynth_murmur3_32.restype = C.c_uint32
+        L.fwsynth_murmur3_32.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
+        L.fwsynth_records.restype = C.c_int
+        L.fwsynth_records.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_char_p, C.c_void_p, C.c_uint64, C.c_int]
+        L.fwsynth_line.restype = C.c_int
+        L.fwsynth_line.argtypes = [C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint32, C.c_char_p, C.c_void_p, C.c_uint64]
+        _synth = L
+    return _synth
 
 
 def murmur3_32(data: bytes, seed: int = 0) -> int:
-    return _host().fwhost_murmur3_32(data, len(data), seed)
+    return _host().fwsynth_murmur3_32(data, len(data), seed)
 
 
 class Workload:
@@ -54,18 +60,18 @@ class Workload:
         if out is None:
             out = np.empty((n_examples, self.record_len), dtype=np.uint32)
         assert out.dtype == np.uint32 and out.flags.c_contiguous and out.size >= n_examples * self.record_len
-        rc = _host().fwhost_synth_records(out.ctypes.data_as(C.c_void_p), n_examples, first, self.n_namespaces,
+        rc = _host().fwsynth_records(out.ctypes.data_as(C.c_void_p), n_examples, first, self.n_namespaces,
                                           self.ns_names.encode(), self.cardinality.ctypes.data_as(C.c_void_p), seed, threads)
         if rc != 0:
-            raise RuntimeError("fwhost_synth_records failed")
+            raise RuntimeError("fwsynth_records failed")
         return out
 
     def line(self, i, seed=1) -> str:
         buf = C.create_string_buffer(64 + 24 * self.n_namespaces)
-        n = _host().fwhost_synth_line(buf, len(buf), i, self.n_namespaces, self.ns_names.encode(),
+        n = _host().fwsynth_line(buf, len(buf), i, self.n_namespaces, self.ns_names.encode(),
                                       self.cardinality.ctypes.data_as(C.c_void_p), seed)
         if n < 0:
-            raise RuntimeError("fwhost_synth_line failed")
+            raise RuntimeError("fwsynth_line failed")
         return buf.value.decode()
 
     # algorithmic bytes per example, SURVEY.md section 8(d)

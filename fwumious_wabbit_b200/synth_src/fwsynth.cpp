@@ -1,8 +1,10 @@
-// Synthetic record generator (see include/fwhost.h).  Deterministic and shardable: every draw is a
+// Synthetic record generator of bench.py and the tests -> libfwsynth.so.  NOT part of the product library (libfwgpu.so): the
+// reference arm of bench.py generates its input without loading any product code.  Deterministic and shardable: every draw is a
 // pure function of (seed, example index, namespace index), so the CPU baseline and the GPU arm of
 // bench.py see the same stream without a multi-GB file.
-#include "../../../include/fwhost.h"
-#include "murmur3.hpp"
+#include "../csrc/host/murmur3.hpp"
+#include <cstdint>
+#include <cstddef>
 
 #include <algorithm>
 #include <cmath>
@@ -65,9 +67,9 @@ inline int feature_name(char *buf, char ns, uint32_t id) { return std::snprintf(
 
 } // namespace
 
-extern "C" uint32_t fwhost_murmur3_32(const void *key, size_t len, uint32_t seed) { return fwhost::murmur3_32(key, len, seed); }
+extern "C" uint32_t fwsynth_murmur3_32(const void *key, size_t len, uint32_t seed) { return fwhost::murmur3_32(key, len, seed); }
 
-extern "C" int fwhost_synth_records(uint32_t *out, uint64_t n_examples, uint64_t first_example, uint32_t n_ns, const char *ns_names,
+extern "C" int fwsynth_records(uint32_t *out, uint64_t n_examples, uint64_t first_example, uint32_t n_ns, const char *ns_names,
                                     const uint32_t *card, uint64_t seed, int n_threads)
 {
     if (!out || !ns_names || !card || n_ns == 0 || n_ns > 255) return -1;
@@ -113,7 +115,7 @@ extern "C" int fwhost_synth_records(uint32_t *out, uint64_t n_examples, uint64_t
     return 0;
 }
 
-extern "C" int fwhost_synth_line(char *dst, size_t cap, uint64_t i, uint32_t n_ns, const char *ns_names, const uint32_t *card, uint64_t seed)
+extern "C" int fwsynth_line(char *dst, size_t cap, uint64_t i, uint32_t n_ns, const char *ns_names, const uint32_t *card, uint64_t seed)
 {
     std::vector<uint32_t> ids(n_ns);
     uint32_t label;

@@ -1,7 +1,6 @@
 /*
  * fwhost.h -- host-side (CPU, C++ inside, C ABI outside) pieces either side of the GPU hot path:
- * hashing, the VW text parser, the .fwcache reader/writer, the regressor file format and the
- * synthetic-data generator used by bench.py.  They restate the reference's host code
+ * hashing, the VW text parser, the .fwcache reader/writer and the regressor file format.  They restate the reference's host code
  * (parser.rs, cache.rs, persistence.rs, vwmap.rs) so that a maintainer can keep using the Rust
  * host unchanged; nothing here is on the GPU hot path and nothing here calls oracle/.
  */
@@ -17,24 +16,6 @@ extern "C" {
 
 /* fasthash murmur3::hash32_with_seed == MurmurHash3_x86_32 (call sites parser.rs:82-83, 382-385) */
 uint32_t fwhost_murmur3_32(const void *key, size_t len, uint32_t seed);
-
-/*
- * Synthetic CTR-like data in the reference's record format (parser.rs:57-74), fixed width
- * (every namespace single-valued, value 1.0): [3+N, label, 1.0f, hash_0 .. hash_{N-1}].
- * Namespace j is named ns_names[j] (1 byte each, like benchmark/generate.py's A, B, C...); its
- * feature for example i is the string "<name><id>" with id drawn log-uniformly (Zipf ~ 1) from
- * [0, cardinality[j]) by a counter-based RNG keyed on (seed, i, j), hashed exactly as the parser
- * would hash the VW text line.  Labels are Bernoulli(sigmoid(planted additive + pairwise score)).
- * first_example lets callers generate disjoint shards / streams.  n_threads <= 0: all cores.
- * out must hold n_examples * (3 + n_namespaces) words.
- */
-int fwhost_synth_records(uint32_t *out, uint64_t n_examples, uint64_t first_example, uint32_t n_namespaces,
-                         const char *ns_names, const uint32_t *cardinality, uint64_t seed, int n_threads);
-
-/* The VW text line that produces record i of the stream above (for parser round-trip tests).
- * Returns the number of bytes written (excluding the trailing NUL), or -1 if cap is too small. */
-int fwhost_synth_line(char *dst, size_t cap, uint64_t example_index, uint32_t n_namespaces, const char *ns_names,
-                      const uint32_t *cardinality, uint64_t seed);
 
 /* ---- everything below returns 0 / a count on success and a negative value on failure with a message in err ----
  * Strings returned as char* are malloc'ed: release them with fwhost_free. */
@@ -78,6 +59,12 @@ const char *fwhost_regressor_mi_json(void *reader);
 uint64_t fwhost_regressor_weights_len(void *reader);
 int fwhost_regressor_read(void *reader, void *dst, uint64_t bytes);
 int fwhost_regressor_skip(void *reader, uint64_t bytes);
+/* what the writer stored: its optimizer (FWGPU_OPT_*; SGD = weights only, else accumulators follow, persistence.rs:163-172) and
+ * whether the FFM block is quantised (ModelInstance.dequantize_weights, persistence.rs:144-161) */
+uint32_t fwhost_regressor_optimizer(void *reader);
+int fwhost_regressor_dequantize(void *reader);
+/* quantization.rs:77-95 dequantize_ffm_weights: reads the 8-byte header and n 16-bit buckets, writes n f32 weights */
+int fwhost_regressor_read_quantized(void *reader, float *dst, uint64_t n);
 void fwhost_regressor_close(void *reader);
 
 /* ModelInstance JSON + vwmap JSON -> fwgpu_model_desc (struct fwgpu_model_desc of include/fwgpu.h, passed as void*). */

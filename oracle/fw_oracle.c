@@ -779,6 +779,7 @@ float fwo_forward_backward(fwo_regressor *r, const fwo_feature_buffer *fb, int u
     if (has_ffm) { /* BlockFFM::forward_backward, block_ffm.rs:122-261 */
         const float *W = r->ffm_w;
         for (uint32_t i = 0; i < F * F; i++) out[i] = 0.0f;
+        if (fb->n_ffm) __builtin_prefetch(&contra[fb->ffm[0].contra_field_index], 1, 3); /* block_ffm.rs:163 */
         uint32_t idx = 0;
         for (uint32_t field = 0; field < F; field++) { /* :165-217 */
             uint32_t field_k = field * k;
@@ -789,14 +790,17 @@ float fwo_forward_backward(fwo_regressor *r, const fwo_feature_buffer *fb, int u
             }
             int first = 1;
             while (idx < fb->n_ffm && fb->ffm[idx].contra_field_index == field_k) {
+                /* the reference's software prefetches (block_ffm.rs:163, 184, 194, 205): hints only, the arithmetic
+                 * below is untouched.  :184 fetches the NEXT feature's row head, :194/:205 the next k-block of this row. */
+                if (idx + 1 < fb->n_ffm) __builtin_prefetch(&W[fb->ffm[idx + 1].hash], 0, 3);
                 const fwo_ffm_feat *ft = &fb->ffm[idx];
                 float v = ft->value;
                 size_t fi = ft->hash, off = field_k;
                 if (first) {
-                    for (uint32_t z = 0; z < F; z++) { for (uint32_t q = 0; q < k; q++) contra[off + q] = W[fi + q] * v; off += Fk; fi += k; }
+                    for (uint32_t z = 0; z < F; z++) { __builtin_prefetch(&W[fi + k], 0, 3); for (uint32_t q = 0; q < k; q++) contra[off + q] = W[fi + q] * v; off += Fk; fi += k; }
                     first = 0;
                 } else {
-                    for (uint32_t z = 0; z < F; z++) { for (uint32_t q = 0; q < k; q++) contra[off + q] += W[fi + q] * v; off += Fk; fi += k; }
+                    for (uint32_t z = 0; z < F; z++) { __builtin_prefetch(&W[fi + k], 0, 3); for (uint32_t q = 0; q < k; q++) contra[off + q] += W[fi + q] * v; off += Fk; fi += k; }
                 }
                 idx++;
             }

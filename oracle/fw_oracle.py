@@ -11,6 +11,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "libfworacle.so")
+_SO_NATIVE = os.path.join(_HERE, "_build", "libfworacle_native.so")
 
 OPT_SGD, OPT_ADAGRAD_FLEX, OPT_ADAGRAD_LUT = 0, 1, 2
 GRAPH_REGRESSOR, GRAPH_FFM_BLOCK_ONLY = 0, 1
@@ -84,14 +85,31 @@ class Batch(C.Structure):
 
 
 _lib = None
+_use_native = False
+
+
+def use_native_build():
+    """bench.py's CPU legs: load a copy compiled -march=native ON THIS MACHINE (same source, same -ffp-contract=off) instead
+    of the portable x86-64-v3 build.  Must be called before the first lib(); falls back to the portable build when there
+    is no compiler on the box.  Returns the flags string that was used."""
+    global _use_native
+    if _lib is not None:
+        return "x86-64-v3 (library already loaded)"
+    try:
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "native"])  # always rebuilt: a copy made on another machine may not run here
+        _use_native = os.path.exists(_SO_NATIVE)
+    except Exception:
+        _use_native = False
+    return "-O3 -march=native" if _use_native else "-O3 -march=x86-64-v3 (no compiler on this box)"
 
 
 def lib():
     global _lib
     if _lib is not None:
         return _lib
-    build()
-    L = C.CDLL(_SO)
+    if not _use_native:
+        build()
+    L = C.CDLL(_SO_NATIVE if _use_native else _SO)
     L.fwo_murmur3_32.restype = C.c_uint32
     L.fwo_murmur3_32.argtypes = [C.c_char_p, C.c_size_t, C.c_uint32]
     L.fwo_lut_build.argtypes = [C.c_float, C.c_float, C.c_float, C.POINTER(C.c_float)]

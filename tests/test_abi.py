@@ -72,3 +72,68 @@ def test_no_cpu_fallback():
         fw.Regressor(fw.ModelInstance.new_empty())
     assert ei.value.status == _lib.ERR_CUDA
     assert "no CPU fallback" in str(ei.value)
+
+
+# ------------------------------------------------------------------ struct layout: header == ctypes == the Rust stub
+def _c_struct_fields(header_text, name):
+    """[(field, ctype, array_len)] of `typedef struct <name> { ... } <name>;` (comments stripped)."""
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header_text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(const )?(\w+) ?(\*?)(.*)", decl)
+        base, ptr, names = m.group(2), m.group(3), m.group(4)
+        for nm in names.split(","):
+            nm = nm.strip()
+            is_ptr = bool(ptr) or nm.startswith("*")
+            nm = nm.lstrip("* ")
+            arr = re.match(r"(\w+)\[(\w+)\]", nm)
+            if arr:
+                out.append((arr.group(1), base, arr.group(2), is_ptr))
+            else:
+                out.append((nm, base, None, is_ptr))
+    return out
+
+
+def test_model_desc_layout_matches_everywhere(tmp_path):
+    """include/fwgpu.h, the ctypes mirror and the Rust #[repr(C)] stub in INTEGRATION.md declare fwgpu_model_desc with
+    the same fields in the same order, and the compiler's sizeof/offsetof agree with ctypes (a drifted mirror shifts every
+    later field silently)."""
+    import subprocess
+
+    hdr = open(os.path.join(ROOT, "include", "fwgpu.h")).read()
+    c_fields = _c_struct_fields(hdr, "fwgpu_model_desc")
+    c_names = [f[0] for f in c_fields]
+    py_names = [f[0] for f in _lib.ModelDesc._fields_]
+    assert c_names == py_names
+    # the Rust stub
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    rust = re.search(r"pub struct FwgpuModelDesc \{(.*?)\n\}", md, re.S).group(1)
+    rust = re.sub(r"//[^\n]*", "", rust)
+    rust_fields = re.findall(r"pub (\w+): ([^,]+),", rust)
+    assert [f[0] for f in rust_fields] == c_names
+    rust_type = {"float": "f32", "uint32_t": "u32", "uint8_t": "u8"}
+    for (name, base, arr, is_ptr), (_, rt) in zip(c_fields, rust_fields):
+        rt = rt.strip()
+        want = f"*const {rust_type[base]}" if is_ptr else (f"[{rust_type[base]}; 8]" if arr else rust_type[base])
+        assert rt == want, (name, rt, want)
+    # the initialiser in desc_from() names every field as well
+    init = re.search(r"FwgpuModelDesc \{\n(.*?)\n    \}\n\}", md, re.S).group(1)
+    assert [m for m in re.findall(r"(\w+):", re.sub(r"//[^\n]*", "", init)) if m in c_names] == c_names
+    # sizeof / offsetof from the C compiler vs ctypes
+    src = tmp_path / "layout.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "fwgpu.h"', "int main(void){",
+             'printf("sizeof %zu\\n", sizeof(fwgpu_model_desc));']
+    lines += [f'printf("{n} %zu\\n", offsetof(fwgpu_model_desc, {n}));' for n in c_names]
+    lines += ['printf("batch %zu\\n", sizeof(fwgpu_batch));', "return 0;}"]
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.splitlines())
+    assert int(got["sizeof"]) == ctypes.sizeof(_lib.ModelDesc)
+    for n in c_names:
+        assert int(got[n]) == getattr(_lib.ModelDesc, n).offset, n
+    assert int(got["batch"]) == ctypes.sizeof(_lib.Batch)
