@@ -142,3 +142,54 @@ def test_cli_gz_input_and_lz4_cache(tmp_path):
     shutil.copy(f"{d}/train.vw", f"{d}/train.txt")
     r = subprocess.run([FW] + ns + ["--data", f"{d}/train.txt"], capture_output=True, text=True)
     assert r.returncode != 0 and "Please specify a valid input format (.vw, .zst, .gz)" in r.stderr
+
+
+def test_cli_multi_batch_and_holdout_equal_single_batch(tmp_path):
+    """Inputs larger than --batch_size, and the split --holdout_after causes, feed every mini-batch the right records:
+    in --sequential mode (bit-exact reference semantics) 7 batches of 1000 + a holdout split predict exactly what one batch
+    does (the offsets handed to fwgpu_learn_records are absolute, so the record base must not be shifted)."""
+    d = str(tmp_path)
+    generate(d, n_train=6500, n_eval=10)
+    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 -b 18 --ffm_bit_precision 18 --adaptive --sgd --sequential --holdout_after 4321".split()
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_one.txt", "--batch_size", "100000"])
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_many.txt", "--batch_size", "1000"])
+    assert open(f"{d}/p_one.txt").read() == open(f"{d}/p_many.txt").read()
+    # examples from holdout_after on are scored, not learned: the model is frozen there, so re-scoring that tail with the
+    # saved regressor (-t) gives the same lines
+    run(ns + rest + ["--data", f"{d}/train.vw", "-f", f"{d}/m.fw", "--save_resume", "--batch_size", "1000"])
+    run(ns + ["-i", f"{d}/m.fw", "-t", "--data", f"{d}/train.vw", "-p", f"{d}/p_t.txt"])
+    assert open(f"{d}/p_many.txt").read().splitlines()[4320:] == open(f"{d}/p_t.txt").read().splitlines()[4320:]
+    # Hogwild mode with small batches still learns (this is the path that read misaligned words before)
+    run(ns + rest[:-3] + ["--data", f"{d}/train.vw", "-p", f"{d}/p_h.txt", "--batch_size", "512"])
+    p = np.loadtxt(f"{d}/p_h.txt")
+    assert balanced_accuracy(p[3000:], labels_of(f"{d}/train.vw")[3000:]) > 0.9
+
+
+def test_cli_testonly_save_writes_a_loadable_inference_file(tmp_path):
+    """`-t -i model -f out --save_resume`: the immutable ctx exports weights only, so the file it writes must say SGD
+    (persistence.rs:163-172) -- and must load again and predict identically."""
+    d = str(tmp_path)
+    generate(d, n_train=3000, n_eval=10)
+    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 -b 18 --ffm_bit_precision 18 --adaptive --sgd".split()
+    run(ns + rest + ["--data", f"{d}/train.vw", "-f", f"{d}/full.fw", "--save_resume"])
+    run(ns + ["-i", f"{d}/full.fw", "-t", "--data", f"{d}/train.vw", "-p", f"{d}/p1.txt", "-f", f"{d}/resaved.fw", "--save_resume"])
+    assert os.path.getsize(f"{d}/resaved.fw") < 0.6 * os.path.getsize(f"{d}/full.fw")
+    run(ns + ["-i", f"{d}/resaved.fw", "-t", "--data", f"{d}/train.vw", "-p", f"{d}/p2.txt"])
+    assert open(f"{d}/p1.txt").read() == open(f"{d}/p2.txt").read()
+
+
+def test_cli_prediction_model_delay(tmp_path):
+    """--prediction_model_delay D (main.rs:200-258): example i is scored by a model that has not seen the last D examples.
+    With D >= the file every prediction comes from the initial model; with a small D the model still learns."""
+    d = str(tmp_path)
+    generate(d, n_train=3000, n_eval=10)
+    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 -b 18 --ffm_bit_precision 18 --adaptive --sgd".split()
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_all.txt", "--prediction_model_delay", "5000"])
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_t.txt", "-t"])
+    assert open(f"{d}/p_all.txt").read() == open(f"{d}/p_t.txt").read()
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_50.txt", "--prediction_model_delay", "50"])
+    p = np.loadtxt(f"{d}/p_50.txt")
+    assert len(p) == 3000 and balanced_accuracy(p[1500:], labels_of(f"{d}/train.vw")[1500:]) > 0.85

@@ -106,3 +106,41 @@ def test_file_interchange_with_oracle_tables(tmp_path):
     _, _, re2 = host.new_regressor_from_filename(path, True)
     got = re2.learn_records(recs[:m].reshape(-1), n_examples=m, update=False)
     assert np.max(np.abs(got - want)) <= 1e-5
+
+
+def test_quantized_inference_file_is_dequantized_on_load(tmp_path):
+    """A file written with --weight_quantization (main.rs:140-147, quantization.rs:41-95) stores the FFM block as an 8-byte
+    header {increment, min} and one half-float bucket number per weight; loading it dequantizes (persistence.rs:144-161,
+    block_ffm.rs:853-857) instead of mis-reading the block as f32."""
+    import ctypes as C
+
+    vw = host.VwNamespaceMap.new(VW)
+    mi = ModelInstance.new_empty()
+    mi.learning_rate, mi.power_t, mi.bit_precision = 0.1, 0.0, 10
+    mi.ffm_k, mi.ffm_bit_precision, mi.ffm_power_t, mi.ffm_learning_rate = 2, 10, 0.0, 0.1
+    mi.ffm_fields, mi.optimizer, mi.num_namespaces = [[0], [1]], Optimizer.SGD, 2
+    rng = np.random.default_rng(4)
+    n_lr, n_ffm = 1 << 10, (1 << 10) + 4
+    lr_w = rng.normal(0, 0.1, n_lr).astype(np.float32)
+    w = rng.normal(0, 0.2, n_ffm).astype(np.float32)
+    # quantize_ffm_weights: min/max rounded to 1e-4, 65025 buckets, bucket number stored as f16
+    wmin = np.float32(np.round(w.min() * np.float32(10000.0)) / np.float32(10000.0))
+    wmax = np.float32(np.round(w.max() * np.float32(10000.0)) / np.float32(10000.0))
+    inc = np.float32((wmax - wmin) / np.float32(65025.0))
+    buckets = np.round((w - wmin) / inc).astype(np.float16)
+    payload_ffm = np.concatenate([np.array([inc, wmin], np.float32).view(np.uint8), buckets.view(np.uint8)])
+    j = json.loads(host.model_instance_to_json(mi, vw))
+    j["dequantize_weights"] = True
+    path = str(tmp_path / "q.fw")
+    L = host._L()
+    blocks = [lr_w.view(np.uint8), payload_ffm]
+    ptrs = (C.c_void_p * 2)(*[b.ctypes.data_as(C.c_void_p) for b in blocks])
+    sizes = (C.c_uint64 * 2)(*[b.nbytes for b in blocks])
+    err = C.create_string_buffer(1024)
+    assert L.fwhost_regressor_write(path.encode(), vw.source_json.encode(), json.dumps(j).encode(), n_lr + n_ffm, ptrs, sizes, 2, err, 1024) == 0, err.value
+    _, _, re = host.new_regressor_from_filename(path, immutable=True)
+    got, _ = re.get_ffm()
+    want = (wmin + buckets.astype(np.float32) * inc).astype(np.float32)
+    assert np.array_equal(got, want)
+    assert np.max(np.abs(got - w)) < 0.01            # half-float bucket numbers: coarse above bucket 2048, as in the reference
+    assert np.array_equal(re.get_lr_table()[:, 0], lr_w)

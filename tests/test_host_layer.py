@@ -216,3 +216,34 @@ def test_regressor_file_layout(tmp_path):  # persistence.rs:55-97 (no GPU needed
     back = np.empty(8, np.float32)
     assert L.fwhost_regressor_read(r, back.ctypes.data_as(C.c_void_p), 32) == 0 and np.array_equal(back, lr)
     L.fwhost_regressor_close(r)
+
+
+def test_regressor_reader_reports_optimizer_and_dequantizes(tmp_path):
+    """fwhost_regressor_optimizer / _dequantize come from the parsed ModelInstance (any key order / whitespace), and
+    fwhost_regressor_read_quantized restates quantization.rs:77-95 (half-float bucket numbers incl. subnormals)."""
+    import ctypes as C
+
+    L = host._L()
+    vw = host.VwNamespaceMap.new("A,a\nB,b\n")
+    from fwumious_wabbit_b200 import ModelInstance
+
+    mi = ModelInstance.new_empty()
+    mi.num_namespaces, mi.optimizer = 2, Optimizer.SGD
+    j = json.loads(host.model_instance_to_json(mi, vw))
+    j["dequantize_weights"] = True
+    compact = json.dumps(j, separators=(",", ":"))       # no space after the colon: a substring search would miss "SGD"
+    halves = np.array([0, 1, 2, 1023, 1024, 2049, 40000, 65025, 6e-8, 3e-5], dtype=np.float16)
+    payload = np.concatenate([np.array([0.25, -3.0], np.float32).view(np.uint8), halves.view(np.uint8)])
+    ptrs = (C.c_void_p * 1)(payload.ctypes.data_as(C.c_void_p))
+    sizes = (C.c_uint64 * 1)(payload.nbytes)
+    err = C.create_string_buffer(1024)
+    path = str(tmp_path / "q.fw").encode()
+    assert L.fwhost_regressor_write(path, vw.source_json.encode(), compact.encode(), len(halves), ptrs, sizes, 1, err, 1024) == 0, err.value
+    r = L.fwhost_regressor_open(path, err, 1024)
+    assert r, err.value
+    assert L.fwhost_regressor_optimizer(r) == Optimizer.SGD and L.fwhost_regressor_dequantize(r) == 1
+    out = np.empty(len(halves), np.float32)
+    assert L.fwhost_regressor_read_quantized(r, out.ctypes.data_as(C.c_void_p), len(halves)) == 0
+    L.fwhost_regressor_close(r)
+    want = (np.float32(-3.0) + halves.astype(np.float32) * np.float32(0.25)).astype(np.float32)
+    assert np.array_equal(out, want)
