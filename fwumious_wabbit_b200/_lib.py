@@ -99,6 +99,8 @@ def lib():
     L.fwgpu_get_lut.argtypes = [vp, C.c_int, vp]
     L.fwgpu_debug_logistic.argtypes = [vp, vp, vp, C.c_uint64]
     L.fwgpu_debug_logistic.restype = C.c_int32
+    L.fwgpu_debug_path_counts.argtypes = [vp, vp]
+    L.fwgpu_debug_path_counts.restype = C.c_int32
     L.fwgpu_set_examples_seen.argtypes = [vp, C.c_uint64]
     L.fwgpu_get_examples_seen.argtypes = [vp]
     L.fwgpu_get_examples_seen.restype = C.c_uint64
@@ -122,6 +124,6 @@ EXPORTED_SYMBOLS = [
     "fwgpu_learn_batch", "fwgpu_predict_batch", "fwgpu_learn_records", "fwgpu_translate_records",
     "fwgpu_dataset_upload", "fwgpu_dataset_learn", "fwgpu_dataset_free",
     "fwgpu_block_len", "fwgpu_export_block", "fwgpu_import_block", "fwgpu_get_lut",
-    "fwgpu_set_examples_seen", "fwgpu_get_examples_seen", "fwgpu_debug_logistic",
+    "fwgpu_set_examples_seen", "fwgpu_get_examples_seen", "fwgpu_debug_logistic", "fwgpu_debug_path_counts",
     "fwgpu_set_profiling", "fwgpu_kernel_time", "fwgpu_host_alloc", "fwgpu_host_free", "fwgpu_version",
 ]

@@ -113,6 +113,8 @@ struct fwgpu_ctx {
     int force_T = 0;
     int minb = 4;
     uint64_t launches = 0;
+    uint64_t n_fixed = 0, n_fixed_cta = 0, n_general = 0; // launches per learn-kernel family (fwgpu_debug_path_counts)
+    unsigned long long *stat_general_examples = nullptr;  // device: examples the general kernel handled
     uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
     uint32_t ramp_div = 32;
     uint32_t max_inflight = 0; // 0 = unlimited
@@ -215,6 +217,7 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     for (DevBuf *b : {&c->hX, &c->hdX, &c->h_label, &c->h_imp, &c->h_outidx, &c->h_dy}) if (b->p) cudaFree(b->p);
     for (int i = 0; i < FWGPU_MAX_NN_LAYERS; i++) { if (c->hH[i].p) cudaFree(c->hH[i].p); if (c->hdZ[i].p) cudaFree(c->hdZ[i].p); }
     cudaFree(c->err_flag);
+    cudaFree(c->stat_general_examples);
     if (c->err_host) cudaFreeHost(c->err_host);
     for (int i = 0; i < 2; i++) { if (c->ev_ready[i]) cudaEventDestroy(c->ev_ready[i]); if (c->ev_free[i]) cudaEventDestroy(c->ev_free[i]); }
     for (int i = 0; i < 2; i++) { if (c->ev_pred_ready[i]) cudaEventDestroy(c->ev_pred_ready[i]); if (c->ev_pred_out[i]) cudaEventDestroy(c->ev_pred_out[i]); }
@@ -314,6 +317,8 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     }
     CUDA_TRY(c, cudaMalloc((void **)&c->err_flag, 4));
     CUDA_TRY(c, cudaMemset(c->err_flag, 0, 4));
+    CUDA_TRY(c, cudaMalloc((void **)&c->stat_general_examples, 8));
+    CUDA_TRY(c, cudaMemset(c->stat_general_examples, 0, 8));
     CUDA_TRY(c, cudaHostAlloc((void **)&c->err_host, 4, cudaHostAllocDefault));
     *c->err_host = 0;
 
@@ -618,7 +623,7 @@ template <int T, int VEC, int MINB> static cudaError_t launch_learn_tvm(fwgpu_ct
     if (full_groups) *full_groups = (uint32_t)(c->num_sms * per_sm) * GROUPS;
     if (grid == 0) return cudaSuccess;
     kern<<<grid, 256, smem, c->stream>>>(p);
-    c->launches++;
+    c->launches++; c->n_general++;
     return cudaGetLastError();
 }
 
@@ -656,7 +661,7 @@ static fwgpu_status make_learn_params(fwgpu_ctx *c, uint32_t n_cap, int update, 
     p.div_cpr = make_fastdiv(std::max<uint32_t>(c->cpr, 1)); p.div_k = make_fastdiv(std::max<uint32_t>(c->k, 1)); p.div_F = make_fastdiv(std::max<uint32_t>(c->F, 1));
     p.optimizer = c->optimizer;
     p.lr_lr = c->d.learning_rate; p.lr_mpt = -c->d.power_t; p.ffm_lr = c->d.ffm_learning_rate; p.ffm_mpt = -c->d.ffm_power_t;
-    p.update = update; p.err_flag = c->err_flag;
+    p.update = update; p.err_flag = c->err_flag; p.stat_examples = c->stat_general_examples;
     p.simple_update = 1; // measured on B200 (c3): one chunk at a time with 4 blocks/SM beats rounds of four with 3
     if (const char *t = getenv("FWGPU_SIMPLE_UPDATE")) p.simple_update = atoi(t);
     p.kv = (c->k == 0 || c->k % std::max<uint32_t>(c->VEC, 1) == 0) ? 1 : 0;
@@ -755,7 +760,7 @@ template <int G, int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(f
     *full_groups = (uint32_t)(c->num_sms * per_sm) * per_block;
     if (grid == 0) return cudaSuccess;
     kern<<<grid, NW * 32, smem, c->stream>>>(p);
-    c->launches++;
+    c->launches++; c->n_fixed++;
     return cudaGetLastError();
 }
 
@@ -797,7 +802,7 @@ template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *
     *full_groups = (uint32_t)(c->num_sms * per_sm);
     if (grid == 0) return cudaSuccess;
     kern<<<grid, 256, smem, c->stream>>>(p);
-    c->launches++;
+    c->launches++; c->n_fixed_cta++;
     return cudaGetLastError();
 }
 
@@ -1562,6 +1567,17 @@ extern "C" fwgpu_status fwgpu_debug_logistic(fwgpu_ctx *c, const float *in, floa
     c->launches++;
     CUDA_TRY(c, cudaMemcpyAsync(out, dout, n * 4, cudaMemcpyDeviceToHost, c->stream));
     return fwgpu_sync(c);
+}
+
+extern "C" fwgpu_status fwgpu_debug_path_counts(fwgpu_ctx *c, uint64_t *out4)
+{
+    if (!c || !out4) return FWGPU_ERR_INVALID;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    unsigned long long ex = 0;
+    CUDA_TRY(c, cudaMemcpy(&ex, c->stat_general_examples, 8, cudaMemcpyDeviceToHost));
+    out4[0] = c->n_fixed; out4[1] = c->n_fixed_cta; out4[2] = c->n_general; out4[3] = ex;
+    return FWGPU_OK;
 }
 
 extern "C" fwgpu_status fwgpu_set_examples_seen(fwgpu_ctx *c, uint64_t n)

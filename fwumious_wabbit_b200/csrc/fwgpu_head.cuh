@@ -140,7 +140,9 @@ __global__ void __launch_bounds__(256, (BM * BN > 64 * 128) ? 1 : 2) k_head_gemm
             const size_t o = (size_t)gm * p.ldc + gn;
             if (EPI == HEAD_EPI_BIAS_ACT) {
                 float y = __fadd_rn(p.bias[gn], acc[i][j]);          // output = bias, then sgemv adds W x (block_neural.rs:207-220)
-                if (p.relu && y < 0.0f) y = -0.0f;                   // block_relu.rs:88-97: output 0, mask 0
+                // block_relu.rs:88-97: x < 0 -> output 0, derivative 0 (stored as -0.0f = the mask); anything else passes with
+                // derivative 1 -- including a pre-activation that is exactly -0.0, which is therefore stored as +0.0
+                if (p.relu) y = y < 0.0f ? -0.0f : __fadd_rn(y, 0.0f);
                 p.C[o] = y;
             } else if (EPI == HEAD_EPI_MASK) {
                 float v = acc[i][j];

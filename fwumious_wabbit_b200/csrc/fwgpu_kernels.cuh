@@ -84,6 +84,7 @@ struct LearnParams {
     int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
     int phase;              // 0 = fused single pass; 1 / 2 = the two passes around a dense head (HeadIO)
     HeadIO io;
+    unsigned long long *stat_examples; // += examples this launch handles (fwgpu_debug_path_counts: which kernel did the work)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
     if (gid >= n_groups) return; // whole groups leave; the named barriers below are per group
 
     const uint32_t n_total = p.n_examples_dev ? *p.n_examples_dev : p.n_examples;
+    if (gid == 0 && tg == 0 && p.stat_examples && n_total) atomicAdd(p.stat_examples, (unsigned long long)n_total);
     for (uint32_t ex = gid; ex < n_total; ex += n_groups) {
         const ExMeta m = p.meta[ex];
         const uint32_t n = m.ffm_cnt, nlr = m.lr_cnt;
@@ -826,13 +828,18 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
                 else if (gl != 0.0f) fixed_lr_apply(p, optimizer, lr_h[r], gl, __fmul_rn(gl, gl), lrw[r].y);
             }
         }
+        // One record in flight (hogwild_max_inflight = 1, the setting of the per-example parity tests): REDG is fire-and-forget,
+        // so every lane's reductions are fenced and the group re-converges before the next record's gather may read them.
+        const bool one_in_flight = p.max_groups == 1;
         if (++bias_n >= bias_period) {
             if (bias_lane) {
                 if (bias_G != 0.0f) fixed_lr_apply(p, optimizer, bias_h, bias_G, bias_G2, bias_cell.y);
+                if (one_in_flight) __threadfence();
                 bias_cell = __ldcg(p.lr + bias_h); // consumed a round later
             }
             bias_G = 0.0f; bias_G2 = 0.0f; bias_n = 0;
         }
+        if (one_in_flight) { __threadfence(); __syncwarp(); }
     }
     if (bias_lane && bias_G != 0.0f) fixed_lr_apply(p, optimizer, bias_h, bias_G, bias_G2, bias_cell.y);
 }
@@ -1035,6 +1042,9 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
             }
             atomicAdd(cell, -upd);
         }
+        // one record in flight (per-example parity tests): this record's reductions are visible before the barrier at the
+        // top of the next iteration lets anybody gather
+        if (p.max_groups == 1) __threadfence();
     }
 }
 

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(UMMA_THREADS, 1) k_umma_gemm(const HeadGemmPar
                 if (n + j >= p.N) continue;
                 if (EPI == HEAD_EPI_BIAS_ACT) {
                     v[j] = __fadd_rn(p.bias[n + j], v[j]);
-                    if (p.relu && v[j] < 0.0f) v[j] = -0.0f; // block_relu.rs:88-97: output 0, the sign bit keeps the mask
+                    if (p.relu) v[j] = v[j] < 0.0f ? -0.0f : __fadd_rn(v[j], 0.0f); // block_relu.rs:88-97: output 0, -0.0f is the mask; an exact -0.0 input passes as +0.0
                 } else if (EPI == HEAD_EPI_MASK) {
                     if (p.mask_on && __float_as_uint(p.mask_src[(size_t)row * p.ld_mask + n + j]) == 0x80000000u) v[j] = 0.0f; // block_relu.rs:101-108
                 } else if (EPI == HEAD_EPI_ADD_DIRECT) {

@@ -244,6 +244,12 @@ class Regressor:
         self._check(self.L.fwgpu_kernel_time(self.h, kind, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def path_counts(self):
+        """{fixed, fixed_cta, general: launches per learn-kernel family; general_examples: examples the general kernel handled}."""
+        out = (C.c_uint64 * 4)()
+        self._check(self.L.fwgpu_debug_path_counts(self.h, out))
+        return {"fixed": int(out[0]), "fixed_cta": int(out[1]), "general": int(out[2]), "general_examples": int(out[3])}
+
     def launch_count(self):
         return int(self.L.fwgpu_launch_count(self.h))
 

@@ -10,6 +10,9 @@
 #include <cmath>
 #include <cstdio>
 #include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -73,25 +76,38 @@ extern "C" int fwsynth_records(uint32_t *out, uint64_t n_examples, uint64_t firs
                                     const uint32_t *card, uint64_t seed, int n_threads)
 {
     if (!out || !ns_names || !card || n_ns == 0 || n_ns > 255) return -1;
-    // vocabulary tables: hash of "<ns><id>" seeded with hash(ns) (parser.rs:82-83, 382-385), 31 bits
-    std::vector<std::vector<uint32_t>> vocab(n_ns);
+    // vocabulary tables: hash of "<ns><id>" seeded with hash(ns) (parser.rs:82-83, 382-385), 31 bits.  Built once per
+    // (namespace letter, cardinality) and kept for the life of the process: bench.py asks for many slices of one stream.
+    static std::mutex cache_mu;
+    static std::map<std::pair<char, uint32_t>, std::shared_ptr<std::vector<uint32_t>>> cache;
+    std::vector<std::shared_ptr<std::vector<uint32_t>>> vocab(n_ns);
     unsigned hw = std::thread::hardware_concurrency();
     int nt = n_threads > 0 ? n_threads : (int)(hw ? hw : 1);
-    auto fill_vocab = [&](uint32_t j) {
-        uint32_t ns_seed = fwhost::murmur3_32(&ns_names[j], 1, 0);
-        vocab[j].resize(card[j]);
-        char buf[16];
-        for (uint32_t id = 0; id < card[j]; id++) {
-            int len = feature_name(buf, ns_names[j], id);
-            vocab[j][id] = fwhost::murmur3_32(buf, (size_t)len, ns_seed) & 0x7fffffffu;
-        }
-    };
     {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        std::vector<uint32_t> todo;
+        for (uint32_t j = 0; j < n_ns; j++) {
+            auto it = cache.find({ns_names[j], card[j]});
+            if (it != cache.end()) vocab[j] = it->second;
+            else { vocab[j] = std::make_shared<std::vector<uint32_t>>(card[j]); todo.push_back(j); }
+        }
+        // one namespace = many ids: split every table over the threads (a few namespaces hold 1e7 ids)
         std::vector<std::thread> th;
-        std::atomic_uint next{0};
         for (int t = 0; t < nt; t++)
-            th.emplace_back([&] { for (uint32_t j; (j = next++) < n_ns;) fill_vocab(j); });
+            th.emplace_back([&, t] {
+                char buf[16];
+                for (uint32_t j : todo) {
+                    const uint32_t ns_seed = fwhost::murmur3_32(&ns_names[j], 1, 0);
+                    std::vector<uint32_t> &v = *vocab[j];
+                    const uint64_t per = (card[j] + nt - 1) / nt, a = std::min<uint64_t>(card[j], per * t), b = std::min<uint64_t>(card[j], a + per);
+                    for (uint64_t id = a; id < b; id++) {
+                        int len = feature_name(buf, ns_names[j], (uint32_t)id);
+                        v[id] = fwhost::murmur3_32(buf, (size_t)len, ns_seed) & 0x7fffffffu;
+                    }
+                }
+            });
         for (auto &t : th) t.join();
+        for (uint32_t j : todo) cache[{ns_names[j], card[j]}] = vocab[j];
     }
     const uint32_t rec_len = 3 + n_ns;
     const uint32_t one_bits = 0x3f800000u;
@@ -102,7 +118,7 @@ extern "C" int fwsynth_records(uint32_t *out, uint64_t n_examples, uint64_t firs
             draw_ids(seed, first_example + e, n_ns, card, ids.data(), &label);
             uint32_t *r = out + e * rec_len;
             r[0] = rec_len; r[1] = label; r[2] = one_bits;
-            for (uint32_t j = 0; j < n_ns; j++) r[3 + j] = vocab[j][ids[j]];
+            for (uint32_t j = 0; j < n_ns; j++) r[3 + j] = (*vocab[j])[ids[j]];
         }
     };
     std::vector<std::thread> th;

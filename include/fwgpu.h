@@ -211,6 +211,11 @@ fwgpu_status fwgpu_get_lut(const fwgpu_ctx *ctx, int which, float *dst2048);
 fwgpu_status fwgpu_set_profiling(fwgpu_ctx *ctx, int enabled);
 fwgpu_status fwgpu_kernel_time(fwgpu_ctx *ctx, int kind, double *total_ms, uint64_t *launches);
 
+/* Which kernel family did the work so far (tests assert that the kernels the bench times are the ones under test):
+ * out4 = { launches of the warp-per-record fused kernel (k_learn_fixed), launches of the block-per-record fused kernel
+ * (k_learn_fixed_cta), launches of the general kernel (k_learn), examples the general kernel processed }.  Synchronous. */
+fwgpu_status fwgpu_debug_path_counts(fwgpu_ctx *ctx, uint64_t *out4);
+
 /* Debug/verification: out[i] = logistic(in[i]) computed by the device routine the kernels use
  * (block_loss_functions.rs:15-17 with glibc-exact expf).  Host pointers, synchronous. */
 fwgpu_status fwgpu_debug_logistic(fwgpu_ctx *ctx, const float *in, float *out, uint64_t n);

@@ -1255,3 +1255,148 @@ void fwo_learn_records_wave(fwo_regressor *r, const fwo_translate_spec *spec, co
     free(gsum_ffm); free(g2_ffm); free(gsum_lr); free(g2_lr); free(touched);
     (void)F; (void)k;
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Head wave emulation (test tool, no reference counterpart): the batched semantics the device
+ * gives a model with a dense head.  A sub-batch of `wave` examples is scored against ONE weight
+ * snapshot; the dense layers then receive, per weight, G1 = sum_b g_bj x_bi and
+ * G2 = sum_b (g_bj x_bi)^2 computed from the pre-update weights (block_neural.rs:266-305 per
+ * example, summed), one optimizer step  acc += G2 ; w -= step(G1, acc);  the sparse LR / FFM
+ * tables are updated example after example from the gradients the head's backward pass left
+ * for each input (block_ffm.rs:265-288, block_lr.rs:135-151), using the local gradients of the
+ * snapshot forward.  With wave == 1 this is fwo_learn, arithmetic included.
+ * ---------------------------------------------------------------------------------------- */
+void fwo_learn_records_head_wave(fwo_regressor *r, const fwo_translate_spec *spec, const uint32_t *records,
+                                 const uint64_t *rec_off, uint64_t n_records, uint32_t wave, float *preds)
+{
+    if (r->n_layers == 0 || wave == 0) return;
+    const uint32_t F = r->F, k = r->k, Fk = r->Fk, nl = r->n_layers;
+    const uint32_t cap = 4096;
+    const uint32_t n_lr_out = r->d.num_combos;
+    const uint32_t x_len = n_lr_out + (r->d.ffm_k > 0 ? F * (F + 1) / 2 : 0);
+    fwo_lr_feat *lr = (fwo_lr_feat *)malloc(sizeof(fwo_lr_feat) * cap * (size_t)wave);
+    fwo_ffm_feat *ffm = (fwo_ffm_feat *)malloc(sizeof(fwo_ffm_feat) * cap * (size_t)wave);
+    uint32_t *n_lr = (uint32_t *)malloc(4 * (size_t)wave), *n_ffm = (uint32_t *)malloc(4 * (size_t)wave);
+    float *gs = (float *)malloc(4 * (size_t)wave);
+    float *DX = (float *)malloc(4 * (size_t)wave * x_len);
+    float *loc = (float *)malloc(4 * (size_t)wave * F * Fk + 16);
+    float *in_s[FWO_MAX_NN_LAYERS + 1], *mask_s[FWO_MAX_NN_LAYERS + 1], *G1[FWO_MAX_NN_LAYERS + 1], *G2[FWO_MAX_NN_LAYERS + 1], *err[FWO_MAX_NN_LAYERS + 1];
+    for (uint32_t l = 0; l < nl; l++) {
+        nn_layer *L = &r->layers[l];
+        size_t np = (size_t)(L->n_in + 1) * L->n_out;
+        in_s[l] = (float *)malloc(4 * (size_t)wave * L->n_in);
+        mask_s[l] = (float *)malloc(4 * (size_t)wave * L->n_out);
+        G1[l] = (float *)calloc(np, 4); G2[l] = (float *)calloc(np, 4);
+        err[l] = (float *)malloc(4 * ((size_t)L->n_in + 1));
+    }
+    uint32_t m = 0;
+    for (uint64_t a = 0; a < n_records; a += m) {
+        m = (uint32_t)((a + wave <= n_records) ? wave : n_records - a);
+        /* phase 1: forward of every example on the snapshot */
+        for (uint32_t i = 0; i < m; i++) {
+            fwo_feature_buffer fb;
+            fb.lr = lr + (size_t)i * cap; fb.ffm = ffm + (size_t)i * cap;
+            if (fwo_translate(spec, records + rec_off[a + i], (fwo_lr_feat *)fb.lr, cap, &n_lr[i], (fwo_ffm_feat *)fb.ffm, cap, &n_ffm[i], &fb.label, &fb.example_importance) != 0) n_lr[i] = n_ffm[i] = 0;
+            if (n_ffm[i] > F) { n_ffm[i] = 0; n_lr[i] = 0; } /* the tool covers single-valued fields (the fused device path) */
+            fb.example_number = a + i; fb.n_lr = n_lr[i]; fb.n_ffm = n_ffm[i];
+            float p = fwo_forward_backward(r, &fb, 0);
+            if (preds) preds[a + i] = p;
+            float g;
+            { /* the sigmoid block's gradient for this example, from the final neuron's output */
+                float y = r->layers[nl - 1].out[0];
+                (void)sigmoid_block(&y, 1, fb.label, fb.example_importance, &g);
+                if (fb.example_importance == 0.0f) g = 0.0f; /* regressor.rs:366-370 */
+            }
+            gs[i] = g;
+            memcpy(loc + (size_t)i * F * Fk, tls_scratch.local, 4 * (size_t)n_ffm[i] * Fk);
+            for (uint32_t l = 0; l < nl; l++) {
+                nn_layer *L = &r->layers[l];
+                memcpy(in_s[l] + (size_t)i * L->n_in, L->in, 4 * (size_t)L->n_in);
+                memcpy(mask_s[l] + (size_t)i * L->n_out, L->mask, 4 * (size_t)L->n_out);
+            }
+        }
+        /* phase 2: dense backward of every example on the snapshot, gradient sums per weight */
+        for (uint32_t i = 0; i < m; i++) {
+            float *dx = DX + (size_t)i * x_len;
+            float g = gs[i];
+            if (g == 0.0f) { for (uint32_t t = 0; t < x_len; t++) dx[t] = 0.0f; continue; }
+            const float *up = &g;
+            const float *direct = NULL;
+            for (int l = (int)nl - 1; l >= 0; l--) {
+                nn_layer *L = &r->layers[l];
+                const float *in = in_s[l] + (size_t)i * L->n_in;
+                float *oe = err[l];
+                size_t bias_offset = (size_t)L->n_in * L->n_out;
+                for (uint32_t t = 0; t < L->n_in; t++) oe[t] = 0.0f;
+                for (uint32_t j = 0; j < L->n_out; j++) {
+                    float gg = up[j];
+                    if (gg == 0.0f) continue;
+                    size_t jo = (size_t)j * L->n_in;
+                    for (uint32_t t = 0; t < L->n_in; t++) {
+                        float gradient = gg * in[t];
+                        G1[l][jo + t] += gradient; G2[l][jo + t] += gradient * gradient;
+                        oe[t] += L->w[jo + t] * gg;
+                    }
+                    G1[l][bias_offset + j] += gg; G2[l][bias_offset + j] += gg * gg;
+                }
+                if (l == (int)nl - 1) direct = oe + (L->n_in - x_len); /* final neuron's inputs are [h, x] */
+                if (l > 0) {
+                    nn_layer *P = &r->layers[l - 1];
+                    const float *pm = mask_s[l - 1] + (size_t)i * P->n_out;
+                    for (uint32_t t = 0; t < P->n_out; t++) oe[t] = pm[t] * oe[t]; /* block_relu.rs:101-108 */
+                    up = oe;
+                } else {
+                    for (uint32_t t = 0; t < x_len; t++) dx[t] = oe[t] + direct[t]; /* block_misc.rs:452-473 */
+                }
+            }
+        }
+        /* phase 3: one optimizer step per dense weight */
+        for (uint32_t l = 0; l < nl; l++) {
+            nn_layer *L = &r->layers[l];
+            size_t np = (size_t)(L->n_in + 1) * L->n_out;
+            for (size_t t = 0; t < np; t++) {
+                float g1 = G1[l][t], g2 = G2[l][t];
+                if (g1 == 0.0f && g2 == 0.0f) continue;
+                G1[l][t] = 0.0f; G2[l][t] = 0.0f;
+                float step;
+                if (r->opt_nn.kind == FWO_OPT_SGD) step = g1 * r->opt_nn.lr;
+                else {
+                    float new_acc = L->acc[t] + g2;
+                    L->acc[t] = new_acc;
+                    if (r->opt_nn.kind == FWO_OPT_ADAGRAD_LUT) step = g1 * r->opt_nn.lut[f2bits(new_acc) >> 20];
+                    else { step = g1 * r->opt_nn.lr * powf(new_acc, r->opt_nn.minus_power_t); if (isnan(step) || isinf(step)) step = 0.0f; }
+                }
+                L->w[t] -= step;
+            }
+        }
+        /* phase 4: sparse tables, example after example */
+        for (uint32_t i = 0; i < m; i++) {
+            if (gs[i] == 0.0f) continue;
+            const float *dx = DX + (size_t)i * x_len;
+            const float *G = loc + (size_t)i * F * Fk;
+            const fwo_ffm_feat *fe = ffm + (size_t)i * cap;
+            size_t li = 0;
+            for (uint32_t e = 0; e < n_ffm[i]; e++) {
+                size_t fi = fe[e].hash;
+                uint32_t f = fe[e].contra_field_index / k;
+                for (uint32_t z = 0; z < F; z++) {
+                    uint32_t hi = f > z ? f : z, lo = f > z ? z : f;
+                    float general_gradient = dx[n_lr_out + hi * (hi + 1) / 2 + lo]; /* block_misc.rs:814-833 */
+                    for (uint32_t q = 0; q < k; q++) {
+                        float gradient = general_gradient * G[li];
+                        float upd = opt_update(&r->opt_ffm, gradient, &r->ffm_acc[fi]);
+                        r->ffm_w[fi] -= upd;
+                        li++; fi++;
+                    }
+                }
+            }
+            for (uint32_t e = 0; e < n_lr[i]; e++) {
+                const fwo_lr_feat *f = &lr[(size_t)i * cap + e];
+                float upd = opt_update(&r->opt_lr, dx[f->combo_index] * f->value, &r->lr[f->hash].acc);
+                r->lr[f->hash].w -= upd;
+            }
+        }
+    }
+    for (uint32_t l = 0; l < nl; l++) { free(in_s[l]); free(mask_s[l]); free(G1[l]); free(G2[l]); free(err[l]); }
+    free(lr); free(ffm); free(n_lr); free(n_ffm); free(gs); free(DX); free(loc);
+}

@@ -185,6 +185,10 @@ double fwo_hogwild_run(fwo_regressor *r, const fwo_translate_spec *spec, const u
  * mode 1 = per-slot aggregated update).  See fw_oracle.c. */
 void fwo_learn_records_wave(fwo_regressor *r, const fwo_translate_spec *spec, const uint32_t *records,
                             const uint64_t *rec_off, uint64_t n_records, uint32_t wave, int mode, float *preds);
+/* Test tool: batched semantics of a model with a dense head (sub-batch of `wave` examples against one snapshot; dense layers
+ * take summed gradients G1 / G2, sparse tables are updated example by example).  wave == 1 is fwo_learn. */
+void fwo_learn_records_head_wave(fwo_regressor *r, const fwo_translate_spec *spec, const uint32_t *records,
+                                 const uint64_t *rec_off, uint64_t n_records, uint32_t wave, float *preds);
 
 #ifdef __cplusplus
 }

@@ -163,6 +163,9 @@ def lib():
     L.fwo_learn_records_wave.argtypes = [C.c_void_p, C.POINTER(TranslateSpec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                          C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_float)]
     L.fwo_learn_records_wave.restype = None
+    L.fwo_learn_records_head_wave.argtypes = [C.c_void_p, C.POINTER(TranslateSpec), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                              C.c_uint64, C.c_uint32, C.POINTER(C.c_float)]
+    L.fwo_learn_records_head_wave.restype = None
     _lib = L
     return L
 
@@ -394,6 +397,16 @@ class Regressor:
         preds = np.zeros(n, dtype=np.float32)
         lib().fwo_learn_records_wave(self.h, C.byref(spec.c), _u32p(records), rec_off.ctypes.data_as(C.POINTER(C.c_uint64)),
                                      n, wave, mode, _f32p(preds))
+        return preds
+
+    def learn_head_wave(self, spec, records, rec_off, wave):
+        """Test tool: the device's batched semantics for a model with a dense head (see fwo_learn_records_head_wave)."""
+        records = np.ascontiguousarray(records, dtype=np.uint32)
+        rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+        n = rec_off.shape[0] - 1
+        preds = np.zeros(n, dtype=np.float32)
+        lib().fwo_learn_records_head_wave(self.h, C.byref(spec.c), _u32p(records), rec_off.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                          n, wave, _f32p(preds))
         return preds
 
     def hogwild(self, spec, records, rec_off, n_threads, want_preds=False):

@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_reference_arm_prints_one_json_line_with_the_contract_keys():
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--examples", "50000", "--steps", "1", "--warmup", "1"],
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--examples", "20000", "--steps", "1", "--warmup", "1"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -18,7 +18,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "examples/s" and d["higher_is_better"] is True and d["value"] > 0
     assert d["metric"] == "examples/sec FFM training" and d["n_gpus"] == 1 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["config"]["workload"].startswith("c2:") and d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert d["config"]["workload"].startswith("c3:") and d["dtype"] == "f32" and d["data"] == "synthetic" and d["vs_baseline"] is None
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "examples per step" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": "examples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}

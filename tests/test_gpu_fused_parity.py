@@ -1,0 +1,201 @@
+"""The kernels bench.py times, pinned to the oracle in UPDATE mode (run on the B200 box: pytest -m gpu).
+
+test_gpu_parity.py's bit-exact sequential tests run the general kernel (k_learn, exact_order); the throughput numbers come
+from the fused kernels -- k_learn_fixed<16,4,1,LUT> on c2, k_learn_fixed_cta on c3 / c4, its two-phase form plus the tcgen05
+head GEMMs on c5.  Here those kernels run with ONE record in flight (hogwild_max_inflight = 1: the reference's sequential
+semantics, block_ffm.rs:265-288 / block_lr.rs:135-151) and every prediction and the final tables are compared with the
+oracle; then at full concurrency against the oracle's logloss on full-shape streams (SURVEY 8d parity gates)."""
+import numpy as np
+import pytest
+
+import fwumious_wabbit_b200 as fw
+from fwumious_wabbit_b200 import _lib, synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def _oracle_run(w, recs, threads=1):
+    n = recs.shape[0]
+    ora = util.oracle_regressor(w.mi)
+    rec_off = np.arange(n + 1, dtype=np.uint64) * w.record_len
+    _, want = ora.hogwild(util.oracle_spec(w.mi), recs.reshape(-1), rec_off, threads, want_preds=True)
+    return ora, want
+
+
+def _table_report(name, got, want, atol):
+    d = np.abs(got.astype(np.float64) - want.astype(np.float64))
+    bad = int(np.count_nonzero(d > atol))
+    return f"{name}: max |d| {d.max():.3e}, entries over {atol:g}: {bad} of {d.size}", d.max(), bad
+
+
+@pytest.mark.parametrize("name,n,kernel", [("c2", 10_000, "fixed"), ("c3", 2_000, "fixed_cta")])
+def test_fused_kernel_one_in_flight_matches_oracle(name, n, kernel):
+    """c2 through k_learn_fixed<16,4,1,LUT> and c3 through k_learn_fixed_cta<2,0>, update = 1, one record in flight:
+    per-example |dp| <= 1e-5 against the sequential oracle over the whole stream (every prediction depends on all earlier
+    updates, so a wrong sign or a wrong pair in any field's update shows up within a few hundred records), and the final
+    weight / accumulator tables agree.  The fused kernels sum the forward in a different order than the reference's tape
+    (shuffle tree), so this tier is 1e-5, not bit-exact; the step function of AdagradLUT may put a handful of accumulators
+    that sit on a bucket edge into the neighbouring bucket (a 6 % change of ONE step), hence the two-level table check."""
+    w = synth.workload(name)
+    w.mi.hogwild_max_inflight = 1
+    recs = w.records(n)
+    ora, want = _oracle_run(w, recs)
+    re = fw.Regressor(w.mi)
+    got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    counts = re.path_counts()
+    assert counts[kernel] > 0 and counts["general_examples"] == 0, counts   # the fused kernel did all of it
+    err = float(np.max(np.abs(got - want)))
+    assert err <= TOL, err
+    wts, acc = re.get_ffm()
+    lr = re.get_lr_table()
+    msgs = []
+    for nm, g, o, atol in (("ffm_w", wts, ora.ffm_weights, 2e-6), ("lr_w", lr[:, 0], ora.lr_table[:, 0], 2e-6)):
+        msg, mx, bad = _table_report(nm, g, o, atol)
+        msgs.append(msg)
+        assert mx <= 2e-4 and bad <= max(8, g.size // 100_000), msg
+    np.testing.assert_allclose(acc, ora.ffm_acc, rtol=2e-5, atol=1e-9)
+    np.testing.assert_allclose(lr[:, 1], ora.lr_table[:, 1], rtol=2e-5, atol=1e-9)
+    # exactly the same cells were touched
+    assert np.array_equal(acc != 0.0, ora.ffm_acc != 0.0)
+    print("; ".join(msgs))
+
+
+def test_fused_cta_phases_one_in_flight_match_oracle(monkeypatch):
+    """The two-phase form of the block-per-record kernel (PHASE 1 forward -> head -> PHASE 2 update) on the full c5 shape,
+    one example per sub-batch: predictions within 1e-5 of the sequential oracle over 300 examples, tables close."""
+    w = synth.workload("c5")
+    w.mi.hogwild_max_inflight = 1
+    n = 300
+    recs = w.records(n)
+    ora, want = _oracle_run(w, recs)
+    re = fw.Regressor(w.mi)
+    util.sync_tables_from_oracle(re, util.oracle_regressor(w.mi))   # identical dense init on both sides
+    re.set_examples_seen(0)
+    got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    assert re.path_counts()["fixed_cta"] > 0
+    assert float(np.max(np.abs(got - want))) <= TOL
+    msg, mx, bad = _table_report("ffm_w", re.get_ffm()[0], ora.ffm_weights, 2e-6)
+    assert mx <= 2e-4 and bad <= 8, msg
+
+
+# ------------------------------------------------------------------ full-shape Hogwild gates
+@pytest.mark.parametrize("name,n,tol", [("c2", 10_000_000, 0.01), ("c3", 100_000, 0.01)])
+def test_full_shape_hogwild_logloss_gate(name, n, tol):
+    """Default mode (thousands of records in flight, concurrency ramp) on the full BASELINE shapes: progressive logloss
+    within 1 % (relative) of the sequential oracle on the same stream -- c2 on 10^7 examples, c3 on 10^5.
+    One fwgpu_learn_records call per stream, i.e. the chunking and ramp the bench uses."""
+    w = synth.workload(name)
+    recs = w.records(n)
+    _, want = _oracle_run(w, recs)
+    re = fw.Regressor(w.mi)
+    got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    counts = re.path_counts()
+    assert counts["fixed" if name == "c2" else "fixed_cta"] > 0 and counts["general_examples"] == 0, counts
+    labels = recs[:, 1].astype(np.float32)
+    ll_o, ll_g = util.logloss(want, labels), util.logloss(got, labels)
+    prior = util.logloss(np.full(n, labels.mean()), labels)
+    assert ll_o < prior and ll_g < prior, (ll_o, ll_g, prior)
+    assert abs(ll_g - ll_o) / ll_o < tol, (ll_g, ll_o)
+    # the second half alone (a trained model under full concurrency)
+    h = n // 2
+    assert abs(util.logloss(got[h:], labels[h:]) - util.logloss(want[h:], labels[h:])) / util.logloss(want[h:], labels[h:]) < tol
+
+
+def _small_c5(n_ns=10, k=4):
+    w = synth.Workload("c5s", synth._mi(n_ns, ffm_k=k, ffm_bits=14, bits=14, lr=0.05, ffm_lr=0.02, ffm_init_acc=0.1),
+                       synth.NS_LETTERS[:n_ns], [50] * 4 + [2000] * (n_ns - 4), "scaled-down c5")
+    w.mi.nn_layers = [{"width": "32", "activation": "relu"}, {"width": "32", "activation": "relu"}]
+    w.mi.nn_learning_rate, w.mi.nn_power_t, w.mi.nn_init_acc_gradient = 0.02, 0.5, 0.1
+    return w
+
+
+@pytest.mark.parametrize("shape", ["small", "c5"])
+def test_head_umma_subbatch_matches_batched_oracle(shape, monkeypatch):
+    """The tensor-core head path (sub-batches >= 512 rows: tcgen05 3xTF32 GEMMs, fused epilogues, summed-gradient optimizer
+    step) against the oracle's batched-head semantics (fwo_learn_records_head_wave) at the SAME fixed sub-batch of 1024:
+    every example of the first sub-batch sees the same snapshot on both sides -> per-example |dp| <= 2e-5 and the dense
+    weights after the first step agree; over the whole stream the sparse updates of a sub-batch land in a different order
+    (and PHASE 2 re-reads rows other examples are updating), so later predictions are compared statistically."""
+    monkeypatch.setenv("FWGPU_HEAD_BATCH", "1024")
+    w = _small_c5() if shape == "small" else synth.workload("c5")
+    w.mi.hogwild_ramp_div = 0xFFFFFFFF          # no concurrency ramp: every sub-batch is 1024 rows from the first example
+    n = 1024
+    recs = w.records(8 * n)
+    spec = util.oracle_spec(w.mi)
+    rec_off = np.arange(n + 1, dtype=np.uint64) * w.record_len
+    ora = util.oracle_regressor(w.mi)
+    re = fw.Regressor(w.mi)
+    util.sync_tables_from_oracle(re, ora)
+    re.set_examples_seen(0)
+    want = ora.learn_head_wave(spec, recs[:n].reshape(-1), rec_off, n)
+    got = re.learn_records(recs[:n].reshape(-1), n_examples=n, update=True)
+    err = float(np.max(np.abs(got - want)))
+    assert err <= 2e-5, err
+    for l in range(re.nn_layer_count()):
+        gw, ga = re.get_nn(l)
+        msg, mx, bad = _table_report(f"nn{l}_w", gw, ora.nn_weights(l), 5e-6)
+        assert mx <= 5e-4 and bad <= max(4, gw.size // 2000), msg      # LUT bucket edges: a handful of weights take a 6 % different step
+        np.testing.assert_allclose(ga, ora.nn_acc(l), rtol=1e-3, atol=1e-7)
+    # the whole stream, statistically: 8 sub-batches
+    rec_off8 = np.arange(8 * n + 1, dtype=np.uint64) * w.record_len
+    ora2, re2 = util.oracle_regressor(w.mi), fw.Regressor(w.mi)
+    util.sync_tables_from_oracle(re2, ora2)
+    re2.set_examples_seen(0)
+    want8 = ora2.learn_head_wave(spec, recs.reshape(-1), rec_off8, n)
+    got8 = re2.learn_records(recs.reshape(-1), n_examples=8 * n, update=True)
+    labels = (recs[:, 1] == 1).astype(np.float32)
+    ll_o, ll_g = util.logloss(want8, labels), util.logloss(got8, labels)
+    assert abs(ll_g - ll_o) / ll_o < 0.01, (ll_g, ll_o)
+    print(f"first sub-batch max |dp| {err:.2e}; stream max |dp| {float(np.max(np.abs(got8 - want8))):.2e}; logloss {ll_g:.5f} vs {ll_o:.5f}")
+
+
+def test_c5_full_shape_hogwild_logloss_gate(monkeypatch):
+    """Full c5 shape, 2*10^4 examples, tensor-core head path forced from the first sub-batch of 1024 (no ramp): progressive
+    logloss within 1 % of the batched oracle at the same sub-batch size, and within 3 % of the sequential oracle."""
+    monkeypatch.setenv("FWGPU_HEAD_BATCH", "1024")
+    w = synth.workload("c5")
+    w.mi.hogwild_ramp_div = 0xFFFFFFFF
+    n = 20_000
+    recs = w.records(n)
+    spec = util.oracle_spec(w.mi)
+    rec_off = np.arange(n + 1, dtype=np.uint64) * w.record_len
+    ora = util.oracle_regressor(w.mi)
+    re = fw.Regressor(w.mi)
+    util.sync_tables_from_oracle(re, ora)
+    re.set_examples_seen(0)
+    want = ora.learn_head_wave(spec, recs.reshape(-1), rec_off, 1024)
+    got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
+    labels = (recs[:, 1] == 1).astype(np.float32)
+    ll_o, ll_g = util.logloss(want, labels), util.logloss(got, labels)
+    assert abs(ll_g - ll_o) / ll_o < 0.01, (ll_g, ll_o)
+    _, seq = _oracle_run(w, recs)
+    assert abs(ll_g - util.logloss(seq, labels)) / util.logloss(seq, labels) < 0.03
+
+
+def test_translate_f32_namespace_bit_exact():
+    """A namespace declared f32 (vwmap.rs:16-20, feature_buffer.rs:48-108): its dynamic pairs hold parsed floats and translate
+    emits value 1.0 -- stream of records with f32 and categorical namespaces, translated on the device, u32-equal to the
+    oracle's translate."""
+    from fwumious_wabbit_b200 import ModelInstance, Optimizer
+    from tests.test_gpu_parity import _random_records
+
+    rng = np.random.default_rng(21)
+    n_ns = 6
+    mi = ModelInstance.new_empty()
+    mi.bit_precision, mi.ffm_k, mi.ffm_bit_precision, mi.optimizer = 20, 4, 19, Optimizer.AdagradLUT
+    mi.feature_combo_descs = [([0], 1.0), ([1], 2.0), ([2, 3], 1.0), ([4, 5, 0], 0.5), ([5], 1.0)]
+    mi.ffm_fields, mi.num_namespaces = [[0], [1, 2], [3], [4, 5]], n_ns
+    mi.ns_is_f32 = [0, 1, 0, 1, 0, 0]
+    mi.max_ffm_per_example, mi.max_lr_per_example = 64, 128
+    recs, offs = _random_records(rng, 500, n_ns, multi=True)
+    re = fw.Regressor(mi)
+    got = re.translate_records(recs, rec_off=offs)
+    want = util.oracle_translate_batch(util.oracle_spec(mi), recs, rec_off=offs.astype(np.uint64))
+    for key in ("lr_off", "lr_hash", "lr_combo", "ffm_off", "ffm_hash", "ffm_field"):
+        assert np.array_equal(getattr(got, key), want[key]), key
+    for key in ("labels", "importance", "lr_val", "ffm_val"):
+        assert np.array_equal(getattr(got, key).view(np.uint32), want[key].view(np.uint32)), key
+    # an f32 namespace really took the value-1.0 branch somewhere
+    assert np.any(want["ffm_val"] == 1.0) and np.any(want["ffm_val"] != 1.0)

@@ -525,3 +525,36 @@ def test_merand48_range_and_determinism():
     assert all(0.0 <= x < 1.0 for x in xs)
     assert len(set(xs)) > 990
     assert abs(np.mean(xs) - 0.5) < 0.05
+
+
+def test_head_wave_tool_with_one_example_in_flight_is_the_sequential_learner():
+    """fwo_learn_records_head_wave (the batched-head semantics the device is compared with) collapses to fwo_learn when the
+    sub-batch is one example: same predictions and the same tables, bit for bit -- which pins the tool's dense backward,
+    triangle backward and sparse update to the restated reference arithmetic."""
+    from fwumious_wabbit_b200 import synth
+    from tests import util
+
+    n_ns, k = 6, 4
+    w = synth.Workload("c5t", synth._mi(n_ns, ffm_k=k, ffm_bits=12, bits=12, lr=0.05, ffm_lr=0.02, ffm_init_acc=0.1),
+                       synth.NS_LETTERS[:n_ns], [30] * n_ns, "tiny head model")
+    w.mi.nn_layers = [{"width": "8", "activation": "relu"}, {"width": "5", "activation": "relu"}]
+    w.mi.nn_learning_rate, w.mi.nn_power_t, w.mi.nn_init_acc_gradient = 0.02, 0.5, 0.1
+    n = 400
+    recs = w.records(n)
+    recs[::7, 2] = np.float32(0.0).view(np.uint32)      # importance 0: scored, not learned
+    recs[5::11, 3 + 2] = 0x80000000                      # an absent namespace
+    spec = util.oracle_spec(w.mi)
+    rec_off = np.arange(n + 1, dtype=np.uint64) * w.record_len
+    a, b = util.oracle_regressor(w.mi), util.oracle_regressor(w.mi)
+    _, want = a.hogwild(spec, recs.reshape(-1), rec_off, 1, want_preds=True)
+    got = b.learn_head_wave(spec, recs.reshape(-1), rec_off, 1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(a.ffm_weights.view(np.uint32), b.ffm_weights.view(np.uint32))
+    assert np.array_equal(a.lr_table.view(np.uint32), b.lr_table.view(np.uint32))
+    for l in range(a.nn_layer_count):
+        assert np.array_equal(a.nn_weights(l).view(np.uint32), b.nn_weights(l).view(np.uint32))
+        assert np.array_equal(a.nn_acc(l).view(np.uint32), b.nn_acc(l).view(np.uint32))
+    # a real sub-batch differs (staleness) but stays close and still learns
+    c = util.oracle_regressor(w.mi)
+    p64 = c.learn_head_wave(spec, recs.reshape(-1), rec_off, 64)
+    assert np.all(np.isfinite(p64)) and np.max(np.abs(p64[:64] - want[:1])) < 1.0
