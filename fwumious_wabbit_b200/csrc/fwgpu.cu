@@ -105,6 +105,7 @@ struct fwgpu_ctx {
     bool fast_enabled = true; // FWGPU_FAST=0 turns the fused kernel off (measurement / debugging)
     bool fast_g16 = true;     // narrow models: two records per warp (FWGPU_G16=0: always one)
     bool fast_cta = false;    // wide model: one block per record (k_learn_fixed_cta) instead of one warp
+    bool fast_rows = false;   // ... through k_learn_rows (bulk-copy gather / bulk-reduce scatter) when weights + accumulators of a record fit in shared memory
     int fast_ub = 2;
     uint32_t *err_flag = nullptr;
     uint32_t *err_host = nullptr; // pinned
@@ -456,6 +457,14 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
             c->fast_cta = c->F > 0 && c->F <= 256 && n_lr_max <= 256 && smem_need * 2 <= c->smem_optin;
             ok = c->fast_cta;
         }
+        if (c->fast_cta) {
+            // k_learn_rows: weight AND accumulator rows of one record in shared memory, pair units held in registers
+            const uint32_t k4 = c->k / 4, lpp = (k4 == 1 || k4 == 2 || k4 == 4) ? k4 : 1;
+            const size_t n_units = (size_t)c->F * (c->F - 1) / 2 * lpp;
+            const size_t smem_rows = (size_t)2 * c->F * c->Fk * 4 + 2048 * 4 + (size_t)((c->F + 3) & ~3u) * 4 + 64;
+            c->fast_rows = c->F >= 2 && n_units <= (size_t)ROWS_MAXU * 256 && smem_rows <= c->smem_optin;
+            if (const char *t = getenv("FWGPU_ROWS")) c->fast_rows = c->fast_rows && atoi(t) != 0;
+        }
         if (const char *t = getenv("FWGPU_UB")) c->fast_ub = atoi(t);
         c->fast_ok = ok;
         if (const char *t = getenv("FWGPU_G16")) c->fast_g16 = atoi(t) != 0;
@@ -806,6 +815,54 @@ template <int UB, int PHASE = 0> static cudaError_t launch_fixed_cta(fwgpu_ctx *
     return cudaGetLastError();
 }
 
+// k_learn_rows: same records, same parameters; shared memory holds the weight rows, and for an updating launch the
+// accumulator rows and the FFM look-up table as well
+static RowsParams rows_params(const fwgpu_ctx *c, const FixedCtaParams &q)
+{
+    RowsParams r{};
+    r.lr = q.lr; r.ffm_w = q.ffm_w; r.ffm_acc = q.ffm_acc; r.lut_lr = q.lut_lr; r.lut_ffm = q.lut_ffm;
+    r.records = q.records; r.rec_off = q.rec_off; r.off_base = q.off_base; r.fixed_len = q.fixed_len;
+    r.ex_begin = q.ex_begin; r.n_examples = q.n_examples;
+    r.F = q.F; r.k = q.k; r.Fk = q.Fk; r.k4 = q.k / 4;
+    r.lpp = (r.k4 == 1 || r.k4 == 2 || r.k4 == 4) ? r.k4 : 1;
+    r.n_units = q.F * (q.F - 1) / 2 * r.lpp;
+    r.field_ns = q.field_ns; r.n_combos = q.n_combos; r.combo_off = q.combo_off; r.combo_ns = q.combo_ns; r.combo_weight = q.combo_weight;
+    r.add_constant = q.add_constant; r.lr_mask = q.lr_mask; r.ffm_mask = q.ffm_mask;
+    r.optimizer = q.optimizer; r.lr_lr = q.lr_lr; r.lr_mpt = q.lr_mpt; r.ffm_lr = q.ffm_lr; r.ffm_mpt = q.ffm_mpt;
+    r.update = q.update; r.preds = q.preds; r.leftover_idx = q.leftover_idx; r.leftover_cnt = q.leftover_cnt; r.max_groups = q.max_groups;
+    r.io = q.io;
+    (void)c;
+    return r;
+}
+template <int PHASE, int OPTK> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups);
+template <int PHASE> static cudaError_t launch_rows(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups)
+{
+    if (p.optimizer == OPT_LUT) return launch_rows_k<PHASE, (int)OPT_LUT>(c, p, full_groups);
+    return launch_rows_k<PHASE, -1>(c, p, full_groups);
+}
+template <int PHASE, int OPTK> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups)
+{
+    auto kern = k_learn_rows<PHASE, OPTK>;
+    const bool writes = PHASE != 1 && p.update != 0;
+    const size_t rows = (size_t)p.F * p.Fk * 4;
+    const size_t smem = rows + ((writes && p.optimizer != OPT_SGD) ? rows : 0) + ((writes && p.optimizer == OPT_LUT) ? 2048 * 4 : 0) +
+                        (size_t)((p.F + 3) & ~3u) * 4 + 8 * 4 + 16 +
+                        (p.max_groups == 1 ? (size_t)(p.n_combos + 1 + p.F * (p.F + 1) / 2) * 4 : 0); // parity mode: the tape
+    cudaError_t e0 = ensure_dyn_smem(c, kern, smem);
+    if (e0 != cudaSuccess) return e0;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) per_sm = 1;
+    uint32_t grid = std::min<uint32_t>(p.n_examples, (uint32_t)(c->num_sms * per_sm));
+    if (p.max_groups) grid = std::min<uint32_t>(grid, p.max_groups);
+    *full_groups = (uint32_t)(c->num_sms * per_sm);
+    if (grid == 0) return cudaSuccess;
+    kern<<<grid, 256, smem, c->stream>>>(p);
+    c->launches++; c->n_fixed_cta++;
+    return cudaGetLastError();
+}
+
 // ---- dense head (fwgpu_head.cuh) ----------------------------------------------------------------
 template <bool A_T, bool B_T, int EPI, int BM, int BN> static void launch_head_gemm_tile(fwgpu_ctx *c, HeadGemmParams &p, cudaStream_t stream)
 {
@@ -994,8 +1051,8 @@ static fwgpu_status head_learn(fwgpu_ctx *c, uint32_t count, int update, uint32_
                     ProfScope ps(c, 0);
                     if (phase == 1) {
                         CUDA_TRY(c, cudaMemsetAsync(cp.leftover_cnt, 0, 16, c->stream));
-                        e = launch_fixed_cta<2, 1>(c, cp, smem_cta, &full_groups);
-                    } else e = launch_fixed_cta<2, 2>(c, cp, smem_cta, &full_groups);
+                        e = c->fast_rows ? launch_rows<1>(c, rows_params(c, cp), &full_groups) : launch_fixed_cta<2, 1>(c, cp, smem_cta, &full_groups);
+                    } else e = c->fast_rows ? launch_rows<2>(c, rows_params(c, cp), &full_groups) : launch_fixed_cta<2, 2>(c, cp, smem_cta, &full_groups);
                 }
                 if (e != cudaSuccess) { c->set_error(std::string("k_learn_fixed_cta launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
                 if (phase == 1) { // records the fused kernel cannot take: translate them once, both passes use the result
@@ -1212,7 +1269,8 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 cp.update = update; cp.preds = fp.preds; cp.leftover_idx = left_idx; cp.leftover_cnt = left_cnt; cp.max_groups = cap;
                 const size_t smem_cta = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 8 + 64;
                 ProfScope ps(c, 0);
-                switch (c->fast_ub) {
+                if (c->fast_rows) e = launch_rows<0>(c, rows_params(c, cp), &full_groups);
+                else switch (c->fast_ub) {
                 case 1: e = launch_fixed_cta<1>(c, cp, smem_cta, &full_groups); break;
                 case 4: e = launch_fixed_cta<4>(c, cp, smem_cta, &full_groups); break;
                 default: e = launch_fixed_cta<2>(c, cp, smem_cta, &full_groups); break;

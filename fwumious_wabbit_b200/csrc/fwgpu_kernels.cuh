@@ -791,6 +791,32 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
         float wsum = part;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+        if (p.max_groups == 1) {
+            // One record in flight = the reference's sequential loop: the sigmoid input is summed in the reference's own order,
+            // left to right over the tape [LR combo outputs..., triangle outputs...] (graph.rs:251-284,
+            // block_loss_functions.rs:116-120), every lane redoing the same serial sum from the group's shared rows.  The
+            // prediction and the gradient are then BIT-exact, and AdagradLUT -- a step function of the accumulator's top bits
+            // -- never lands in another bucket.  Everything else (translate, gather, gradients, atomics) is the code above.
+            float ws = 0.0f;
+#pragma unroll
+            for (int r = 0; r < NLR; r++)
+                for (int i = 0; i < G; i++) { // combo i + G r: out[combo] = w * value, 0.0 when the combo has no feature (block_lr.rs:38-45)
+                    const float t = __shfl_sync(0xffffffffu, lr_ok[r] ? __fmul_rn(lrw[r].x, c_w[r]) : 0.0f, g0 + i);
+                    ws = __fadd_rn(ws, t);
+                }
+            __syncwarp();
+            for (uint32_t f = 1; f < F; f++)        // 2 * out[f][z], z < f (block_misc.rs:871-881); the diagonal of a lone feature is 0
+                for (uint32_t z = 0; z < f; z++) {
+                    float corr = 0.0f;              // block_ffm.rs:246-257: correction += w * (v * contra), v = 1.0
+                    for (uint32_t q = 0; q < k4; q++) {
+                        const float4 a = S[f * row_stride + z * k4 + q], b = S[z * row_stride + f * k4 + q];
+                        corr = __fadd_rn(corr, __fmul_rn(a.x, b.x)); corr = __fadd_rn(corr, __fmul_rn(a.y, b.y));
+                        corr = __fadd_rn(corr, __fmul_rn(a.z, b.z)); corr = __fadd_rn(corr, __fmul_rn(a.w, b.w));
+                    }
+                    ws = __fadd_rn(ws, corr);
+                }
+            wsum = ws;
+        }
 
         float pr, g;
         if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
@@ -1046,6 +1072,331 @@ __global__ void __launch_bounds__(256, 4) k_learn_fixed_cta(const FixedCtaParams
         // top of the next iteration lets anybody gather
         if (p.max_groups == 1) __threadfence();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_learn_rows<PHASE>: the fused path for WIDE models, rebuilt around bulk asynchronous copies (one per row and array)
+// instead of one LDGSTS / ATOMG / REDG per 16 bytes.  Same contract as k_learn_fixed_cta (raw records in the cache's
+// in-place encoding, one namespace per field, k % 4 == 0; anything else -> leftover list), one 256-thread block per record:
+//   * gather: thread e < F issues cp.async.bulk global -> shared for row e of the WEIGHTS and of the ACCUMULATORS
+//     (two pieces each: the row without its own-field block, which a single-valued field never uses, block_ffm.rs:236-244);
+//     an mbarrier counts the bytes, nobody spends an instruction or a register on the 97 KB in flight;
+//   * forward + update are organised by field PAIR: the thread that holds chunk (e, z-block) also holds its partner
+//     (z, e-block), so dot(a, b) is the pair's forward term, g * b and g * a are the two gradients, and both chunks are
+//     overwritten IN PLACE with the weight step  -g * LUT[acc + g^2]  and the accumulator increment  g^2  -- no thread ever
+//     reads what another one rewrites, so there is no barrier between gather and scatter except the sigmoid's reduction;
+//   * scatter: thread e issues cp.reduce.async.bulk shared -> global (.add.f32) for row e of both arrays: the L2 adds
+//     the whole row, fire and forget.  The optimizer step uses the accumulator snapshot that came with the gather
+//     (acc += g^2 is still exact -- nothing is lost -- but concurrent records that hit one slot all step from the value
+//     they gathered; with ONE record in flight this is the reference's sequential arithmetic, optimizer.rs:147-156);
+//   * the next record's header slots are prefetched while this one computes; two blocks per SM alternate between
+//     waiting for their rows and computing.
+// The same code serves a hash-range-sharded table (fwgpu_create_sharded): a remote row is pulled with the same bulk copy
+// over NVLink and its gradient row is pushed back as ONE bulk reduction that the owner's L2 applies.
+// Shared memory per block: 2 * F*F*k*4 B (+ 8 KB LUT): 105 KB for 39 fields x k = 8 -> two blocks per SM.
+// ---------------------------------------------------------------------------------------------
+struct RowsParams {
+    float2 *lr; float *ffm_w; float *ffm_acc; const float *lut_lr; const float *lut_ffm;
+    const uint32_t *records; const uint32_t *rec_off; uint32_t off_base, fixed_len;
+    uint32_t ex_begin, n_examples;
+    uint32_t F, k, Fk, k4;
+    uint32_t lpp, n_units;         // lanes per field pair (k/4 when that is 1, 2 or 4, else 1); units = pairs * lpp
+    const uint32_t *field_ns;
+    uint32_t n_combos; const uint32_t *combo_off, *combo_ns; const float *combo_weight; uint32_t add_constant;
+    uint32_t lr_mask, ffm_mask;
+    uint32_t optimizer; float lr_lr, lr_mpt, ffm_lr, ffm_mpt;
+    int update;
+    float *preds;
+    uint32_t *leftover_idx, *leftover_cnt;
+    uint32_t max_groups;
+    HeadIO io;                     // dense-head models only (PHASE 1 / 2)
+};
+constexpr int ROWS_MAXU = 8;       // pair units per thread held in registers: n_units <= 8 * 256
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(b)) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *b, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t *b, uint32_t parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(smem_u32(b)), "r"(parity) : "memory");
+}
+// global -> shared, completion counted in bytes on the mbarrier (UBLKCP)
+__device__ __forceinline__ void bulk_load(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *b)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(b)) : "memory");
+}
+// shared -> global, element-wise f32 add performed by the L2 that owns the line (local HBM or, for a sharded table, the peer's)
+__device__ __forceinline__ void bulk_reduce_add(void *gmem_dst, const void *smem_src, uint32_t bytes)
+{
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+
+// optimizer.rs calculate_update with the LUT in shared memory
+__device__ __forceinline__ float opt_step_s(uint32_t optimizer, float grad, float new_acc, const float *lut_s, float lr, float mpt)
+{
+    if (optimizer == OPT_LUT) return __fmul_rn(grad, lut_s[__float_as_uint(new_acc) >> 20]);
+    if (optimizer == OPT_FLEX) { const float u = __fmul_rn(__fmul_rn(grad, lr), powf(new_acc, mpt)); return (isnan(u) || isinf(u)) ? 0.0f : u; }
+    return __fmul_rn(grad, lr);
+}
+
+// OPTK: the optimizer as a compile-time constant (OPT_LUT, the reference's default under --adaptive: no powf code) or -1 = optimizer
+template <int PHASE, int OPTK>
+__global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
+{
+    const uint32_t optimizer = OPTK < 0 ? p.optimizer : (uint32_t)OPTK;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t F = p.F, k = p.k, Fk = p.Fk, k4 = p.k4, lpp = p.lpp;
+    const bool writes = PHASE != 1 && p.update != 0;           // this launch updates the tables
+    const bool has_acc = writes && optimizer != OPT_SGD;     // accumulator rows travel with the weight rows
+    const bool use_lut = writes && optimizer == OPT_LUT;
+    float *W = reinterpret_cast<float *>(smem_raw);
+    float *A = W + (size_t)F * Fk;
+    float *lut_s = A + (has_acc ? (size_t)F * Fk : 0);
+    uint32_t *slots = reinterpret_cast<uint32_t *>(lut_s + (use_lut ? 2048 : 0));
+    float *red = reinterpret_cast<float *>(slots + ((F + 3) & ~3u));
+    uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8);
+    float *terms = reinterpret_cast<float *>(bar + 2); // one-record-in-flight mode only: the sigmoid's inputs in tape order
+
+    uint32_t n_blocks = gridDim.x;
+    if (p.max_groups && p.max_groups < n_blocks) n_blocks = p.max_groups;
+    if (blockIdx.x >= n_blocks) return;
+    const bool one_in_flight = p.max_groups == 1; // per-example parity runs: every write is complete before the next record gathers
+
+    if (tid == 0) mbar_init(bar, F);              // one arrival per row-issuing thread and record
+    if (use_lut) for (uint32_t i = tid; i < 2048; i += 256) lut_s[i] = __ldg(p.lut_ffm + i);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u); // <= 256 (host checks); = the number of LR outputs
+    // static geometry: unit u = tid + 256 j is lane (u % lpp) of field pair (u / lpp) = (e, z), e < z; it owns the 16-byte
+    // quarters q = u % lpp, + lpp, ... of the chunk pair  a = row e, block towards z   and   b = row z, block towards e
+    uint32_t offA[ROWS_MAXU], offB[ROWS_MAXU], tri[ROWS_MAXU];
+#pragma unroll
+    for (int j = 0; j < ROWS_MAXU; j++) {
+        const uint32_t u = tid + 256u * j;
+        offA[j] = 0xffffffffu; offB[j] = 0; tri[j] = 0;
+        if (u < p.n_units) {
+            const uint32_t pr = u / lpp, q0 = u - pr * lpp;
+            uint32_t z = (uint32_t)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f); // pr = z (z - 1) / 2 + e
+            while (z * (z - 1) / 2 > pr) z--;
+            while ((z + 1) * z / 2 <= pr) z++;
+            const uint32_t e = pr - z * (z - 1) / 2;
+            offA[j] = e * Fk + z * k + 4 * q0;
+            offB[j] = z * Fk + e * k + 4 * q0;
+            tri[j] = n_lr + z * (z + 1) / 2 + e; // position on the tape / in the head's input (block_misc.rs:871-881)
+        }
+    }
+    const uint32_t my_field_ns = tid < F ? __ldg(p.field_ns + tid) : 0;
+    const uint32_t b1 = tid < F ? tid * k * 4 : 0, b2 = tid < F ? (F - 1 - tid) * k * 4 : 0; // row bytes before / after the own-field block
+    auto rec_ptr = [&](uint32_t ex) { return p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len); };
+
+    uint32_t ex = p.ex_begin + blockIdx.x;
+    const uint32_t ex_end = p.ex_begin + p.n_examples;
+    uint32_t slot_next = (ex < ex_end && tid < F) ? __ldg(rec_ptr(ex) + 3 + my_field_ns) : 0x80000000u;
+    uint32_t parity = 0;
+
+    for (; ex < ex_end; ex += n_blocks) {
+        const uint32_t *rec = rec_ptr(ex);
+        // ---- translate (feature_buffer.rs:178-338), in-place slots only ----
+        const uint32_t slot = slot_next;
+        const bool absent = tid < F && slot == 0x80000000u;
+        bool bad = tid < F && (slot & 0x80000000u) && !absent;
+        uint32_t lr_h = 0; float lr_v = 0.0f; bool lr_ok = false;
+        if (tid < p.n_combos) {
+            const uint32_t o0 = __ldg(p.combo_off + tid), o1 = __ldg(p.combo_off + tid + 1);
+            uint32_t h = 0; bool ok = true;
+            for (uint32_t o = o0; o < o1; o++) {
+                const uint32_t sl = __ldg(rec + 3 + __ldg(p.combo_ns + o));
+                if (sl & 0x80000000u) { ok = false; if (sl != 0x80000000u) bad = true; }
+                h = (o == o0) ? sl : ((h * 16777619u) ^ sl);
+            }
+            lr_ok = ok; lr_h = h & p.lr_mask; lr_v = __ldg(p.combo_weight + tid);
+        } else if (tid == p.n_combos && p.add_constant) { lr_ok = true; lr_h = 11650396u & p.lr_mask; lr_v = 1.0f; }
+        const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
+        // the bulk reductions this thread issued for the previous record have finished READING shared memory
+        if (tid < F) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); slots[tid] = slot; }
+        const int flags = __syncthreads_or((bad ? 1 : 0) | (absent ? 2 : 0)); // publishes slots[]; the buffers are free
+        {
+            const uint32_t nx = ex + n_blocks;
+            slot_next = (nx < ex_end && tid < F) ? __ldg(rec_ptr(nx) + 3 + my_field_ns) : 0x80000000u;
+        }
+        if (flags & 1) {
+            // PHASE 2 walks the same records as PHASE 1: the leftover list already holds this one
+            if (PHASE != 2 && tid == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
+            continue; // uniform
+        }
+        const uint32_t row = ex - p.io.row_base;
+        float g = 0.0f;
+        if (PHASE == 2) { g = __ldg(p.io.dy + row); if (g == 0.0f) continue; } // uniform: nothing to update
+
+        // ---- gather: one bulk copy per row piece and array, completion counted on the mbarrier ----
+        const uint32_t h_row = slot & p.ffm_mask;
+        if (tid < F) {
+            if (!absent) {
+                mbar_arrive_expect_tx(bar, (b1 + b2) * (has_acc ? 2u : 1u));
+                float *wr = W + (size_t)tid * Fk;
+                if (b1) bulk_load(wr, p.ffm_w + h_row, b1, bar);
+                if (b2) bulk_load(wr + (tid + 1) * k, p.ffm_w + h_row + (tid + 1) * k, b2, bar);
+                if (has_acc) {
+                    float *ar = A + (size_t)tid * Fk;
+                    if (b1) bulk_load(ar, p.ffm_acc + h_row, b1, bar);
+                    if (b2) bulk_load(ar + (tid + 1) * k, p.ffm_acc + h_row + (tid + 1) * k, b2, bar);
+                }
+            } else mbar_arrive(bar);
+        }
+        const float2 lr_cell = (PHASE != 2 || writes) && lr_ok ? __ldcg(p.lr + lr_h) : make_float2(0.f, 0.f);
+        if (flags & 2) { // some field is absent: its row reads as zeros (no feature, no interaction)
+            for (uint32_t e = 0; e < F; e++)
+                if (slots[e] == 0x80000000u) {
+                    for (uint32_t i = tid; i < Fk; i += 256) { W[(size_t)e * Fk + i] = 0.0f; if (has_acc) A[(size_t)e * Fk + i] = 0.0f; }
+                }
+            __syncthreads();
+        }
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+
+        const float *dxr = PHASE == 2 ? p.io.dX + (size_t)row * p.io.ldx : nullptr;
+        if (PHASE != 2) {
+            // ---- forward: sum over field pairs of <a, b> (block_ffm.rs:219-261 through the triangle, block_misc.rs:871-881) ----
+            float part = lr_ok ? __fmul_rn(lr_cell.x, lr_v) : 0.0f;
+            float *xr = PHASE == 1 ? p.io.X + (size_t)row * p.io.ldx : nullptr;
+            if (PHASE == 1) {
+                if (tid < n_lr) xr[tid] = part; // one feature of value 1.0 per combo: out[combo] = w * combo weight (block_lr.rs:38-45)
+                if (tid < F) xr[p.io.n_lr_out + tri_index(tid, tid)] = 0.0f; // a lone feature has no intra-field term
+                if (tid == 0) { p.io.row_label[row] = label; p.io.row_importance[row] = importance; p.io.row_out_index[row] = ex; }
+            }
+            // <a, b> over my quarter(s), every product and sum rounded separately in the order of block_ffm.rs:246-257
+            auto fold = [](float acc, const float4 &x, const float4 &y) {
+                acc = __fadd_rn(acc, __fmul_rn(x.x, y.x)); acc = __fadd_rn(acc, __fmul_rn(x.y, y.y));
+                acc = __fadd_rn(acc, __fmul_rn(x.z, y.z)); return __fadd_rn(acc, __fmul_rn(x.w, y.w));
+            };
+#pragma unroll
+            for (int j = 0; j < ROWS_MAXU; j++) {
+                const bool on = offA[j] != 0xffffffffu;
+                float sd = 0.0f;
+                if (one_in_flight && lpp > 1) {
+                    // parity mode: the lanes of a pair chain their quarters in order, so the pair's term is rounded exactly like
+                    // the reference's k-long running sum; the complete term ends up in the pair's last lane
+                    const float4 x = on ? *reinterpret_cast<const float4 *>(W + offA[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 y = on ? *reinterpret_cast<const float4 *>(W + offB[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    sd = fold(0.0f, x, y);
+                    for (uint32_t step = 1; step < lpp; step++) {
+                        const float prev = __shfl_up_sync(0xffffffffu, sd, 1);
+                        if ((lane & (lpp - 1)) == step) sd = fold(prev, x, y);
+                    }
+                    if (on && (lane & (lpp - 1)) == lpp - 1) { if (PHASE == 1) xr[tri[j]] = sd; else terms[tri[j]] = sd; }
+                    continue;
+                }
+                if (on) {
+                    for (uint32_t q = 0; q * lpp < k4; q++) // one iteration for k = 4, 8, 16
+                        sd = fold(sd, *reinterpret_cast<const float4 *>(W + offA[j] + 4 * q * lpp), *reinterpret_cast<const float4 *>(W + offB[j] + 4 * q * lpp));
+                }
+                if (one_in_flight) { if (on) { if (PHASE == 1) xr[tri[j]] = sd; else terms[tri[j]] = sd; } continue; } // lpp == 1: already in order
+                if (PHASE == 1) { // = 2 * out[z][e]: the lanes of one pair are neighbours in the warp
+                    if (lpp >= 2) sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+                    if (lpp >= 4) sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+                    if (on && (lane & (lpp - 1)) == 0) xr[tri[j]] = sd;
+                } else part += sd;
+            }
+            if (PHASE == 1) continue; // uniform; the next iteration's barrier protects the buffers
+            float wsum;
+            if (one_in_flight) {
+                // One record in flight = the reference's sequential loop: the sigmoid input is summed in the reference's own
+                // order, left to right over the tape [LR combo outputs..., triangle outputs...] (graph.rs:251-284,
+                // block_loss_functions.rs:116-120), so prediction and gradient are BIT-exact and AdagradLUT never lands in another
+                // bucket.  Gather, gradients, optimizer step and scatter are the code every other mode runs.
+                if (tid < n_lr) terms[tid] = part;                                      // out[combo] = w * value, or 0.0 (block_lr.rs:38-45)
+                if (tid < F) terms[n_lr + tri_index(tid, tid)] = 0.0f;                  // a lone feature has no intra-field term
+                __syncthreads();
+                const uint32_t x_len = n_lr + F * (F + 1) / 2;
+                wsum = 0.0f;
+                for (uint32_t i = 0; i < x_len; i++) wsum = __fadd_rn(wsum, terms[i]);
+            } else {
+                wsum = warp_sum(part);
+                if (lane == 0) red[warp] = wsum;
+                __syncthreads();
+                wsum = 0.0f;
+#pragma unroll
+                for (int w_ = 0; w_ < 8; w_++) wsum += red[w_];
+            }
+
+            float pr;
+            if (isnan(wsum)) { pr = logistic(0.0f); g = 0.0f; }
+            else if (wsum < -50.0f) { pr = logistic(-50.0f); g = 0.0f; }
+            else if (wsum > 50.0f) { pr = logistic(50.0f); g = 0.0f; }
+            else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
+            if (tid == 0) p.preds[ex] = pr;
+            if (!(p.update && importance != 0.0f && g != 0.0f)) continue; // uniform; regressor.rs:366-370
+        }
+
+        // ---- update, in place: weights := -step, accumulators := g^2 (block_ffm.rs:265-288, optimizer.rs:147-156) ----
+#pragma unroll
+        for (int j = 0; j < ROWS_MAXU; j++) {
+            if (offA[j] == 0xffffffffu) continue;
+            const float gz = PHASE == 2 ? __ldg(dxr + tri[j]) : g; // d_out[e][z] = d_out[z][e] (block_misc.rs:823-832)
+            for (uint32_t q = 0; q * lpp < k4; q++) {
+                float4 *pa = reinterpret_cast<float4 *>(W + offA[j] + 4 * q * lpp), *pb = reinterpret_cast<float4 *>(W + offB[j] + 4 * q * lpp);
+                const float4 a = *pa, b = *pb;
+                // gradient of a slot = d_out * value * partner, value = 1.0 (block_ffm.rs:246-257, 269-287)
+                const float ga[4] = {__fmul_rn(gz, b.x), __fmul_rn(gz, b.y), __fmul_rn(gz, b.z), __fmul_rn(gz, b.w)};
+                const float gb[4] = {__fmul_rn(gz, a.x), __fmul_rn(gz, a.y), __fmul_rn(gz, a.z), __fmul_rn(gz, a.w)};
+                float ua[4], ub[4];
+                if (has_acc) {
+                    float4 *qa = reinterpret_cast<float4 *>(A + offA[j] + 4 * q * lpp), *qb = reinterpret_cast<float4 *>(A + offB[j] + 4 * q * lpp);
+                    const float4 ca = *qa, cb = *qb;
+                    const float sa[4] = {ca.x, ca.y, ca.z, ca.w}, sb[4] = {cb.x, cb.y, cb.z, cb.w};
+                    float g2a[4], g2b[4];
+#pragma unroll
+                    for (int c = 0; c < 4; c++) {
+                        g2a[c] = __fmul_rn(ga[c], ga[c]); g2b[c] = __fmul_rn(gb[c], gb[c]);
+                        ua[c] = -opt_step_s(optimizer, ga[c], __fadd_rn(sa[c], g2a[c]), lut_s, p.ffm_lr, p.ffm_mpt);
+                        ub[c] = -opt_step_s(optimizer, gb[c], __fadd_rn(sb[c], g2b[c]), lut_s, p.ffm_lr, p.ffm_mpt);
+                    }
+                    *qa = make_float4(g2a[0], g2a[1], g2a[2], g2a[3]);
+                    *qb = make_float4(g2b[0], g2b[1], g2b[2], g2b[3]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { ua[c] = -__fmul_rn(ga[c], p.ffm_lr); ub[c] = -__fmul_rn(gb[c], p.ffm_lr); }
+                }
+                *pa = make_float4(ua[0], ua[1], ua[2], ua[3]);
+                *pb = make_float4(ub[0], ub[1], ub[2], ub[3]);
+            }
+        }
+        // ---- LR update (block_lr.rs:135-151) from the cell gathered with the record: two fire-and-forget reductions ----
+        if (lr_ok) {
+            float *cell = reinterpret_cast<float *>(p.lr + lr_h);
+            const float grad = __fmul_rn(PHASE == 2 ? __ldg(dxr + tid) : g, lr_v);
+            if (grad != 0.0f) {
+                float upd;
+                if (optimizer == OPT_SGD) upd = __fmul_rn(grad, p.lr_lr);
+                else {
+                    const float gg = __fmul_rn(grad, grad);
+                    red_add_f32(cell + 1, gg);
+                    upd = opt_step(optimizer, grad, __fadd_rn(lr_cell.y, gg), p.lut_lr, p.lr_lr, p.lr_mpt);
+                }
+                red_add_f32(cell, -upd);
+            }
+        }
+        // ---- scatter: the rewritten rows go back as bulk reductions, one per row piece and array ----
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // my shared-memory writes are visible to the copy engine
+        __syncthreads();
+        if (tid < F && !absent) {
+            float *wr = W + (size_t)tid * Fk;
+            if (b1) bulk_reduce_add(p.ffm_w + h_row, wr, b1);
+            if (b2) bulk_reduce_add(p.ffm_w + h_row + (tid + 1) * k, wr + (tid + 1) * k, b2);
+            if (has_acc) {
+                float *ar = A + (size_t)tid * Fk;
+                if (b1) bulk_reduce_add(p.ffm_acc + h_row, ar, b1);
+                if (b2) bulk_reduce_add(p.ffm_acc + h_row + (tid + 1) * k, ar + (tid + 1) * k, b2);
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (one_in_flight) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // complete, not just read
+        }
+        if (one_in_flight) __threadfence(); // the LR reductions too, before the barrier at the top of the next iteration
+    }
+    if (tid < F) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the reductions that read it
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -159,11 +159,15 @@ def test_cli_multi_batch_and_holdout_equal_single_batch(tmp_path):
     # saved regressor (-t) gives the same lines
     run(ns + rest + ["--data", f"{d}/train.vw", "-f", f"{d}/m.fw", "--save_resume", "--batch_size", "1000"])
     run(ns + ["-i", f"{d}/m.fw", "-t", "--data", f"{d}/train.vw", "-p", f"{d}/p_t.txt"])
-    assert open(f"{d}/p_many.txt").read().splitlines()[4320:] == open(f"{d}/p_t.txt").read().splitlines()[4320:]
-    # Hogwild mode with small batches still learns (this is the path that read misaligned words before)
+    # (training mode returns the training-order forward, -t the predict-order one: same value up to the last float bits)
+    assert np.max(np.abs(np.loadtxt(f"{d}/p_many.txt")[4320:] - np.loadtxt(f"{d}/p_t.txt")[4320:])) <= 2e-6
+    # Hogwild mode with small batches learns as well as the sequential run does on this short stream (this is the path that
+    # read misaligned words before)
     run(ns + rest[:-3] + ["--data", f"{d}/train.vw", "-p", f"{d}/p_h.txt", "--batch_size", "512"])
-    p = np.loadtxt(f"{d}/p_h.txt")
-    assert balanced_accuracy(p[3000:], labels_of(f"{d}/train.vw")[3000:]) > 0.9
+    y = labels_of(f"{d}/train.vw")
+    ll_seq = -np.mean(np.where(y[3000:4320] == 1, np.log(np.loadtxt(f"{d}/p_one.txt")[3000:4320]), np.log(1 - np.loadtxt(f"{d}/p_one.txt")[3000:4320])))
+    ll_hog = -np.mean(np.where(y[3000:4320] == 1, np.log(np.loadtxt(f"{d}/p_h.txt")[3000:4320]), np.log(1 - np.loadtxt(f"{d}/p_h.txt")[3000:4320])))
+    assert ll_hog < 0.693 and abs(ll_hog - ll_seq) / ll_seq < 0.03, (ll_hog, ll_seq)
 
 
 def test_cli_testonly_save_writes_a_loadable_inference_file(tmp_path):
@@ -190,6 +194,14 @@ def test_cli_prediction_model_delay(tmp_path):
     run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_all.txt", "--prediction_model_delay", "5000"])
     run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_t.txt", "-t"])
     assert open(f"{d}/p_all.txt").read() == open(f"{d}/p_t.txt").read()
-    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_50.txt", "--prediction_model_delay", "50"])
-    p = np.loadtxt(f"{d}/p_50.txt")
-    assert len(p) == 3000 and balanced_accuracy(p[1500:], labels_of(f"{d}/train.vw")[1500:]) > 0.85
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_50.txt", "--prediction_model_delay", "50", "--sequential"])
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_0.txt", "--sequential"])
+    y = labels_of(f"{d}/train.vw")
+
+    def ll(path):
+        p = np.loadtxt(path)
+        assert len(p) == 3000
+        return -np.mean(np.where(y[1500:] == 1, np.log(p[1500:]), np.log(1 - p[1500:])))
+
+    # a model that lags 50 examples behind scores almost as well as the up-to-date one, and better than the untrained one
+    assert ll(f"{d}/p_50.txt") < ll(f"{d}/p_t.txt") and abs(ll(f"{d}/p_50.txt") - ll(f"{d}/p_0.txt")) / ll(f"{d}/p_0.txt") < 0.05
