@@ -142,6 +142,18 @@ struct fwgpu_ctx {
     // hash-range-sharded tables over the GPUs of one box (fwgpu_shard.hpp); null = everything in this GPU's HBM
     ShardGroup *shard = nullptr;
     ShardedArray sh_lr, sh_w, sh_acc;
+    // one model over several GPUs, owner-side updates (k_learn_rows<PUSH> + k_apply_inbox): every rank's inbox is one range of
+    // sh_inbox; a chunk of at most shard_chunk records per rank is followed by ONE exchange step, the NCCL all-gather of the
+    // per-owner push counts (which is also the barrier between "pushed" and "apply")
+    bool push_ok = false;
+    ShardedArray sh_inbox;
+    uint32_t shard_chunk = 8192, inbox_cap = 0, owner_shift = 32;
+    uint64_t inbox_rank_bytes = 0, shard_chunks_done = 0;
+    uint32_t *push_cnt = nullptr, *counts_all[2] = {nullptr, nullptr};
+    bool shard_overlap = true;
+    cudaStream_t apply_stream = nullptr;
+    cudaEvent_t ev_gathered[2]{}, ev_applied[2]{};
+    bool ev_applied_rec[2] = {false, false};
     std::string err;
     void set_error(const std::string &s) { err = s; }
 };
@@ -205,7 +217,11 @@ extern "C" void fwgpu_destroy(fwgpu_ctx *c)
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     if (c->head_side_stream) cudaStreamSynchronize(c->head_side_stream);
     if (c->shard) {
-        c->shard->destroy_array(c->sh_lr); c->shard->destroy_array(c->sh_w); c->shard->destroy_array(c->sh_acc);
+        if (c->apply_stream) cudaStreamSynchronize(c->apply_stream);
+        c->shard->destroy_array(c->sh_lr); c->shard->destroy_array(c->sh_w); c->shard->destroy_array(c->sh_acc); c->shard->destroy_array(c->sh_inbox);
+        cudaFree(c->push_cnt); cudaFree(c->counts_all[0]); cudaFree(c->counts_all[1]);
+        for (int i = 0; i < 2; i++) { if (c->ev_gathered[i]) cudaEventDestroy(c->ev_gathered[i]); if (c->ev_applied[i]) cudaEventDestroy(c->ev_applied[i]); }
+        if (c->apply_stream) cudaStreamDestroy(c->apply_stream);
         delete c->shard;
         c->lr = nullptr; c->ffm_w = nullptr; c->ffm_acc = nullptr;
     }
@@ -479,6 +495,33 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
         c->max_inflight = d.hogwild_max_inflight ? d.hogwild_max_inflight : (constant_step ? 16u : 0u);
         if (const char *t = getenv("FWGPU_MAX_INFLIGHT")) c->max_inflight = (uint32_t)strtoul(t, nullptr, 10);
     }
+    if (c->shard && c->fast_rows && c->F > 0 && !d.immutable && c->shard->world <= 16 && !getenv("FWGPU_SHARD_DIRECT")) {
+        // Owner-side update path.  Collective: every rank takes the same decisions from the same descriptor.
+        ShardGroup &g = *c->shard;
+        const uint64_t shard_floats = c->sh_w.sizes.size() > 1 && c->sh_w.sizes[1] ? c->sh_w.sizes[0] / 4 : 0;
+        bool pow2 = shard_floats && (shard_floats & (shard_floats - 1)) == 0;
+        c->owner_shift = 32; // everything on rank 0 (table too small to split)
+        if (pow2) { c->owner_shift = 0; while ((1ull << c->owner_shift) < shard_floats) c->owner_shift++; }
+        if (shard_floats == 0 || pow2) {
+            if (const char *t = getenv("FWGPU_SHARD_CHUNK")) c->shard_chunk = std::max(64, atoi(t));
+            if (const char *t = getenv("FWGPU_SHARD_OVERLAP")) c->shard_overlap = atoi(t) != 0;
+            if (!g.comm_init()) { c->set_error("shard group (NCCL): " + g.error); return FWGPU_ERR_NCCL; }
+            const uint64_t entry_bytes = (uint64_t)(c->Fk + ROWS_HDR) * 4;
+            c->inbox_cap = c->shard_chunk * c->F;                               // worst case: every row of a chunk goes to one owner
+            c->inbox_rank_bytes = g.round_up(2ull * g.world * c->inbox_cap * entry_bytes); // [half][source][cap]
+            std::vector<size_t> sizes(g.world, (size_t)c->inbox_rank_bytes);
+            if (!g.create_array(c->sh_inbox, sizes)) { c->set_error("sharded inbox: " + g.error); return FWGPU_ERR_CUDA; }
+            CUDA_TRY(c, cudaMalloc((void **)&c->push_cnt, 16 * 4));
+            for (int i = 0; i < 2; i++) {
+                CUDA_TRY(c, cudaMalloc((void **)&c->counts_all[i], 16 * 16 * 4));
+                CUDA_TRY(c, cudaMemset(c->counts_all[i], 0, 16 * 16 * 4));
+                CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_gathered[i], cudaEventDisableTiming));
+                CUDA_TRY(c, cudaEventCreateWithFlags(&c->ev_applied[i], cudaEventDisableTiming));
+            }
+            CUDA_TRY(c, cudaStreamCreateWithFlags(&c->apply_stream, cudaStreamNonBlocking));
+            c->push_ok = true;
+        }
+    }
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     // nobody trains before every shard is initialised
     if (c->shard && !c->shard->barrier()) { c->set_error("shard group: " + c->shard->error); return FWGPU_ERR_CUDA; }
@@ -567,6 +610,7 @@ extern "C" fwgpu_status fwgpu_sync(fwgpu_ctx *c)
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->d2h_stream));
+    if (c->apply_stream) CUDA_TRY(c, cudaStreamSynchronize(c->apply_stream));
     return check_err_flag(c);
 }
 
@@ -834,18 +878,18 @@ static RowsParams rows_params(const fwgpu_ctx *c, const FixedCtaParams &q)
     (void)c;
     return r;
 }
-template <int PHASE, int OPTK> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups);
+template <int PHASE, int OPTK, bool PUSH> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups);
 template <int PHASE> static cudaError_t launch_rows(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups)
 {
-    if (p.optimizer == OPT_LUT) return launch_rows_k<PHASE, (int)OPT_LUT>(c, p, full_groups);
-    return launch_rows_k<PHASE, -1>(c, p, full_groups);
+    if (p.optimizer == OPT_LUT) return launch_rows_k<PHASE, (int)OPT_LUT, false>(c, p, full_groups);
+    return launch_rows_k<PHASE, -1, false>(c, p, full_groups);
 }
-template <int PHASE, int OPTK> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups)
+template <int PHASE, int OPTK, bool PUSH> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups)
 {
-    auto kern = k_learn_rows<PHASE, OPTK>;
+    auto kern = k_learn_rows<PHASE, OPTK, PUSH>;
     const bool writes = PHASE != 1 && p.update != 0;
-    const size_t rows = (size_t)p.F * p.Fk * 4;
-    const size_t smem = rows + ((writes && p.optimizer != OPT_SGD) ? rows : 0) + ((writes && p.optimizer == OPT_LUT) ? 2048 * 4 : 0) +
+    const size_t rows = (size_t)p.F * (p.Fk + (PUSH ? ROWS_HDR : 0)) * 4 + (PUSH ? 16 : 0);
+    const size_t smem = rows + ((!PUSH && writes && p.optimizer != OPT_SGD) ? rows : 0) + ((!PUSH && writes && p.optimizer == OPT_LUT) ? 2048 * 4 : 0) +
                         (size_t)((p.F + 3) & ~3u) * 4 + 8 * 4 + 16 +
                         (p.max_groups == 1 ? (size_t)(p.n_combos + 1 + p.F * (p.F + 1) / 2) * 4 : 0); // parity mode: the tape
     cudaError_t e0 = ensure_dyn_smem(c, kern, smem);
@@ -854,6 +898,7 @@ template <int PHASE, int OPTK> static cudaError_t launch_rows_k(fwgpu_ctx *c, co
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
+    if (PUSH && c->shard_overlap && per_sm > 3) per_sm = 3; // leave room for the owner-side apply kernel of the previous chunk
     uint32_t grid = std::min<uint32_t>(p.n_examples, (uint32_t)(c->num_sms * per_sm));
     if (p.max_groups) grid = std::min<uint32_t>(grid, p.max_groups);
     *full_groups = (uint32_t)(c->num_sms * per_sm);
@@ -861,6 +906,46 @@ template <int PHASE, int OPTK> static cudaError_t launch_rows_k(fwgpu_ctx *c, co
     kern<<<grid, 256, smem, c->stream>>>(p);
     c->launches++; c->n_fixed_cta++;
     return cudaGetLastError();
+}
+
+// One chunk of the sharded owner-side update path: push kernel, exchange step, apply kernel.
+//   main stream : [wait: apply of the chunk that last used this inbox half]  zero counters -> k_learn_rows<PUSH> -> [wait: apply of
+//                 the previous chunk] -> NCCL all-gather of the per-owner counts (= barrier: every rank has pushed)
+//   apply stream: wait all-gather -> k_apply_inbox (overlaps the next chunk's push kernel)
+// Inbox halves alternate, so a rank may push chunk i+1 while owners still apply chunk i; chunk i+2 reuses half i only after
+// all-gather i+1, which every rank enqueues after its apply of chunk i.
+static fwgpu_status shard_push_chunk(fwgpu_ctx *c, RowsParams rp, uint32_t *full_groups)
+{
+    ShardGroup &g = *c->shard;
+    const int half = (int)(c->shard_chunks_done & 1);
+    const uint64_t entry_bytes = (uint64_t)(c->Fk + ROWS_HDR) * 4;
+    rp.inbox = (unsigned char *)c->sh_inbox.va;
+    rp.inbox_rank_stride = c->inbox_rank_bytes;
+    rp.inbox_src_off = ((uint64_t)half * g.world + g.rank) * c->inbox_cap * entry_bytes;
+    rp.push_cnt = c->push_cnt; rp.owner_shift = c->owner_shift; rp.world = g.world;
+    CUDA_TRY(c, cudaMemsetAsync(c->push_cnt, 0, 16 * 4, c->stream));
+    cudaError_t e = rp.optimizer == OPT_LUT ? launch_rows_k<0, (int)OPT_LUT, true>(c, rp, full_groups) : launch_rows_k<0, -1, true>(c, rp, full_groups);
+    if (e != cudaSuccess) { c->set_error(std::string("k_learn_rows<PUSH> launch: ") + cudaGetErrorString(e)); return FWGPU_ERR_CUDA; }
+    // the previous chunk's apply (other half) is ordered before this all-gather: see the reuse argument above
+    if (c->ev_applied_rec[half ^ 1]) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_applied[half ^ 1], 0));
+    if (!g.all_gather_u32(c->push_cnt, c->counts_all[half], g.world, c->stream)) { c->set_error("shard group (NCCL): " + g.error); return FWGPU_ERR_NCCL; }
+    c->launches++;
+    cudaStream_t as = c->shard_overlap ? c->apply_stream : c->stream;
+    if (c->shard_overlap) {
+        CUDA_TRY(c, cudaEventRecord(c->ev_gathered[half], c->stream));
+        CUDA_TRY(c, cudaStreamWaitEvent(as, c->ev_gathered[half], 0));
+    }
+    ApplyParams ap{};
+    ap.inbox_half = (const unsigned char *)c->sh_inbox.va + (uint64_t)g.rank * c->inbox_rank_bytes + (uint64_t)half * g.world * c->inbox_cap * entry_bytes;
+    ap.counts_all = c->counts_all[half]; ap.world = g.world; ap.rank = g.rank; ap.cap = c->inbox_cap; ap.entry_bytes = (uint32_t)entry_bytes;
+    ap.F = c->F; ap.k = c->k; ap.Fk = c->Fk; ap.ffm_w = c->ffm_w; ap.ffm_acc = c->ffm_acc; ap.lut_ffm = c->lut_dev + FWGPU_LUT_SIZE;
+    ap.optimizer = c->optimizer; ap.ffm_lr = c->d.ffm_learning_rate; ap.ffm_mpt = -c->d.ffm_power_t;
+    k_apply_inbox<<<c->num_sms * (c->shard_overlap ? 1 : 4), 256, 0, as>>>(ap);
+    c->launches++;
+    CUDA_TRY(c, cudaGetLastError());
+    if (c->shard_overlap) { CUDA_TRY(c, cudaEventRecord(c->ev_applied[half], as)); c->ev_applied_rec[half] = true; }
+    c->shard_chunks_done++;
+    return FWGPU_OK;
 }
 
 // ---- dense head (fwgpu_head.cuh) ----------------------------------------------------------------
@@ -1253,6 +1338,10 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 cnt = (uint32_t)std::min<uint64_t>(cnt, std::max<uint64_t>(2 * seen, c->ramp_div) - seen);
             }
             if (update && c->max_inflight && (cap == 0 || cap > c->max_inflight)) cap = c->max_inflight;
+            // one model over several GPUs: gradients go to the rows' owners chunk by chunk (one record in flight = the parity
+            // mode keeps the direct path: its remote bulk reductions complete before the next record gathers)
+            const bool push = c->push_ok && update && c->fast_cta && c->fast_rows && cap != 1;
+            if (push) cnt = std::min<uint32_t>(cnt, c->shard_chunk);
             fp.ex_begin = done; fp.n_examples = cnt; fp.max_groups = cap;
             uint32_t full_groups = 0;
             cudaError_t e;
@@ -1269,7 +1358,10 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
                 cp.update = update; cp.preds = fp.preds; cp.leftover_idx = left_idx; cp.leftover_cnt = left_cnt; cp.max_groups = cap;
                 const size_t smem_cta = (size_t)c->F * c->Fk * 4 + (size_t)c->F * 8 + 64;
                 ProfScope ps(c, 0);
-                if (c->fast_rows) e = launch_rows<0>(c, rows_params(c, cp), &full_groups);
+                if (push) {
+                    if ((st = shard_push_chunk(c, rows_params(c, cp), &full_groups))) return st;
+                    e = cudaSuccess;
+                } else if (c->fast_rows) e = launch_rows<0>(c, rows_params(c, cp), &full_groups);
                 else switch (c->fast_ub) {
                 case 1: e = launch_fixed_cta<1>(c, cp, smem_cta, &full_groups); break;
                 case 4: e = launch_fixed_cta<4>(c, cp, smem_cta, &full_groups); break;
@@ -1287,6 +1379,11 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
             done += cnt;
         }
         tp.ex_list = left_idx; tp.ex_count = left_cnt;
+        // sharded owner-side path: the call is complete, in stream order, when the owners have applied its last chunk here
+        if (c->push_ok && c->shard_overlap && c->shard_chunks_done) {
+            const int last = (int)((c->shard_chunks_done - 1) & 1);
+            if (c->ev_applied_rec[last]) CUDA_TRY(c, cudaStreamWaitEvent(c->stream, c->ev_applied[last], 0));
+        }
     }
     {
         ProfScope ps(c, 1);

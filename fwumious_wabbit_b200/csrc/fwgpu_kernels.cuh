@@ -649,6 +649,23 @@ __device__ __forceinline__ void fixed_lr_apply(const FixedParams &p, uint32_t op
 
 __device__ __forceinline__ void prefetch_l1(const void *ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 
+// Parity mode of k_learn_fixed: the triangle outputs added to `ws` in tape order, from a group's shared rows (kept out of line:
+// it runs for one record in flight only and must not cost the throughput path registers)
+__device__ __noinline__ float tape_order_ffm_sum(float ws, const float4 *S, uint32_t F, uint32_t k4, uint32_t row_stride)
+{
+    for (uint32_t f = 1; f < F; f++)        // 2 * out[f][z], z < f (block_misc.rs:871-881); the diagonal of a lone feature is 0
+        for (uint32_t z = 0; z < f; z++) {
+            float corr = 0.0f;              // block_ffm.rs:246-257: correction += w * (v * contra), v = 1.0
+            for (uint32_t q = 0; q < k4; q++) {
+                const float4 a = S[f * row_stride + z * k4 + q], b = S[z * row_stride + f * k4 + q];
+                corr = __fadd_rn(corr, __fmul_rn(a.x, b.x)); corr = __fadd_rn(corr, __fmul_rn(a.y, b.y));
+                corr = __fadd_rn(corr, __fmul_rn(a.z, b.z)); corr = __fadd_rn(corr, __fmul_rn(a.w, b.w));
+            }
+            ws = __fadd_rn(ws, corr);
+        }
+    return ws;
+}
+
 // G   : lanes per record (32, or 16 = two records per warp and round when F <= 16, F*F*k/4 <= 64 chunks and at most 16
 //       LR entries: the per-record overhead -- translate, sigmoid, reductions -- is then shared by two records and
 //       every wait for L2 covers two records);
@@ -743,6 +760,15 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
             if (sl == 0) { const uint32_t at = atomicAdd(p.leftover_cnt, 1u); p.leftover_idx[at] = ex; }
             live = false;
         }
+        // Two LR features of ONE record in the same cell (a hash collision between combos, ~1e-4 of the records at -b 18): the
+        // reference applies them one after the other (block_lr.rs:140-150), so the second must see the first one's accumulator.
+        // Those lanes take their accumulator from an atomic's return value instead of the gathered cell.
+        bool lr_dup[NLR];
+#pragma unroll
+        for (int r = 0; r < NLR; r++) {
+            const uint32_t key = (live && lr_ok[r] && c_len[r] != 0xffffffffu) ? lr_h[r] : (0x80000000u | (uint32_t)lane);
+            lr_dup[r] = __popc(__match_any_sync(0xffffffffu, key) & gmask) > 1;
+        }
 
         // ---- gather: one 128-bit load per chunk ----
         float4 v[NCH];
@@ -805,16 +831,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
                     ws = __fadd_rn(ws, t);
                 }
             __syncwarp();
-            for (uint32_t f = 1; f < F; f++)        // 2 * out[f][z], z < f (block_misc.rs:871-881); the diagonal of a lone feature is 0
-                for (uint32_t z = 0; z < f; z++) {
-                    float corr = 0.0f;              // block_ffm.rs:246-257: correction += w * (v * contra), v = 1.0
-                    for (uint32_t q = 0; q < k4; q++) {
-                        const float4 a = S[f * row_stride + z * k4 + q], b = S[z * row_stride + f * k4 + q];
-                        corr = __fadd_rn(corr, __fmul_rn(a.x, b.x)); corr = __fadd_rn(corr, __fmul_rn(a.y, b.y));
-                        corr = __fadd_rn(corr, __fmul_rn(a.z, b.z)); corr = __fadd_rn(corr, __fmul_rn(a.w, b.w));
-                    }
-                    ws = __fadd_rn(ws, corr);
-                }
+            ws = tape_order_ffm_sum(ws, S, F, k4, row_stride);
             wsum = ws;
         }
 
@@ -851,7 +868,14 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
                 if (!lr_ok[r]) continue;
                 const float gl = __fmul_rn(g, c_w[r]);
                 if (c_len[r] == 0xffffffffu) { bias_G = __fadd_rn(bias_G, gl); bias_G2 = __fadd_rn(bias_G2, __fmul_rn(gl, gl)); }
-                else if (gl != 0.0f) fixed_lr_apply(p, optimizer, lr_h[r], gl, __fmul_rn(gl, gl), lrw[r].y);
+                else if (gl != 0.0f) {
+                    float acc_seen = lrw[r].y;
+                    if (lr_dup[r] && optimizer != OPT_SGD) { // ordered by the L2: each duplicate steps from what the previous one left
+                        const float gg = __fmul_rn(gl, gl);
+                        acc_seen = atomicAdd(reinterpret_cast<float *>(p.lr + lr_h[r]) + 1, gg);
+                        red_add_f32(reinterpret_cast<float *>(p.lr + lr_h[r]), -opt_step(optimizer, gl, __fadd_rn(acc_seen, gg), p.lut_lr, p.lr_lr, p.lr_mpt));
+                    } else fixed_lr_apply(p, optimizer, lr_h[r], gl, __fmul_rn(gl, gl), acc_seen);
+                }
             }
         }
         // One record in flight (hogwild_max_inflight = 1, the setting of the per-example parity tests): REDG is fire-and-forget,
@@ -1110,8 +1134,17 @@ struct RowsParams {
     uint32_t *leftover_idx, *leftover_cnt;
     uint32_t max_groups;
     HeadIO io;                     // dense-head models only (PHASE 1 / 2)
+    // PUSH mode (one model over the GPUs of one box, fwgpu_create_sharded): rows are pulled from their owner's HBM with the same
+    // bulk copies; instead of updating in place the block writes the record's RAW gradient rows, each with a 16-byte header
+    // {row base, field, -, -}, and pushes row e as ONE bulk store into the inbox of the rank that owns the row
+    // (inbox[owner][half][source rank][slot]); the owner applies AdaGrad from its own accumulators (k_apply_inbox).
+    unsigned char *inbox;          // one virtual range: rank r's inbox at inbox + r * inbox_rank_stride
+    unsigned long long inbox_rank_stride, inbox_src_off; // bytes; inbox_src_off = offset of (half, this rank)'s sub-ring
+    uint32_t *push_cnt;            // [world] entries this rank has pushed to each owner during the current chunk (local)
+    uint32_t owner_shift, world;   // owner = row base >> owner_shift (>= 32: everything on rank 0), clamped to world - 1
 };
-constexpr int ROWS_MAXU = 8;       // pair units per thread held in registers: n_units <= 8 * 256
+constexpr int ROWS_MAXU = 8;
+constexpr uint32_t ROWS_HDR = 4;   // floats of header in front of each shared-memory row in PUSH mode       // pair units per thread held in registers: n_units <= 8 * 256
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *b, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(b)), "r"(count) : "memory"); }
@@ -1141,19 +1174,20 @@ __device__ __forceinline__ float opt_step_s(uint32_t optimizer, float grad, floa
 }
 
 // OPTK: the optimizer as a compile-time constant (OPT_LUT, the reference's default under --adaptive: no powf code) or -1 = optimizer
-template <int PHASE, int OPTK>
-__global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
+template <int PHASE, int OPTK, bool PUSH>
+__global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_rows(const RowsParams p)
 {
     const uint32_t optimizer = OPTK < 0 ? p.optimizer : (uint32_t)OPTK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t F = p.F, k = p.k, Fk = p.Fk, k4 = p.k4, lpp = p.lpp;
-    const bool writes = PHASE != 1 && p.update != 0;           // this launch updates the tables
-    const bool has_acc = writes && optimizer != OPT_SGD;     // accumulator rows travel with the weight rows
-    const bool use_lut = writes && optimizer == OPT_LUT;
-    float *W = reinterpret_cast<float *>(smem_raw);
-    float *A = W + (size_t)F * Fk;
-    float *lut_s = A + (has_acc ? (size_t)F * Fk : 0);
+    const uint32_t RS = Fk + (PUSH ? ROWS_HDR : 0u);           // shared-memory row stride in floats
+    const bool writes = PHASE != 1 && p.update != 0;           // this launch updates the tables (PUSH: sends gradients)
+    const bool has_acc = !PUSH && writes && optimizer != OPT_SGD; // accumulator rows travel with the weight rows
+    const bool use_lut = !PUSH && writes && optimizer == OPT_LUT;
+    float *W = reinterpret_cast<float *>(smem_raw) + (PUSH ? ROWS_HDR : 0u); // row e at W + e * RS (its header right in front of it)
+    float *A = W + (size_t)F * RS;
+    float *lut_s = A + (has_acc ? (size_t)F * RS : 0);
     uint32_t *slots = reinterpret_cast<uint32_t *>(lut_s + (use_lut ? 2048 : 0));
     float *red = reinterpret_cast<float *>(slots + ((F + 3) & ~3u));
     uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8);
@@ -1164,7 +1198,17 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
     if (blockIdx.x >= n_blocks) return;
     const bool one_in_flight = p.max_groups == 1; // per-example parity runs: every write is complete before the next record gathers
 
-    if (tid == 0) mbar_init(bar, F);              // one arrival per row-issuing thread and record
+    // One bulk copy per row and array (the whole row: its own-field block rides along unused -- 2.5 % of the bytes -- so that a
+    // row is ONE copy, and is zeroed before it is reduced back).  The copies are issued by 8 warps at once: op o = row (o % F)
+    // of array (o / F) belongs to lane o / 8 of warp o % 8, because a warp issues its lanes' bulk copies one after the other.
+    const uint32_t n_ops = F * (has_acc ? 2u : 1u);
+    const uint32_t my_op = lane * 8 + warp;
+    const bool op_on = my_op < n_ops;
+    const uint32_t op_row = op_on ? (my_op >= F ? my_op - F : my_op) : 0;
+    const bool op_acc = my_op >= F;
+    float *const op_smem = (op_acc ? A : W) + (size_t)op_row * RS;
+    float *const op_table = op_acc ? p.ffm_acc : p.ffm_w;
+    if (tid == 0) mbar_init(bar, n_ops);          // one arrival per op and record
     if (use_lut) for (uint32_t i = tid; i < 2048; i += 256) lut_s[i] = __ldg(p.lut_ffm + i);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
@@ -1183,13 +1227,12 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
             while (z * (z - 1) / 2 > pr) z--;
             while ((z + 1) * z / 2 <= pr) z++;
             const uint32_t e = pr - z * (z - 1) / 2;
-            offA[j] = e * Fk + z * k + 4 * q0;
-            offB[j] = z * Fk + e * k + 4 * q0;
+            offA[j] = e * RS + z * k + 4 * q0;
+            offB[j] = z * RS + e * k + 4 * q0;
             tri[j] = n_lr + z * (z + 1) / 2 + e; // position on the tape / in the head's input (block_misc.rs:871-881)
         }
     }
     const uint32_t my_field_ns = tid < F ? __ldg(p.field_ns + tid) : 0;
-    const uint32_t b1 = tid < F ? tid * k * 4 : 0, b2 = tid < F ? (F - 1 - tid) * k * 4 : 0; // row bytes before / after the own-field block
     auto rec_ptr = [&](uint32_t ex) { return p.records + (p.rec_off ? (size_t)(p.rec_off[ex] - p.off_base) : (size_t)ex * p.fixed_len); };
 
     uint32_t ex = p.ex_begin + blockIdx.x;
@@ -1216,7 +1259,8 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
         } else if (tid == p.n_combos && p.add_constant) { lr_ok = true; lr_h = 11650396u & p.lr_mask; lr_v = 1.0f; }
         const float label = (float)__ldg(rec + 1), importance = __uint_as_float(__ldg(rec + 2));
         // the bulk reductions this thread issued for the previous record have finished READING shared memory
-        if (tid < F) { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); slots[tid] = slot; }
+        if (op_on) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (tid < F) slots[tid] = slot;
         const int flags = __syncthreads_or((bad ? 1 : 0) | (absent ? 2 : 0)); // publishes slots[]; the buffers are free
         {
             const uint32_t nx = ex + n_blocks;
@@ -1232,25 +1276,35 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
         if (PHASE == 2) { g = __ldg(p.io.dy + row); if (g == 0.0f) continue; } // uniform: nothing to update
 
         // ---- gather: one bulk copy per row piece and array, completion counted on the mbarrier ----
-        const uint32_t h_row = slot & p.ffm_mask;
-        if (tid < F) {
-            if (!absent) {
-                mbar_arrive_expect_tx(bar, (b1 + b2) * (has_acc ? 2u : 1u));
-                float *wr = W + (size_t)tid * Fk;
-                if (b1) bulk_load(wr, p.ffm_w + h_row, b1, bar);
-                if (b2) bulk_load(wr + (tid + 1) * k, p.ffm_w + h_row + (tid + 1) * k, b2, bar);
-                if (has_acc) {
-                    float *ar = A + (size_t)tid * Fk;
-                    if (b1) bulk_load(ar, p.ffm_acc + h_row, b1, bar);
-                    if (b2) bulk_load(ar + (tid + 1) * k, p.ffm_acc + h_row + (tid + 1) * k, b2, bar);
-                }
+        const uint32_t op_slot = op_on ? slots[op_row] : 0x80000000u;
+        const bool op_present = op_slot != 0x80000000u;
+        const uint32_t h_row = op_slot & p.ffm_mask;  // base of MY op's row
+        unsigned char *push_dst = nullptr;
+        if (op_on) {
+            if (op_present) {
+                mbar_arrive_expect_tx(bar, Fk * 4u);
+                bulk_load(op_smem, op_table + h_row, Fk * 4u, bar);
             } else mbar_arrive(bar);
         }
         const float2 lr_cell = (PHASE != 2 || writes) && lr_ok ? __ldcg(p.lr + lr_h) : make_float2(0.f, 0.f);
+        // Two rows of ONE record whose windows overlap (equal or neighbouring hashes: 2.7 % of the records at 39 fields and
+        // ffm_bit_precision 24) share slots: the reference updates them feature after feature (block_ffm.rs:269-287), so the
+        // second update of a shared slot sees the first one's accumulator.  Such a record takes its accumulators from atomics'
+        // return values (update_with_atomics below) instead of the gathered snapshot.  Checked while the rows are in flight.
+        bool overlap = false;
+        if (!PUSH && writes && tid < F && !absent) {
+            const uint32_t mine = slot & p.ffm_mask;
+            for (uint32_t e = 0; e < tid; e++) {
+                const uint32_t o = slots[e];
+                if (o == 0x80000000u) continue;
+                const uint32_t oh = o & p.ffm_mask, diff = mine > oh ? mine - oh : oh - mine;
+                overlap = overlap || diff < Fk;
+            }
+        }
         if (flags & 2) { // some field is absent: its row reads as zeros (no feature, no interaction)
             for (uint32_t e = 0; e < F; e++)
                 if (slots[e] == 0x80000000u) {
-                    for (uint32_t i = tid; i < Fk; i += 256) { W[(size_t)e * Fk + i] = 0.0f; if (has_acc) A[(size_t)e * Fk + i] = 0.0f; }
+                    for (uint32_t i = tid; i < Fk; i += 256) { W[(size_t)e * RS + i] = 0.0f; if (has_acc) A[(size_t)e * RS + i] = 0.0f; }
                 }
             __syncthreads();
         }
@@ -1309,14 +1363,14 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
                 // bucket.  Gather, gradients, optimizer step and scatter are the code every other mode runs.
                 if (tid < n_lr) terms[tid] = part;                                      // out[combo] = w * value, or 0.0 (block_lr.rs:38-45)
                 if (tid < F) terms[n_lr + tri_index(tid, tid)] = 0.0f;                  // a lone feature has no intra-field term
-                __syncthreads();
+                overlap = __syncthreads_or(overlap ? 1 : 0) != 0;
                 const uint32_t x_len = n_lr + F * (F + 1) / 2;
                 wsum = 0.0f;
                 for (uint32_t i = 0; i < x_len; i++) wsum = __fadd_rn(wsum, terms[i]);
             } else {
                 wsum = warp_sum(part);
                 if (lane == 0) red[warp] = wsum;
-                __syncthreads();
+                overlap = __syncthreads_or(overlap ? 1 : 0) != 0;
                 wsum = 0.0f;
 #pragma unroll
                 for (int w_ = 0; w_ < 8; w_++) wsum += red[w_];
@@ -1329,8 +1383,43 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
             else { pr = logistic(wsum); g = __fmul_rn(-__fsub_rn(label, pr), importance); }
             if (tid == 0) p.preds[ex] = pr;
             if (!(p.update && importance != 0.0f && g != 0.0f)) continue; // uniform; regressor.rs:366-370
+        } else if (!PUSH) overlap = __syncthreads_or(overlap ? 1 : 0) != 0;
+
+        // ---- LR accumulators first (block_lr.rs:135-151): the atomic's return value is needed only after the FFM update, so
+        //      its round trip to the L2 is hidden; duplicates of one cell inside a record are ordered by the L2 ----
+        float lr_grad = 0.0f, lr_gg = 0.0f, lr_old = 0.0f;
+        if (lr_ok) {
+            lr_grad = __fmul_rn(PHASE == 2 ? __ldg(dxr + tid) : g, lr_v);
+            lr_gg = __fmul_rn(lr_grad, lr_grad);
+            if (lr_grad != 0.0f && optimizer != OPT_SGD) lr_old = atomicAdd(reinterpret_cast<float *>(p.lr + lr_h) + 1, lr_gg);
         }
 
+        if (overlap) {
+            // ---- update_with_atomics: this record's rows share slots.  Chunk by chunk like the single-GPU kernels of round 1:
+            //      ATOMG.128 on the accumulators (returns the old value), step, REDG.128 on the weights; nothing is written in
+            //      place and nothing is bulk-reduced for this record. ----
+            const uint32_t cpr = Fk >> 2;
+            for (uint32_t idx = tid; idx < F * cpr; idx += 256) {
+                const uint32_t e = idx / cpr, c = idx - e * cpr, z = c / k4, q4 = c - z * k4;
+                const uint32_t sl = slots[e];
+                if (z == e || sl == 0x80000000u) continue; // own-field chunk: exactly zero gradient; absent field: no row
+                const float4 pv = *reinterpret_cast<const float4 *>(W + (size_t)z * RS + e * k + 4 * q4);
+                const float gz = PHASE == 2 ? __ldg(dxr + n_lr + tri_index(e, z)) : g;
+                const float4 gr = make_float4(__fmul_rn(gz, pv.x), __fmul_rn(gz, pv.y), __fmul_rn(gz, pv.z), __fmul_rn(gz, pv.w));
+                if (gr.x == 0.0f && gr.y == 0.0f && gr.z == 0.0f && gr.w == 0.0f) continue; // partner absent
+                const uint32_t addr = (sl & p.ffm_mask) + 4 * c;
+                float4 upd;
+                if (optimizer == OPT_SGD) upd = make_float4(-__fmul_rn(gr.x, p.ffm_lr), -__fmul_rn(gr.y, p.ffm_lr), -__fmul_rn(gr.z, p.ffm_lr), -__fmul_rn(gr.w, p.ffm_lr));
+                else {
+                    const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + addr), make_float4(__fmul_rn(gr.x, gr.x), __fmul_rn(gr.y, gr.y), __fmul_rn(gr.z, gr.z), __fmul_rn(gr.w, gr.w)));
+                    upd.x = -opt_step(optimizer, gr.x, acc_after(old.x, gr.x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.y = -opt_step(optimizer, gr.y, acc_after(old.y, gr.y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.z = -opt_step(optimizer, gr.z, acc_after(old.z, gr.z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.w = -opt_step(optimizer, gr.w, acc_after(old.w, gr.w), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                }
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + addr), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+            }
+        } else {
         // ---- update, in place: weights := -step, accumulators := g^2 (block_ffm.rs:265-288, optimizer.rs:147-156) ----
 #pragma unroll
         for (int j = 0; j < ROWS_MAXU; j++) {
@@ -1356,6 +1445,9 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
                     }
                     *qa = make_float4(g2a[0], g2a[1], g2a[2], g2a[3]);
                     *qb = make_float4(g2b[0], g2b[1], g2b[2], g2b[3]);
+                } else if (PUSH) {
+#pragma unroll
+                    for (int c = 0; c < 4; c++) { ua[c] = ga[c]; ub[c] = gb[c]; } // the owner takes the step (k_apply_inbox)
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; c++) { ua[c] = -__fmul_rn(ga[c], p.ffm_lr); ub[c] = -__fmul_rn(gb[c], p.ffm_lr); }
@@ -1364,39 +1456,101 @@ __global__ void __launch_bounds__(256, 2) k_learn_rows(const RowsParams p)
                 *pb = make_float4(ub[0], ub[1], ub[2], ub[3]);
             }
         }
-        // ---- LR update (block_lr.rs:135-151) from the cell gathered with the record: two fire-and-forget reductions ----
-        if (lr_ok) {
-            float *cell = reinterpret_cast<float *>(p.lr + lr_h);
-            const float grad = __fmul_rn(PHASE == 2 ? __ldg(dxr + tid) : g, lr_v);
-            if (grad != 0.0f) {
-                float upd;
-                if (optimizer == OPT_SGD) upd = __fmul_rn(grad, p.lr_lr);
-                else {
-                    const float gg = __fmul_rn(grad, grad);
-                    red_add_f32(cell + 1, gg);
-                    upd = opt_step(optimizer, grad, __fadd_rn(lr_cell.y, gg), p.lut_lr, p.lr_lr, p.lr_mpt);
-                }
-                red_add_f32(cell, -upd);
-            }
+        }
+        // ---- LR weights: step from the accumulator the atomic returned ----
+        if (lr_ok && lr_grad != 0.0f) {
+            const float upd = optimizer == OPT_SGD ? __fmul_rn(lr_grad, p.lr_lr) : opt_step(optimizer, lr_grad, __fadd_rn(lr_old, lr_gg), p.lut_lr, p.lr_lr, p.lr_mpt);
+            red_add_f32(reinterpret_cast<float *>(p.lr + lr_h), -upd);
         }
         // ---- scatter: the rewritten rows go back as bulk reductions, one per row piece and array ----
+        if (PUSH) {
+            // one inbox slot per present row, taken from this rank's counter for the owner (one atomic per owner and warp)
+            if (op_on && op_present) {
+                uint32_t owner = p.owner_shift >= 32 ? 0u : (h_row >> p.owner_shift);
+                if (owner >= p.world) owner = p.world - 1; // the spill-over tail lives on the last rank
+                const uint32_t peers = __match_any_sync(__activemask(), owner);
+                const uint32_t leader = __ffs(peers) - 1;
+                uint32_t base = 0;
+                if (lane == leader) base = atomicAdd(p.push_cnt + owner, (uint32_t)__popc(peers));
+                base = __shfl_sync(peers, base, leader);
+                const uint32_t slot_i = base + __popc(peers & ((1u << lane) - 1u));
+                uint32_t *hdr = reinterpret_cast<uint32_t *>(op_smem) - ROWS_HDR;
+                hdr[0] = h_row; hdr[1] = op_row; hdr[2] = 0; hdr[3] = 0;
+                push_dst = p.inbox + (size_t)owner * p.inbox_rank_stride + p.inbox_src_off + (size_t)slot_i * ((size_t)RS * 4);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (op_on && op_present) {
+                const uint32_t src = smem_u32(op_smem - ROWS_HDR);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(push_dst), "r"(src), "r"(RS * 4u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            continue;
+        }
+        if (overlap) { if (one_in_flight) __threadfence(); continue; } // uniform: this record went through the atomics
+        if (op_on && op_present) { // the own-field block of my row takes no update: it goes back as zeros
+            for (uint32_t q = 0; q < k4; q++) *reinterpret_cast<float4 *>(op_smem + op_row * k + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // my shared-memory writes are visible to the copy engine
         __syncthreads();
-        if (tid < F && !absent) {
-            float *wr = W + (size_t)tid * Fk;
-            if (b1) bulk_reduce_add(p.ffm_w + h_row, wr, b1);
-            if (b2) bulk_reduce_add(p.ffm_w + h_row + (tid + 1) * k, wr + (tid + 1) * k, b2);
-            if (has_acc) {
-                float *ar = A + (size_t)tid * Fk;
-                if (b1) bulk_reduce_add(p.ffm_acc + h_row, ar, b1);
-                if (b2) bulk_reduce_add(p.ffm_acc + h_row + (tid + 1) * k, ar + (tid + 1) * k, b2);
-            }
+        if (op_on && op_present) {
+            bulk_reduce_add(op_table + h_row, op_smem, Fk * 4u);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (one_in_flight) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // complete, not just read
         }
         if (one_in_flight) __threadfence(); // the LR reductions too, before the barrier at the top of the next iteration
     }
-    if (tid < F) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the reductions that read it
+    if (op_on) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the reductions that read it
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_apply_inbox: the OWNER's half of the sharded update.  Every entry of this rank's inbox is one gradient row
+// {row base, field, -, -, F*k floats} that some rank (this one included) computed for a row this rank owns; a warp takes an
+// entry and applies AdaGrad chunk by chunk exactly like the single-GPU kernels do (block_ffm.rs:265-288, optimizer.rs:147-156):
+// ATOMG.128 on the local accumulators (returns the old value), LUT step, REDG.128 on the local weights -- all in this GPU's
+// own L2; nothing but the 1.26 KB entry ever crossed NVLink.  The own-field block of an entry is skipped (zero gradient).
+// ---------------------------------------------------------------------------------------------
+struct ApplyParams {
+    const unsigned char *inbox_half;  // this rank's inbox, current half: [world][cap] entries of entry_bytes
+    const uint32_t *counts_all;       // [world][world] after the all-gather: counts_all[s * world + r] = entries rank s pushed to rank r
+    uint32_t world, rank, cap, entry_bytes;
+    uint32_t F, k, Fk;
+    float *ffm_w, *ffm_acc; const float *lut_ffm;
+    uint32_t optimizer; float ffm_lr, ffm_mpt;
+};
+__global__ void __launch_bounds__(256) k_apply_inbox(const ApplyParams p)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t cnt[16], total = 0;
+#pragma unroll
+    for (uint32_t s_ = 0; s_ < 16; s_++) { cnt[s_] = s_ < p.world ? min(__ldcg(p.counts_all + s_ * p.world + p.rank), p.cap) : 0u; total += cnt[s_]; }
+    const uint32_t cpr = p.Fk >> 2, k4 = p.k >> 2;
+    for (uint32_t idx = warp; idx < total; idx += n_warps) {
+        uint32_t s_ = 0, i = idx;
+#pragma unroll
+        for (uint32_t t = 0; t < 16; t++) if (s_ == t && i >= cnt[t]) { i -= cnt[t]; s_ = t + 1; }
+        const unsigned char *ent = p.inbox_half + ((size_t)s_ * p.cap + i) * p.entry_bytes;
+        const uint4 hdr = __ldcg(reinterpret_cast<const uint4 *>(ent));
+        const uint32_t h_row = hdr.x, e = hdr.y;
+        const float4 *gr4 = reinterpret_cast<const float4 *>(ent + 16);
+        for (uint32_t c0 = 0; c0 < cpr; c0 += 32) {
+            const uint32_t c = c0 + lane;
+            if (c >= cpr || c / k4 == e) continue; // own-field block: exactly zero gradient (block_ffm.rs:236-244)
+            const float4 gr = __ldcs(gr4 + c);
+            if (gr.x == 0.0f && gr.y == 0.0f && gr.z == 0.0f && gr.w == 0.0f) continue; // partner field absent
+            float4 upd;
+            if (p.optimizer == OPT_SGD) upd = make_float4(-__fmul_rn(gr.x, p.ffm_lr), -__fmul_rn(gr.y, p.ffm_lr), -__fmul_rn(gr.z, p.ffm_lr), -__fmul_rn(gr.w, p.ffm_lr));
+            else {
+                const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + h_row + 4 * c),
+                                             make_float4(__fmul_rn(gr.x, gr.x), __fmul_rn(gr.y, gr.y), __fmul_rn(gr.z, gr.z), __fmul_rn(gr.w, gr.w)));
+                upd.x = -opt_step(p.optimizer, gr.x, acc_after(old.x, gr.x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                upd.y = -opt_step(p.optimizer, gr.y, acc_after(old.y, gr.y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                upd.z = -opt_step(p.optimizer, gr.z, acc_after(old.z, gr.z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                upd.w = -opt_step(p.optimizer, gr.w, acc_after(old.w, gr.w), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+            }
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + h_row + 4 * c), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

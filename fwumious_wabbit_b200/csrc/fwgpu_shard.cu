@@ -3,6 +3,8 @@
 
 #include <chrono>
 #include <cstring>
+#include <dlfcn.h>
+#include <nccl.h>
 #include <poll.h>
 #include <sys/socket.h>
 #include <sys/stat.h>
@@ -133,7 +135,32 @@ static int connect_retry(const std::string &path, uint32_t timeout_ms)
     }
 }
 
-enum { REQ_FD = 1, REQ_BARRIER = 2 };
+enum { REQ_FD = 1, REQ_BARRIER = 2, REQ_BLOB = 3 };
+
+// ---- NCCL, resolved at run time: libfwgpu.so loads (and every single-GPU entry point works) on machines without libnccl ----
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+    std::string err;
+    NcclApi()
+    {
+        void *h = nullptr;
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) if ((h = dlopen(name, RTLD_NOW | RTLD_GLOBAL))) break;
+        if (!h) { err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        auto get = [&](const char *n, void **fn) { *fn = dlsym(h, n); if (!*fn) err = std::string("libnccl lacks ") + n; return *fn != nullptr; };
+        ok = get("ncclGetUniqueId", (void **)&GetUniqueId) && get("ncclCommInitRank", (void **)&CommInitRank) && get("ncclAllGather", (void **)&AllGather) &&
+             get("ncclCommDestroy", (void **)&CommDestroy) && get("ncclGetErrorString", (void **)&GetErrorString);
+    }
+};
+static NcclApi &nccl()
+{
+    static NcclApi a;
+    return a;
+}
 
 static void serve_connection(ShardGroup *g, int s)
 {
@@ -149,6 +176,12 @@ static void serve_connection(ShardGroup *g, int s)
             const int fd = (arr && arr->own_fd >= 0) ? ::dup(arr->own_fd) : -1;
             lk.unlock();
             if (fd >= 0) { send_fd(s, fd); ::close(fd); }
+        } else if (req[0] == REQ_BLOB) {
+            const bool ready = g->cv.wait_until(lk, deadline, [&] { return g->stop.load() || g->blobs.count(req[1]); });
+            const std::string data = (ready && !g->stop.load()) ? g->blobs[req[1]] : std::string();
+            lk.unlock();
+            const uint32_t len = (uint32_t)data.size();
+            if (send_all(s, &len, 4) && len) send_all(s, data.data(), len);
         } else if (req[0] == REQ_BARRIER) {
             const bool ready = g->cv.wait_until(lk, deadline, [&] { return g->stop.load() || g->phase >= req[1]; });
             lk.unlock();
@@ -205,6 +238,7 @@ bool ShardGroup::start(uint32_t rank_, uint32_t world_, int device_, const char 
 
 ShardGroup::~ShardGroup()
 {
+    if (nccl_comm && nccl().ok) { nccl().CommDestroy((ncclComm_t)nccl_comm); nccl_comm = nullptr; }
     {
         std::lock_guard<std::mutex> lk(mu);
         stop.store(true);
@@ -302,6 +336,59 @@ void ShardGroup::destroy_array(ShardedArray &a)
     for (auto h : a.handles) if (h) d.MemRelease(h);
     a.handles.clear();
     if (a.own_fd >= 0) { ::close(a.own_fd); a.own_fd = -1; }
+}
+
+void ShardGroup::publish_blob(uint32_t id, const std::string &data)
+{
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        blobs[id] = data;
+    }
+    cv.notify_all();
+}
+
+bool ShardGroup::fetch_blob(uint32_t from_rank, uint32_t id, std::string &out)
+{
+    int sock = connect_retry(prefix + "." + std::to_string(from_rank), timeout_ms);
+    if (sock < 0) { error = "cannot reach rank " + std::to_string(from_rank); return false; }
+    const uint32_t req[2] = {REQ_BLOB, id};
+    uint32_t len = 0;
+    bool ok = send_all(sock, req, sizeof(req)) && recv_all(sock, &len, 4, (int)timeout_ms) && len > 0 && len < (1u << 20);
+    if (ok) { out.resize(len); ok = recv_all(sock, &out[0], len, (int)timeout_ms); }
+    ::close(sock);
+    if (!ok) error = "rank " + std::to_string(from_rank) + " did not publish blob " + std::to_string(id);
+    return ok;
+}
+
+bool ShardGroup::comm_init()
+{
+    if (nccl_comm) return true;
+    NcclApi &n = nccl();
+    if (!n.ok) { error = n.err; return false; }
+    ncclUniqueId id;
+    if (rank == 0) {
+        ncclResult_t r = n.GetUniqueId(&id);
+        if (r != ncclSuccess) { error = std::string("ncclGetUniqueId: ") + n.GetErrorString(r); return false; }
+        publish_blob(1, std::string((const char *)&id, sizeof(id)));
+    } else {
+        std::string blob;
+        if (!fetch_blob(0, 1, blob) || blob.size() != sizeof(id)) { if (error.empty()) error = "bad NCCL id blob"; return false; }
+        memcpy(&id, blob.data(), sizeof(id));
+    }
+    ncclComm_t comm = nullptr;
+    ncclResult_t r = n.CommInitRank(&comm, (int)world, id, (int)rank);
+    if (r != ncclSuccess) { error = std::string("ncclCommInitRank: ") + n.GetErrorString(r); return false; }
+    nccl_comm = comm;
+    return true;
+}
+
+bool ShardGroup::all_gather_u32(const uint32_t *send_dev, uint32_t *recv_dev, uint32_t count_per_rank, cudaStream_t stream)
+{
+    NcclApi &n = nccl();
+    if (!nccl_comm) { error = "NCCL communicator not initialised"; return false; }
+    ncclResult_t r = n.AllGather(send_dev, recv_dev, count_per_rank, ncclUint32, (ncclComm_t)nccl_comm, stream);
+    if (r != ncclSuccess) { error = std::string("ncclAllGather: ") + n.GetErrorString(r); return false; }
+    return true;
 }
 
 bool ShardGroup::barrier()

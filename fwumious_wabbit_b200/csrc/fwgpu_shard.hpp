@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -53,6 +54,8 @@ struct ShardGroup {
     std::condition_variable cv;
     uint64_t phase = 0;                // barrier phases this rank has reached
     int active_workers = 0;            // request threads in flight (guarded by mu)
+    std::map<uint32_t, std::string> blobs; // small byte strings this rank publishes to its peers (the NCCL unique id)
+    void *nccl_comm = nullptr;         // ncclComm_t over the group's ranks (libnccl is loaded at run time)
     std::string error;
 
     ~ShardGroup();
@@ -60,6 +63,13 @@ struct ShardGroup {
     bool create_array(ShardedArray &a, const std::vector<size_t> &sizes);
     bool barrier();
     void destroy_array(ShardedArray &a);
+    // NCCL communicator over the ranks of the group (collective; the unique id travels over the rendezvous sockets).  Used for
+    // the one exchange step of the sharded learn path: an all-gather of the per-owner push counts after every chunk, which is
+    // also the barrier between "every rank has pushed its gradient rows" and "owners apply them".
+    bool comm_init();
+    bool all_gather_u32(const uint32_t *send_dev, uint32_t *recv_dev, uint32_t count_per_rank, cudaStream_t stream);
+    void publish_blob(uint32_t id, const std::string &data);
+    bool fetch_blob(uint32_t from_rank, uint32_t id, std::string &out);
     size_t round_up(size_t bytes) const { return (bytes + granularity - 1) / granularity * granularity; }
 };
 

@@ -130,14 +130,25 @@ typedef struct fwgpu_dataset fwgpu_dataset; /* records resident in HBM */
  * allocates the tables in HBM and initialises them like the reference (LR zeros block_lr.rs:97-105,
  * FFM merand48 block_ffm.rs:784-829), builds the AdaGrad look-up tables (optimizer.rs:121-144). */
 fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **out);
-/* The same regressor with its LR / FFM tables hash-range-sharded over the GPUs of one NVLink/NVSwitch box (BASELINE config 4).
- * One process per GPU calls this collectively (rank in [0, world)); the reference's counterpart is the single table all
- * Hogwild workers share (hogwild.rs:24-103).  Rank r owns indices [r*len/world, (r+1)*len/world) (+ the spill-over tail
- * of block_ffm.rs:93-94 on the last rank); every rank maps all ranges into one contiguous virtual range (CUDA VMM +
- * POSIX fd exchange over the unix sockets "<rendezvous>.<rank>"), so the learn kernels address remote rows like local
- * ones: gathers and AdaGrad atomics travel over NVLink to the owner's L2 inside the fused kernel.  Every other entry
- * point works unchanged on such a ctx; fwgpu_import_block is collective (each rank writes the range it owns).
- * Tables too small to split into whole allocation granules live on rank 0.  timeout_ms 0 = 60 s. */
+/* The same regressor as ONE model over the GPUs of one NVLink/NVSwitch box (BASELINE config 4): the LR / FFM tables are
+ * hash-range-sharded, rank r owning indices [r*len/world, (r+1)*len/world) (+ the spill-over tail of block_ffm.rs:93-94 on
+ * the last rank).  One process per GPU calls this collectively (rank in [0, world)); the reference's counterpart is the
+ * single table all Hogwild workers share (hogwild.rs:24-103).  It takes the place of SURVEY 8b's
+ * fwgpu_comm_init(ncclUniqueId, rank, nranks): the ranks rendezvous over the unix sockets "<rendezvous>.<rank>" (owner-only),
+ * exchange their shards' memory handles (CUDA VMM, POSIX fds) and the NCCL unique id there, and map all ranges into one
+ * virtual range, so a row has the same address on every rank.
+ *   - predict, and training with one record in flight (parity mode): rows are pulled from the owner's HBM by bulk copies over
+ *     NVLink inside the learn kernel; parity-mode updates go back as bulk reductions applied by the owner's L2;
+ *   - training (wide models: the bulk-copy kernel): every rank pulls the rows its records need, computes, and PUSHES each
+ *     row's gradient (1.26 KB, one bulk store) into the owner's inbox; after every chunk of records (default 8192 per rank)
+ *     ONE exchange step -- an NCCL all-gather of the per-owner entry counts, which is also the barrier -- and the owners
+ *     apply AdaGrad from their own accumulators (owner-side update, no remote atomics).  These calls are COLLECTIVE: every
+ *     rank must pass the same number of examples to fwgpu_learn_records / fwgpu_dataset_learn(update = 1);
+ *   - narrow models (warp-per-record kernel) keep addressing remote rows directly (remote 128-bit loads / atomics).
+ * Every other entry point works unchanged on such a ctx; fwgpu_import_block is collective (each rank writes the range it
+ * owns); call fwgpu_shard_barrier before fwgpu_export_block so that every owner has applied what it was sent.
+ * Fails with FWGPU_ERR_NCCL when libnccl.so.2 cannot be loaded.  Tables too small to split into whole allocation granules
+ * live on rank 0.  timeout_ms 0 = 60 s. */
 fwgpu_status fwgpu_create_sharded(const fwgpu_model_desc *desc, int device, uint32_t rank, uint32_t world,
                                   const char *rendezvous, uint32_t timeout_ms, fwgpu_ctx **out);
 /* fwgpu_sync + wait until every rank of the shard group has done the same (no-op group of one for unsharded ctxs). */

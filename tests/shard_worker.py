@@ -80,6 +80,61 @@ def main():
         single.close()
     sh.shard_barrier()
     sh.close()
+
+    # D. WIDE model (config 3's shape: 39 fields x k = 8): the bulk-copy kernel.  Rows are pulled from their owners over NVLink;
+    #    D1 one record in flight (direct mode: gradient rows go back as bulk reductions into the owner's L2), last rank alone;
+    #    D2 every rank trains its slice of one stream on the ONE model: gradient rows are pushed to the owners' inboxes, one
+    #       NCCL all-gather per chunk, owners apply AdaGrad (k_learn_rows<PUSH> + k_apply_inbox).
+    os.environ["FWGPU_SHARD_CHUNK"] = "2048"
+    wd = synth.workload("c3")
+    wd.mi.hogwild_max_inflight = 1
+    n1 = 400
+    recs_d = wd.records(n1)
+    sh = fw.Regressor(wd.mi, device=rank, shard=(rank, world, prefix + ".d1"))
+    if rank == world - 1:
+        single = fw.Regressor(wd.mi, device=rank)
+        out["wide_seq_sharded"] = sh.learn_records(recs_d.reshape(-1), n_examples=n1, update=True)
+        out["wide_seq_single"] = single.learn_records(recs_d.reshape(-1), n_examples=n1, update=True)
+        sh.sync()
+        sw, sa = sh.get_ffm(); uw, ua = single.get_ffm()
+        out["wide_seq_tables_equal"] = np.array([np.array_equal(sw, uw), np.array_equal(sa, ua), np.array_equal(sh.get_lr_table(), single.get_lr_table())])
+        out["wide_seq_paths"] = np.array([sh.path_counts()["fixed_cta"], sh.path_counts()["general_examples"]])
+        single.close()
+    sh.shard_barrier()
+    sh.close()
+
+    n_per = int(os.environ.get("FWGPU_TEST_SHARD_N", "40000"))
+    we = synth.workload("c3")
+    mine = we.records(n_per, first=rank * n_per)
+    sh = fw.Regressor(we.mi, device=rank, shard=(rank, world, prefix + ".d2"))
+    sh.shard_barrier()
+    t = time.time()
+    out["wide_hog_preds"] = sh.learn_records(mine.reshape(-1), n_examples=n_per, update=True)
+    sh.shard_barrier()
+    out["wide_hog_secs"] = np.array([time.time() - t])
+    out["wide_hog_labels"] = (mine[:, 1] == 1).astype(np.float32)
+    out["wide_hog_paths"] = np.array([sh.path_counts()["fixed_cta"], sh.path_counts()["general_examples"]])
+    # a second, warm pass for a throughput figure, then the tables as every rank sees them
+    more = we.records(n_per, first=(world + rank) * n_per)
+    sh.shard_barrier()
+    t = time.time()
+    sh.learn_records(more.reshape(-1), n_examples=n_per, update=True, want_preds=False)
+    sh.shard_barrier()
+    out["wide_hog_secs2"] = np.array([time.time() - t])
+    w_all, a_all = sh.get_ffm()
+    import hashlib
+    out["wide_tables_digest"] = np.frombuffer(hashlib.sha256(w_all.tobytes() + a_all.tobytes()).digest(), dtype=np.uint8)
+    out["wide_acc_touched"] = np.array([int(np.count_nonzero(a_all)), int(np.all(np.isfinite(w_all))), int(np.all(a_all >= 0))])
+    if rank == 0:
+        single = fw.Regressor(synth.workload("c3").mi, device=0)
+        allrecs = we.records(2 * world * n_per)
+        out["wide_single_preds"] = single.learn_records(allrecs[:world * n_per].reshape(-1), n_examples=world * n_per, update=True)
+        single.learn_records(allrecs[world * n_per:].reshape(-1), n_examples=world * n_per, update=True, want_preds=False)
+        _, a1 = single.get_ffm()
+        out["wide_single_touched_equal"] = np.array([int(np.array_equal(a1 != 0, a_all != 0)), int(np.count_nonzero(a1))])
+        single.close()
+    sh.shard_barrier()
+    sh.close()
     np.savez(os.path.join(outdir, f"rank{rank}.npz"), **out)
     print(f"rank {rank} done", flush=True)
 

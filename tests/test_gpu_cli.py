@@ -186,22 +186,23 @@ def test_cli_testonly_save_writes_a_loadable_inference_file(tmp_path):
 
 def test_cli_prediction_model_delay(tmp_path):
     """--prediction_model_delay D (main.rs:200-258): example i is scored by a model that has not seen the last D examples.
-    With D >= the file every prediction comes from the initial model; with a small D the model still learns."""
+    With D >= the file every prediction comes from the initial model; with a small D the model scores almost as well as
+    the up-to-date one."""
     d = str(tmp_path)
-    generate(d, n_train=3000, n_eval=10)
-    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B".split()
-    rest = "-l 0.1 -b 18 --ffm_bit_precision 18 --adaptive --sgd".split()
-    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_all.txt", "--prediction_model_delay", "5000"])
+    generate(d, n_train=20000, n_eval=10)
+    ns = "--keep A --keep B --interactions AB --ffm_k 10 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 -b 25 --sgd --power_t 0.0 --noconstant".split()
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_all.txt", "--prediction_model_delay", "50000"])
     run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_t.txt", "-t"])
     assert open(f"{d}/p_all.txt").read() == open(f"{d}/p_t.txt").read()
-    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_50.txt", "--prediction_model_delay", "50", "--sequential"])
-    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_0.txt", "--sequential"])
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_50.txt", "--prediction_model_delay", "50"])
+    run(ns + rest + ["--data", f"{d}/train.vw", "-p", f"{d}/p_0.txt"])
     y = labels_of(f"{d}/train.vw")
 
     def ll(path):
-        p = np.loadtxt(path)
-        assert len(p) == 3000
-        return -np.mean(np.where(y[1500:] == 1, np.log(p[1500:]), np.log(1 - p[1500:])))
+        p = np.clip(np.loadtxt(path), 1e-6, 1 - 1e-6)
+        assert len(p) == 20000
+        return -np.mean(np.where(y[10000:] == 1, np.log(p[10000:]), np.log(1 - p[10000:])))
 
-    # a model that lags 50 examples behind scores almost as well as the up-to-date one, and better than the untrained one
-    assert ll(f"{d}/p_50.txt") < ll(f"{d}/p_t.txt") and abs(ll(f"{d}/p_50.txt") - ll(f"{d}/p_0.txt")) / ll(f"{d}/p_0.txt") < 0.05
+    assert ll(f"{d}/p_0.txt") < ll(f"{d}/p_t.txt") - 0.05                       # training helps on this stream ...
+    assert abs(ll(f"{d}/p_50.txt") - ll(f"{d}/p_0.txt")) < 0.03, (ll(f"{d}/p_50.txt"), ll(f"{d}/p_0.txt"))  # ... and a 50-example lag costs little

@@ -25,13 +25,13 @@ def _n_gpus():
 
 
 @pytest.mark.skipif(_n_gpus() < 2, reason="needs two GPUs")
-def test_sharded_table_two_gpus():
-    world = 2
+@pytest.mark.parametrize("world", [2] + ([8] if _n_gpus() >= 8 else []))
+def test_sharded_table(world):
     with tempfile.TemporaryDirectory() as d:
         prefix = os.path.join(d, "rv")
         procs = [subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "shard_worker.py"), str(r), str(world), prefix, d],
                                   stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(world)]
-        outs = [p.communicate(timeout=600)[0] for p in procs]
+        outs = [p.communicate(timeout=900)[0] for p in procs]
         for r, p in enumerate(procs):
             assert p.returncode == 0, f"rank {r} failed:\n{outs[r][-3000:]}"
         res = [np.load(os.path.join(d, f"rank{r}.npz")) for r in range(world)]
@@ -53,3 +53,29 @@ def test_sharded_table_two_gpus():
     assert abs(ll_sh - ll_1) / ll_1 < 0.01, (ll_sh, ll_1)
     rate = sum(len(res[r]["hog_preds"]) for r in range(world)) / max(float(res[r]["hog_secs2"][0]) for r in range(world))
     print(f"sharded x{world}: logloss {ll_sh:.4f} vs single {ll_1:.4f}; warm pass {rate / 1e6:.1f} M examples/s (wall clock, small batch)")
+    # D1. wide model, one record in flight through the bulk-copy kernel over remote memory: bit-exact with the unsharded run
+    assert np.array_equal(last["wide_seq_sharded"].view(np.uint32), last["wide_seq_single"].view(np.uint32))
+    assert last["wide_seq_tables_equal"].all(), last["wide_seq_tables_equal"]
+    assert last["wide_seq_paths"][0] > 0 and last["wide_seq_paths"][1] == 0
+    # D2. wide model, every rank trains its slice on ONE model through the owner-side update path
+    from fwumious_wabbit_b200 import synth
+
+    n_per = len(res[0]["wide_hog_preds"])
+    p = np.concatenate([res[r]["wide_hog_preds"] for r in range(world)])
+    y = np.concatenate([res[r]["wide_hog_labels"] for r in range(world)])
+    for r in range(world):
+        assert res[r]["wide_hog_paths"][0] > 0 and res[r]["wide_hog_paths"][1] == 0
+        assert np.array_equal(res[r]["wide_tables_digest"], res[0]["wide_tables_digest"])   # one model: every rank reads the same tables
+        assert res[r]["wide_acc_touched"][1] == 1 and res[r]["wide_acc_touched"][2] == 1
+    # every gradient row reached its owner and its slot: exactly the slots a single GPU touches on the same stream
+    assert res[0]["wide_single_touched_equal"][0] == 1, (res[0]["wide_single_touched_equal"], res[0]["wide_acc_touched"])
+    ll_sh = util.logloss(p, y)
+    ll_1 = util.logloss(res[0]["wide_single_preds"], y)
+    w = synth.workload("c3")
+    recs = w.records(world * n_per)
+    ora = util.oracle_regressor(w.mi)
+    _, want = ora.hogwild(util.oracle_spec(w.mi), recs.reshape(-1), np.arange(world * n_per + 1, dtype=np.uint64) * w.record_len, 1, want_preds=True)
+    ll_o = util.logloss(want, y)
+    rate = world * n_per / max(float(res[r]["wide_hog_secs2"][0]) for r in range(world))
+    print(f"wide sharded x{world}: logloss {ll_sh:.4f} vs single GPU {ll_1:.4f} vs sequential oracle {ll_o:.4f}; warm pass {rate / 1e6:.2f} M examples/s (wall clock)")
+    assert abs(ll_sh - ll_o) / ll_o < 0.02 and abs(ll_sh - ll_1) / ll_1 < 0.02, (ll_sh, ll_1, ll_o)

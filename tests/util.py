@@ -120,3 +120,19 @@ def sync_tables_from_oracle(gpu_reg, ora):
             gpu_reg.import_block(_lib.BLOCK_NN0 + l, np.concatenate([ora.nn_weights(l), ora.nn_acc(l)]), True)
         else:
             gpu_reg.import_block(_lib.BLOCK_NN0 + l, ora.nn_weights(l).copy(), False)
+
+
+def sync_oracle_from_gpu(ora, gpu_reg):
+    """Load the GPU regressor's current tables (weights and optimizer state) into the oracle."""
+    from fwumious_wabbit_b200 import _lib
+
+    ora.lr_table[:, :] = gpu_reg.get_lr_table()
+    n, _ = gpu_reg.block_len(_lib.BLOCK_FFM)
+    if n:
+        w, acc = gpu_reg.get_ffm()
+        ora.ffm_weights[:] = w
+        ora.ffm_acc[:] = acc
+    for l in range(ora.nn_layer_count):
+        w, acc = gpu_reg.get_nn(l)
+        ora.nn_weights(l)[:] = w
+        ora.nn_acc(l)[:] = acc
