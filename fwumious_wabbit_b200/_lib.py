@@ -73,6 +73,8 @@ def lib():
     L.fwgpu_create.argtypes = [C.POINTER(ModelDesc), C.c_int, C.POINTER(vp)]
     L.fwgpu_create_sharded.argtypes = [C.POINTER(ModelDesc), C.c_int, C.c_uint32, C.c_uint32, C.c_char_p, C.c_uint32, C.POINTER(vp)]
     L.fwgpu_create_sharded.restype = C.c_int32
+    L.fwgpu_debug_shard_plan.argtypes = [C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, vp, vp]
+    L.fwgpu_debug_shard_plan.restype = C.c_int32
     L.fwgpu_shard_barrier.argtypes = [vp]
     L.fwgpu_shard_barrier.restype = C.c_int32
     L.fwgpu_shard_info.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
@@ -120,7 +122,7 @@ def lib():
 
 # every symbol include/fwgpu.h declares (checked by tests/test_abi.py without a GPU)
 EXPORTED_SYMBOLS = [
-    "fwgpu_create", "fwgpu_create_sharded", "fwgpu_shard_barrier", "fwgpu_shard_info", "fwgpu_destroy", "fwgpu_last_error", "fwgpu_sync", "fwgpu_stream", "fwgpu_launch_count",
+    "fwgpu_create", "fwgpu_create_sharded", "fwgpu_debug_shard_plan", "fwgpu_shard_barrier", "fwgpu_shard_info", "fwgpu_destroy", "fwgpu_last_error", "fwgpu_sync", "fwgpu_stream", "fwgpu_launch_count",
     "fwgpu_learn_batch", "fwgpu_predict_batch", "fwgpu_learn_records", "fwgpu_translate_records",
     "fwgpu_dataset_upload", "fwgpu_dataset_learn", "fwgpu_dataset_free",
     "fwgpu_block_len", "fwgpu_export_block", "fwgpu_import_block", "fwgpu_get_lut",

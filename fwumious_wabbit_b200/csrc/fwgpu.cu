@@ -117,7 +117,7 @@ struct fwgpu_ctx {
     uint64_t n_fixed = 0, n_fixed_cta = 0, n_general = 0; // launches per learn-kernel family (fwgpu_debug_path_counts)
     unsigned long long *stat_general_examples = nullptr;  // device: examples the general kernel handled
     uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
-    uint32_t ramp_div = 32;
+    uint32_t ramp_div = 256;
     uint32_t max_inflight = 0; // 0 = unlimited
     bool ramp_finished = false;
     bool profiling = false;
@@ -150,7 +150,7 @@ struct fwgpu_ctx {
     uint32_t shard_chunk = 8192, inbox_cap = 0, owner_shift = 32;
     uint64_t inbox_rank_bytes = 0, shard_chunks_done = 0;
     uint32_t *push_cnt = nullptr, *counts_all[2] = {nullptr, nullptr};
-    bool shard_overlap = true;
+    bool shard_overlap = false; // apply kernel on a side stream, overlapping the next chunk's push kernel (FWGPU_SHARD_OVERLAP=1)
     cudaStream_t apply_stream = nullptr;
     cudaEvent_t ev_gathered[2]{}, ev_applied[2]{};
     bool ev_applied_rec[2] = {false, false};
@@ -488,7 +488,10 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     }
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
     if (const char *t = getenv("FWGPU_MINB")) c->minb = atoi(t);
-    c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 32;
+    // 256: measured on config 2 (profiles/r02_c2_ramp_sweep.txt): progressive logloss on 10^7 examples is 2.1 % above the
+    // sequential learner's with 32, 0.4 % with 64, 0.2 % with 128, 0.08 % with 256; the ramp then ends after ~3.6 M examples
+    // (c2) / 76 K examples (c3), a few milliseconds of reduced concurrency once per model
+    c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 256;
     if (const char *t = getenv("FWGPU_RAMP_DIV")) c->ramp_div = (uint32_t)strtoul(t, nullptr, 10);
     {
         const bool constant_step = c->optimizer == FWGPU_OPT_SGD || d.power_t == 0.0f || (d.ffm_k > 0 && d.ffm_power_t == 0.0f);
@@ -557,6 +560,24 @@ extern "C" fwgpu_status fwgpu_create_sharded(const fwgpu_model_desc *desc, int d
     if (!rendezvous || world == 0 || rank >= world) { g_create_error = "bad shard arguments"; return FWGPU_ERR_INVALID; }
     ShardCfg sc{rank, world, rendezvous, timeout_ms};
     return create_common(desc, device, &sc, out);
+}
+
+// Pure layout arithmetic of the sharded tables (no GPU needed; tests/test_dist_cpu.py): how a table of `bytes` (+ `tail_bytes` after
+// its last element) splits over `world` ranks at allocation granularity `granularity`, and the shift that maps a float index
+// to its owner (32 = everything on rank 0).
+extern "C" fwgpu_status fwgpu_debug_shard_plan(uint64_t bytes, uint64_t tail_bytes, uint32_t world, uint64_t granularity, uint64_t *sizes_out, uint32_t *owner_shift_out)
+{
+    if (!sizes_out || world == 0 || granularity == 0) return FWGPU_ERR_INVALID;
+    std::vector<size_t> sizes;
+    shard_plan((size_t)bytes, (size_t)tail_bytes, world, (size_t)granularity, sizes);
+    for (uint32_t i = 0; i < world; i++) sizes_out[i] = sizes[i];
+    if (owner_shift_out) {
+        const uint64_t shard_floats = world > 1 && sizes[1] ? sizes[0] / 4 : 0;
+        uint32_t sh = 32;
+        if (shard_floats && (shard_floats & (shard_floats - 1)) == 0) { sh = 0; while ((1ull << sh) < shard_floats) sh++; }
+        *owner_shift_out = sh;
+    }
+    return FWGPU_OK;
 }
 
 extern "C" fwgpu_status fwgpu_shard_barrier(fwgpu_ctx *c)
@@ -714,7 +735,7 @@ static fwgpu_status make_learn_params(fwgpu_ctx *c, uint32_t n_cap, int update, 
     p.div_cpr = make_fastdiv(std::max<uint32_t>(c->cpr, 1)); p.div_k = make_fastdiv(std::max<uint32_t>(c->k, 1)); p.div_F = make_fastdiv(std::max<uint32_t>(c->F, 1));
     p.optimizer = c->optimizer;
     p.lr_lr = c->d.learning_rate; p.lr_mpt = -c->d.power_t; p.ffm_lr = c->d.ffm_learning_rate; p.ffm_mpt = -c->d.ffm_power_t;
-    p.update = update; p.err_flag = c->err_flag; p.stat_examples = c->stat_general_examples;
+    p.update = update; p.err_flag = c->err_flag; p.stat_examples = c->stat_general_examples; p.sys_scope = c->shard ? 1 : 0;
     p.simple_update = 1; // measured on B200 (c3): one chunk at a time with 4 blocks/SM beats rounds of four with 3
     if (const char *t = getenv("FWGPU_SIMPLE_UPDATE")) p.simple_update = atoi(t);
     p.kv = (c->k == 0 || c->k % std::max<uint32_t>(c->VEC, 1) == 0) ? 1 : 0;
@@ -796,9 +817,16 @@ static fwgpu_status launch_learn(fwgpu_ctx *c, uint32_t n_examples, uint32_t n_c
 }
 
 // ---- fused fast path (k_learn_fixed) -----------------------------------------------------------
+template <int G, int NCH, int NLR, int OPTK, bool PARITY> static cudaError_t launch_fixed_kp(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups);
 template <int G, int NCH, int NLR, int OPTK> static cudaError_t launch_fixed_k(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups)
 {
-    auto kern = k_learn_fixed<G, NCH, NLR, OPTK>;
+    // one record in flight (update mode): the parity instantiation (tape-order sum, fences, ordered LR duplicates)
+    if (p.max_groups == 1 && p.update) return launch_fixed_kp<G, NCH, NLR, OPTK, true>(c, p, full_groups);
+    return launch_fixed_kp<G, NCH, NLR, OPTK, false>(c, p, full_groups);
+}
+template <int G, int NCH, int NLR, int OPTK, bool PARITY> static cudaError_t launch_fixed_kp(fwgpu_ctx *c, const FixedParams &p, uint32_t *full_groups)
+{
+    auto kern = k_learn_fixed<G, NCH, NLR, OPTK, PARITY>;
     constexpr int NW = FIXED_WARPS, RPW = 32 / G;
     const size_t smem = (size_t)p.rec_smem_floats * 4 * NW * RPW; // the records' row transposes
     cudaError_t e0 = ensure_dyn_smem(c, kern, smem);
@@ -875,7 +903,7 @@ static RowsParams rows_params(const fwgpu_ctx *c, const FixedCtaParams &q)
     r.optimizer = q.optimizer; r.lr_lr = q.lr_lr; r.lr_mpt = q.lr_mpt; r.ffm_lr = q.ffm_lr; r.ffm_mpt = q.ffm_mpt;
     r.update = q.update; r.preds = q.preds; r.leftover_idx = q.leftover_idx; r.leftover_cnt = q.leftover_cnt; r.max_groups = q.max_groups;
     r.io = q.io;
-    (void)c;
+    r.sys_scope = c->shard ? 1 : 0;
     return r;
 }
 template <int PHASE, int OPTK, bool PUSH> static cudaError_t launch_rows_k(fwgpu_ctx *c, const RowsParams &p, uint32_t *full_groups);
@@ -940,8 +968,11 @@ static fwgpu_status shard_push_chunk(fwgpu_ctx *c, RowsParams rp, uint32_t *full
     ap.counts_all = c->counts_all[half]; ap.world = g.world; ap.rank = g.rank; ap.cap = c->inbox_cap; ap.entry_bytes = (uint32_t)entry_bytes;
     ap.F = c->F; ap.k = c->k; ap.Fk = c->Fk; ap.ffm_w = c->ffm_w; ap.ffm_acc = c->ffm_acc; ap.lut_ffm = c->lut_dev + FWGPU_LUT_SIZE;
     ap.optimizer = c->optimizer; ap.ffm_lr = c->d.ffm_learning_rate; ap.ffm_mpt = -c->d.ffm_power_t;
-    k_apply_inbox<<<c->num_sms * (c->shard_overlap ? 1 : 4), 256, 0, as>>>(ap);
-    c->launches++;
+    static const int apply_blocks_env = getenv("FWGPU_SHARD_APPLY_BLOCKS") ? atoi(getenv("FWGPU_SHARD_APPLY_BLOCKS")) : 0;
+    if (!getenv("FWGPU_SHARD_NO_APPLY")) { // (diagnostic: time the push side alone)
+        k_apply_inbox<<<c->num_sms * (apply_blocks_env > 0 ? apply_blocks_env : (c->shard_overlap ? 1 : 4)), 256, 0, as>>>(ap);
+        c->launches++;
+    }
     CUDA_TRY(c, cudaGetLastError());
     if (c->shard_overlap) { CUDA_TRY(c, cudaEventRecord(c->ev_applied[half], as)); c->ev_applied_rec[half] = true; }
     c->shard_chunks_done++;
@@ -1329,6 +1360,7 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
         fp.optimizer = c->optimizer; fp.lr_lr = c->d.learning_rate; fp.lr_mpt = -c->d.power_t; fp.ffm_lr = c->d.ffm_learning_rate; fp.ffm_mpt = -c->d.ffm_power_t;
         fp.update = update; fp.preds = (float *)c->preds.p; fp.leftover_idx = left_idx; fp.leftover_cnt = left_cnt;
         fp.rec_smem_floats = c->F * (fp.cpr + 1) * 4;
+        fp.sys_scope = c->shard ? 1 : 0;
         uint32_t done = 0;
         while (done < count) {
             uint32_t cnt = count - done, cap = 0;

@@ -84,6 +84,7 @@ struct LearnParams {
     int exact_order;        // sum the sigmoid inputs in the reference's tape order (one example in flight: parity mode)
     int phase;              // 0 = fused single pass; 1 / 2 = the two passes around a dense head (HeadIO)
     HeadIO io;
+    int sys_scope;          // tables span several GPUs (fwgpu_create_sharded): parity-mode fences must reach the peers' memory
     unsigned long long *stat_examples; // += examples this launch handles (fwgpu_debug_path_counts: which kernel did the work)
 };
 
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(256, MINB) k_learn(const LearnParams p)
         }
         // Parity mode: the next example must see this one's weight reductions (REDG is fire-and-forget; without the
         // fence its gather can overtake them).  Hogwild mode tolerates that staleness by design.
-        if (p.exact_order) __threadfence();
+        if (p.exact_order) { if (p.sys_scope) __threadfence_system(); else __threadfence(); }
         group_sync<T>(gib); // C / meta are reused by the next example
     }
 }
@@ -613,6 +614,7 @@ struct FixedParams {
     uint32_t *leftover_idx, *leftover_cnt;
     uint32_t max_groups;
     uint32_t rec_smem_floats;      // F * (cpr + 1) * 4: the transpose area of one record
+    int sys_scope;                 // sharded tables: parity-mode fences at system scope
 };
 
 // Block = FIXED_WARPS independent warps, one record per G-lane group and round; nothing is exchanged between groups.
@@ -671,7 +673,11 @@ __device__ __noinline__ float tape_order_ffm_sum(float ws, const float4 *S, uint
 //       every wait for L2 covers two records);
 // NCH : 16-byte chunks per lane (ceil(F*F*k/4 / G));  NLR : LR entries per lane (ceil((combos + constant) / G));
 // OPTK: the optimizer as a compile-time constant (OPT_LUT: no powf code, no optimizer branches) or -1 = p.optimizer
-template <int G, int NCH, int NLR, int OPTK>
+// PARITY: the instantiation for ONE record in flight (p.max_groups == 1, hogwild_max_inflight = 1): the same translate / gather /
+//       gradient / optimizer code plus (a) the sigmoid input summed in the reference's tape order, (b) fences between records,
+//       (c) LR duplicates inside a record ordered through an atomic's return value.  Kept out of the throughput instantiation
+//       because it costs registers there (the fast path is bound by how many records an SM keeps in flight).
+template <int G, int NCH, int NLR, int OPTK, bool PARITY>
 __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_fixed(const FixedParams p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -766,8 +772,11 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
         bool lr_dup[NLR];
 #pragma unroll
         for (int r = 0; r < NLR; r++) {
-            const uint32_t key = (live && lr_ok[r] && c_len[r] != 0xffffffffu) ? lr_h[r] : (0x80000000u | (uint32_t)lane);
-            lr_dup[r] = __popc(__match_any_sync(0xffffffffu, key) & gmask) > 1;
+            lr_dup[r] = false;
+            if (PARITY) {
+                const uint32_t key = (live && lr_ok[r] && c_len[r] != 0xffffffffu) ? lr_h[r] : (0x80000000u | (uint32_t)lane);
+                lr_dup[r] = __popc(__match_any_sync(0xffffffffu, key) & gmask) > 1;
+            }
         }
 
         // ---- gather: one 128-bit load per chunk ----
@@ -817,7 +826,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
         float wsum = part;
 #pragma unroll
         for (int o = G / 2; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-        if (p.max_groups == 1) {
+        if (PARITY) {
             // One record in flight = the reference's sequential loop: the sigmoid input is summed in the reference's own order,
             // left to right over the tape [LR combo outputs..., triangle outputs...] (graph.rs:251-284,
             // block_loss_functions.rs:116-120), every lane redoing the same serial sum from the group's shared rows.  The
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
                 if (c_len[r] == 0xffffffffu) { bias_G = __fadd_rn(bias_G, gl); bias_G2 = __fadd_rn(bias_G2, __fmul_rn(gl, gl)); }
                 else if (gl != 0.0f) {
                     float acc_seen = lrw[r].y;
-                    if (lr_dup[r] && optimizer != OPT_SGD) { // ordered by the L2: each duplicate steps from what the previous one left
+                    if (PARITY && lr_dup[r] && optimizer != OPT_SGD) { // ordered by the L2: each duplicate steps from what the previous one left
                         const float gg = __fmul_rn(gl, gl);
                         acc_seen = atomicAdd(reinterpret_cast<float *>(p.lr + lr_h[r]) + 1, gg);
                         red_add_f32(reinterpret_cast<float *>(p.lr + lr_h[r]), -opt_step(optimizer, gl, __fadd_rn(acc_seen, gg), p.lut_lr, p.lr_lr, p.lr_mpt));
@@ -880,16 +889,16 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
         }
         // One record in flight (hogwild_max_inflight = 1, the setting of the per-example parity tests): REDG is fire-and-forget,
         // so every lane's reductions are fenced and the group re-converges before the next record's gather may read them.
-        const bool one_in_flight = p.max_groups == 1;
+        const bool one_in_flight = PARITY;
         if (++bias_n >= bias_period) {
             if (bias_lane) {
                 if (bias_G != 0.0f) fixed_lr_apply(p, optimizer, bias_h, bias_G, bias_G2, bias_cell.y);
-                if (one_in_flight) __threadfence();
+                if (one_in_flight) { if (p.sys_scope) __threadfence_system(); else __threadfence(); }
                 bias_cell = __ldcg(p.lr + bias_h); // consumed a round later
             }
             bias_G = 0.0f; bias_G2 = 0.0f; bias_n = 0;
         }
-        if (one_in_flight) { __threadfence(); __syncwarp(); }
+        if (one_in_flight) { if (p.sys_scope) __threadfence_system(); else __threadfence(); __syncwarp(); }
     }
     if (bias_lane && bias_G != 0.0f) fixed_lr_apply(p, optimizer, bias_h, bias_G, bias_G2, bias_cell.y);
 }
@@ -1142,6 +1151,7 @@ struct RowsParams {
     unsigned long long inbox_rank_stride, inbox_src_off; // bytes; inbox_src_off = offset of (half, this rank)'s sub-ring
     uint32_t *push_cnt;            // [world] entries this rank has pushed to each owner during the current chunk (local)
     uint32_t owner_shift, world;   // owner = row base >> owner_shift (>= 32: everything on rank 0), clamped to world - 1
+    int sys_scope;                 // sharded tables: parity-mode fences at system scope
 };
 constexpr int ROWS_MAXU = 8;
 constexpr uint32_t ROWS_HDR = 4;   // floats of header in front of each shared-memory row in PUSH mode       // pair units per thread held in registers: n_units <= 8 * 256
@@ -1175,7 +1185,7 @@ __device__ __forceinline__ float opt_step_s(uint32_t optimizer, float grad, floa
 
 // OPTK: the optimizer as a compile-time constant (OPT_LUT, the reference's default under --adaptive: no powf code) or -1 = optimizer
 template <int PHASE, int OPTK, bool PUSH>
-__global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_rows(const RowsParams p)
+__global__ void __launch_bounds__(256, (PHASE == 1 || PUSH ? 4 : 2)) k_learn_rows(const RowsParams p)
 {
     const uint32_t optimizer = OPTK < 0 ? p.optimizer : (uint32_t)OPTK;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1216,11 +1226,11 @@ __global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_
     const uint32_t n_lr = p.n_combos + (p.add_constant ? 1u : 0u); // <= 256 (host checks); = the number of LR outputs
     // static geometry: unit u = tid + 256 j is lane (u % lpp) of field pair (u / lpp) = (e, z), e < z; it owns the 16-byte
     // quarters q = u % lpp, + lpp, ... of the chunk pair  a = row e, block towards z   and   b = row z, block towards e
-    uint32_t offA[ROWS_MAXU], offB[ROWS_MAXU], tri[ROWS_MAXU];
+    uint32_t offA[ROWS_MAXU], offB[ROWS_MAXU], tri[ROWS_MAXU], ez[ROWS_MAXU];
 #pragma unroll
     for (int j = 0; j < ROWS_MAXU; j++) {
         const uint32_t u = tid + 256u * j;
-        offA[j] = 0xffffffffu; offB[j] = 0; tri[j] = 0;
+        offA[j] = 0xffffffffu; offB[j] = 0; tri[j] = 0; ez[j] = 0;
         if (u < p.n_units) {
             const uint32_t pr = u / lpp, q0 = u - pr * lpp;
             uint32_t z = (uint32_t)((1.0f + sqrtf(1.0f + 8.0f * (float)pr)) * 0.5f); // pr = z (z - 1) / 2 + e
@@ -1230,6 +1240,7 @@ __global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_
             offA[j] = e * RS + z * k + 4 * q0;
             offB[j] = z * RS + e * k + 4 * q0;
             tri[j] = n_lr + z * (z + 1) / 2 + e; // position on the tape / in the head's input (block_misc.rs:871-881)
+            ez[j] = e | (z << 16);
         }
     }
     const uint32_t my_field_ns = tid < F ? __ldg(p.field_ns + tid) : 0;
@@ -1292,13 +1303,13 @@ __global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_
         // second update of a shared slot sees the first one's accumulator.  Such a record takes its accumulators from atomics'
         // return values (update_with_atomics below) instead of the gathered snapshot.  Checked while the rows are in flight.
         bool overlap = false;
-        if (!PUSH && writes && tid < F && !absent) {
-            const uint32_t mine = slot & p.ffm_mask;
-            for (uint32_t e = 0; e < tid; e++) {
-                const uint32_t o = slots[e];
-                if (o == 0x80000000u) continue;
-                const uint32_t oh = o & p.ffm_mask, diff = mine > oh ? mine - oh : oh - mine;
-                overlap = overlap || diff < Fk;
+        if (!PUSH && writes) {
+#pragma unroll
+            for (int j = 0; j < ROWS_MAXU; j++) { // every field pair is somebody's unit: the F^2 / 2 comparisons cost two LDS each
+                if (offA[j] == 0xffffffffu) continue;
+                const uint32_t se = slots[ez[j] & 0xffffu], sz = slots[ez[j] >> 16];
+                const uint32_t he = se & p.ffm_mask, hz = sz & p.ffm_mask, diff = he > hz ? he - hz : hz - he;
+                overlap = overlap || (diff < Fk && se != 0x80000000u && sz != 0x80000000u);
             }
         }
         if (flags & 2) { // some field is absent: its row reads as zeros (no feature, no interaction)
@@ -1363,7 +1374,9 @@ __global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_
                 // bucket.  Gather, gradients, optimizer step and scatter are the code every other mode runs.
                 if (tid < n_lr) terms[tid] = part;                                      // out[combo] = w * value, or 0.0 (block_lr.rs:38-45)
                 if (tid < F) terms[n_lr + tri_index(tid, tid)] = 0.0f;                  // a lone feature has no intra-field term
-                overlap = __syncthreads_or(overlap ? 1 : 0) != 0;
+                // (a sharded table in parity mode takes the atomics path too: an atomic's return value proves that the owner has
+                //  performed it, which a bulk reduction into a peer's memory does not)
+                overlap = __syncthreads_or(overlap ? 1 : 0) != 0 || (p.sys_scope && !PUSH);
                 const uint32_t x_len = n_lr + F * (F + 1) / 2;
                 wsum = 0.0f;
                 for (uint32_t i = 0; i < x_len; i++) wsum = __fadd_rn(wsum, terms[i]);
@@ -1487,7 +1500,7 @@ __global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_
             }
             continue;
         }
-        if (overlap) { if (one_in_flight) __threadfence(); continue; } // uniform: this record went through the atomics
+        if (overlap) { if (one_in_flight) { if (p.sys_scope) __threadfence_system(); else __threadfence(); } continue; } // uniform: this record went through the atomics
         if (op_on && op_present) { // the own-field block of my row takes no update: it goes back as zeros
             for (uint32_t q = 0; q < k4; q++) *reinterpret_cast<float4 *>(op_smem + op_row * k + 4 * q) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -1498,7 +1511,7 @@ __global__ void __launch_bounds__(256, (PHASE == 1 ? 4 : PUSH ? 3 : 2)) k_learn_
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
             if (one_in_flight) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // complete, not just read
         }
-        if (one_in_flight) __threadfence(); // the LR reductions too, before the barrier at the top of the next iteration
+        if (one_in_flight) { if (p.sys_scope) __threadfence_system(); else __threadfence(); } // the LR reductions too, before the barrier at the top of the next iteration
     }
     if (op_on) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // shared memory must outlive the reductions that read it
 }
@@ -1518,6 +1531,7 @@ struct ApplyParams {
     float *ffm_w, *ffm_acc; const float *lut_ffm;
     uint32_t optimizer; float ffm_lr, ffm_mpt;
 };
+constexpr int APPLY_UB = 3;
 __global__ void __launch_bounds__(256) k_apply_inbox(const ApplyParams p)
 {
     const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -1533,22 +1547,37 @@ __global__ void __launch_bounds__(256) k_apply_inbox(const ApplyParams p)
         const uint4 hdr = __ldcg(reinterpret_cast<const uint4 *>(ent));
         const uint32_t h_row = hdr.x, e = hdr.y;
         const float4 *gr4 = reinterpret_cast<const float4 *>(ent + 16);
-        for (uint32_t c0 = 0; c0 < cpr; c0 += 32) {
-            const uint32_t c = c0 + lane;
-            if (c >= cpr || c / k4 == e) continue; // own-field block: exactly zero gradient (block_ffm.rs:236-244)
-            const float4 gr = __ldcs(gr4 + c);
-            if (gr.x == 0.0f && gr.y == 0.0f && gr.z == 0.0f && gr.w == 0.0f) continue; // partner field absent
-            float4 upd;
-            if (p.optimizer == OPT_SGD) upd = make_float4(-__fmul_rn(gr.x, p.ffm_lr), -__fmul_rn(gr.y, p.ffm_lr), -__fmul_rn(gr.z, p.ffm_lr), -__fmul_rn(gr.w, p.ffm_lr));
-            else {
-                const float4 old = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + h_row + 4 * c),
-                                             make_float4(__fmul_rn(gr.x, gr.x), __fmul_rn(gr.y, gr.y), __fmul_rn(gr.z, gr.z), __fmul_rn(gr.w, gr.w)));
-                upd.x = -opt_step(p.optimizer, gr.x, acc_after(old.x, gr.x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                upd.y = -opt_step(p.optimizer, gr.y, acc_after(old.y, gr.y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                upd.z = -opt_step(p.optimizer, gr.z, acc_after(old.z, gr.z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
-                upd.w = -opt_step(p.optimizer, gr.w, acc_after(old.w, gr.w), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+        // APPLY_UB chunks per lane in flight: all gradient loads, then all accumulator atomics, then the steps and reductions,
+        // so that a warp waits for one round trip to the L2 per 96 chunks instead of one per 32
+        for (uint32_t c0 = 0; c0 < cpr; c0 += 32 * APPLY_UB) {
+            float4 gr[APPLY_UB], old[APPLY_UB];
+            bool on[APPLY_UB];
+#pragma unroll
+            for (int u = 0; u < APPLY_UB; u++) {
+                const uint32_t c = c0 + 32 * u + lane;
+                on[u] = c < cpr && c / k4 != e; // own-field block: exactly zero gradient (block_ffm.rs:236-244)
+                gr[u] = on[u] ? __ldcs(gr4 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + h_row + 4 * c), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+#pragma unroll
+            for (int u = 0; u < APPLY_UB; u++) {
+                on[u] = on[u] && !(gr[u].x == 0.0f && gr[u].y == 0.0f && gr[u].z == 0.0f && gr[u].w == 0.0f); // partner field absent
+                if (on[u] && p.optimizer != OPT_SGD)
+                    old[u] = atomicAdd(reinterpret_cast<float4 *>(p.ffm_acc + h_row + 4 * (c0 + 32 * u + lane)),
+                                       make_float4(__fmul_rn(gr[u].x, gr[u].x), __fmul_rn(gr[u].y, gr[u].y), __fmul_rn(gr[u].z, gr[u].z), __fmul_rn(gr[u].w, gr[u].w)));
+            }
+#pragma unroll
+            for (int u = 0; u < APPLY_UB; u++) {
+                if (!on[u]) continue;
+                float4 upd;
+                if (p.optimizer == OPT_SGD) upd = make_float4(-__fmul_rn(gr[u].x, p.ffm_lr), -__fmul_rn(gr[u].y, p.ffm_lr), -__fmul_rn(gr[u].z, p.ffm_lr), -__fmul_rn(gr[u].w, p.ffm_lr));
+                else {
+                    upd.x = -opt_step(p.optimizer, gr[u].x, acc_after(old[u].x, gr[u].x), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.y = -opt_step(p.optimizer, gr[u].y, acc_after(old[u].y, gr[u].y), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.z = -opt_step(p.optimizer, gr[u].z, acc_after(old[u].z, gr[u].z), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                    upd.w = -opt_step(p.optimizer, gr[u].w, acc_after(old[u].w, gr[u].w), p.lut_ffm, p.ffm_lr, p.ffm_mpt);
+                }
+                asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p.ffm_w + h_row + 4 * (c0 + 32 * u + lane)), "f"(upd.x), "f"(upd.y), "f"(upd.z), "f"(upd.w) : "memory");
+            }
         }
     }
 }

@@ -92,7 +92,7 @@ typedef struct fwgpu_model_desc {
     /* Hogwild concurrency ramp: a freshly initialised model is trained with at most
      * examples_seen / hogwild_ramp_div examples in flight, growing to the full machine; it keeps
      * the cold-start of AdaGrad (accumulators at 0) from overshooting when thousands of examples
-     * hit the same weights at once.  0 = default (32); 0xffffffff = no ramp.  DESIGN.md "semantics". */
+     * hit the same weights at once.  0 = default (256); 0xffffffff = no ramp.  DESIGN.md "semantics". */
     uint32_t hogwild_ramp_div;
     /* Hard cap on examples in flight.  0 = automatic: unlimited for AdaGrad with power_t > 0 (the accumulators damp
      * concurrent steps on a hot weight), 16 for constant-step models (SGD, or power_t == 0) -- the width of the
@@ -134,7 +134,7 @@ fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **
  * hash-range-sharded, rank r owning indices [r*len/world, (r+1)*len/world) (+ the spill-over tail of block_ffm.rs:93-94 on
  * the last rank).  One process per GPU calls this collectively (rank in [0, world)); the reference's counterpart is the
  * single table all Hogwild workers share (hogwild.rs:24-103).  It takes the place of SURVEY 8b's
- * fwgpu_comm_init(ncclUniqueId, rank, nranks): the ranks rendezvous over the unix sockets "<rendezvous>.<rank>" (owner-only),
+ * fwgpu_comm_init [ncclUniqueId, rank, nranks]: the ranks rendezvous over the unix sockets "<rendezvous>.<rank>" (owner-only),
  * exchange their shards' memory handles (CUDA VMM, POSIX fds) and the NCCL unique id there, and map all ranges into one
  * virtual range, so a row has the same address on every rank.
  *   - predict, and training with one record in flight (parity mode): rows are pulled from the owner's HBM by bulk copies over
@@ -151,6 +151,10 @@ fwgpu_status fwgpu_create(const fwgpu_model_desc *desc, int device, fwgpu_ctx **
  * live on rank 0.  timeout_ms 0 = 60 s. */
 fwgpu_status fwgpu_create_sharded(const fwgpu_model_desc *desc, int device, uint32_t rank, uint32_t world,
                                   const char *rendezvous, uint32_t timeout_ms, fwgpu_ctx **out);
+/* The layout arithmetic behind fwgpu_create_sharded, as a pure function (no GPU): sizes_out[world] = bytes of the table each
+ * rank's HBM holds (equal hash ranges when they are whole allocation granules, else everything on rank 0; the tail goes to
+ * the last rank), *owner_shift_out = s such that float index i of the table lives on rank min(i >> s, world - 1) (32 = rank 0). */
+fwgpu_status fwgpu_debug_shard_plan(uint64_t bytes, uint64_t tail_bytes, uint32_t world, uint64_t granularity, uint64_t *sizes_out, uint32_t *owner_shift_out);
 /* fwgpu_sync + wait until every rank of the shard group has done the same (no-op group of one for unsharded ctxs). */
 fwgpu_status fwgpu_shard_barrier(fwgpu_ctx *ctx);
 /* rank / world of the ctx's shard group and the FFM index range [first, first+count) this rank's HBM holds. */

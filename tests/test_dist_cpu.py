@@ -50,3 +50,33 @@ def test_two_rank_shards_and_timing(tmp_path):
             assert got[q].tolist() == [want, q * n, n]          # shards are the disjoint contiguous slices of one stream
         assert got[world][0] == int((10.0 + 5.0 * (world - 1)) * 1000)  # max over ranks
     assert dist_util.whole_job_rate(n, 3, world, 15.0) == world * n * 3 / 0.015
+
+
+def test_shard_plan_and_owner_mapping():
+    """Layout arithmetic of the one-model path (fwgpu_create_sharded), no GPU: equal hash ranges over the ranks, the spill-over
+    tail (block_ffm.rs:93-94) on the last rank, and the shift the push kernel uses to find a row's owner agrees with the byte
+    ranges -- for config 4 (ffm_bit_precision 28, 39 fields x k = 8) on 2, 4 and 8 ranks; a table too small to split into
+    whole allocation granules stays on rank 0."""
+    import ctypes as C
+
+    from fwumious_wabbit_b200 import _lib
+
+    L = _lib.lib()
+    gran = 2 << 20
+    for world in (2, 4, 8):
+        sizes = (C.c_uint64 * world)()
+        shift = C.c_uint32(0)
+        n_floats, tail = 1 << 28, 39 * 8 + 64
+        assert L.fwgpu_debug_shard_plan(n_floats * 4, tail * 4, world, gran, sizes, C.byref(shift)) == 0
+        sizes = list(sizes)
+        assert all(s % gran == 0 for s in sizes) and sum(sizes) >= (n_floats + tail) * 4
+        assert sizes[:-1] == [n_floats * 4 // world] * (world - 1) and sizes[-1] >= n_floats * 4 // world + tail * 4
+        offs = np.concatenate([[0], np.cumsum(sizes)])
+        rng = np.random.default_rng(world)
+        for i in list(rng.integers(0, n_floats, 2000)) + [0, n_floats - 1, n_floats, n_floats + tail - 1] + [r * n_floats // world for r in range(world)]:
+            owner = min(int(i) >> shift.value, world - 1)
+            assert offs[owner] <= int(i) * 4 < offs[owner + 1], (world, i, owner)
+    sizes = (C.c_uint64 * 2)()
+    shift = C.c_uint32(0)
+    assert L.fwgpu_debug_shard_plan((1 << 18) * 8, 0, 2, gran, sizes, C.byref(shift)) == 0   # a 2 MiB LR table: one granule
+    assert list(sizes) == [gran, 0] and shift.value == 32

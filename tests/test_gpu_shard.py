@@ -43,6 +43,8 @@ def test_sharded_table(world):
         assert np.array_equal(res[r]["pred_sharded"], res[r]["pred_single"])
     # B. sequential training through remote memory is bit-exact with the unsharded run
     last = res[world - 1]
+    print("B: narrow sequential max |dp|", float(np.max(np.abs(last["seq_sharded"] - last["seq_single"]))), "tables", last["seq_tables_equal"],
+          "| D1: wide sequential max |dp|", float(np.max(np.abs(last["wide_seq_sharded"] - last["wide_seq_single"]))), "tables", last["wide_seq_tables_equal"])
     assert np.array_equal(last["seq_sharded"].view(np.uint32), last["seq_single"].view(np.uint32))
     assert last["seq_tables_equal"].all(), last["seq_tables_equal"]
     # C. two GPUs training one model concurrently: progressive logloss within 1 % of one GPU training the whole stream
