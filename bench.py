@@ -58,8 +58,8 @@ STEP_EXAMPLES = {"c1": 10_000_000, "c2": 10_000_000, "c3": 2_000_000, "c4": 2_00
 CPU_SAMPLE = {"c1": 4_000_000, "c2": 2_000_000, "c3": 100_000, "c4": 100_000, "c5": 15_000}          # sequential, 1 thread
 CPU_SAMPLE_HOGWILD = {"c1": 16_000_000, "c2": 8_000_000, "c3": 1_000_000, "c4": 1_000_000, "c5": 100_000}  # multi-thread legs
 KERNEL_NAME = {"c2": "k_learn_fixed<16,4,1,OPT_LUT> (16 lanes per record, two records per warp)",
-               "c3": "k_learn_rows<0> (block per record, one bulk copy per row, records double-buffered)",
-               "c4": "k_learn_rows<0> (block per record, one bulk copy per row, records double-buffered)",
+               "c3": "k_learn_rows<0,LUT> (block per record: one bulk copy per row and array in, pair-owned in-place update, one bulk reduction per row and array out)",
+               "c4": "k_learn_rows<0,LUT> (block per record: one bulk copy per row and array in, pair-owned in-place update, one bulk reduction per row and array out)",
                "c5": "k_learn_rows<1> + <2> (forward / update phases around the head's GEMMs)"}
 
 
@@ -272,7 +272,7 @@ def logloss(preds, labels):
     return float(-np.mean(np.where(labels == 1, np.log(p), np.log(1 - p))))
 
 
-def measure(env, wname, n, steps, warmup, *, do_e2e=True, predict_only=False, uniform=False, one_model=False, tags=()):
+def measure(env, wname, n, steps, warmup, *, do_e2e=True, predict_only=False, uniform=False, one_model=False, max_inflight=0, tags=()):
     """One workload on this rank's GPU: value (records resident in HBM), optionally e2e (host buffers through the C ABI),
     roofline of the dominant kernel.  Returns the dict of a bench line (rank 0) -- collective over ranks."""
     import ctypes as C
@@ -284,6 +284,8 @@ def measure(env, wname, n, steps, warmup, *, do_e2e=True, predict_only=False, un
 
     world, rank, local_rank, dist = env.world, env.rank, env.local_rank, env.dist
     w = synth.workload(wname)
+    if max_inflight:
+        w.mi.hogwild_max_inflight = max_inflight   # 1 = parity mode: the reference's sequential semantics through the fused kernel
     shard = (rank, world, f"/tmp/fwgpu_shard_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}_{wname}") if (one_model and world > 1) else None
     re = fw.Regressor(w.mi, device=local_rank, shard=shard)
     stream = torch.cuda.ExternalStream(re.stream_ptr(), device=torch.device("cuda", local_rank))
@@ -473,6 +475,9 @@ def run_ours(args):
                 sub("c4x1", "c4", do_e2e=False, tags=["c4x1: the 2^28-row table on one GPU"])
             sub("c4x1_uniform_ids", "c4", do_e2e=False, uniform=True, tags=["c4x1: the 2^28-row table on one GPU"])
             sub(f"{head}_predict_only", head, do_e2e=False, predict_only=True)
+            # the parity tier's price: the same fused kernel with ONE record in flight (bit-exact with the reference's
+            # sequential learner, tests/test_gpu_fused_parity.py) next to the Hogwild number above
+            sub(f"{head}_one_record_in_flight", head, n=20_000, do_e2e=False, max_inflight=1, tags=["parity mode: one record in flight, bit-exact with the sequential reference"])
         elif head != "c4":
             sub("c4_one_model", "c4", do_e2e=False, one_model=True)
     cpu = None

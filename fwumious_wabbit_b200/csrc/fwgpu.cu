@@ -926,7 +926,7 @@ template <int PHASE, int OPTK, bool PUSH> static cudaError_t launch_rows_k(fwgpu
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
-    if (PUSH && c->shard_overlap && per_sm > 3) per_sm = 3; // leave room for the owner-side apply kernel of the previous chunk
+    if (PUSH && c->shard_overlap && per_sm > 2) per_sm = 2; // half of every SM is left to the owner-side apply kernel of the previous chunk
     uint32_t grid = std::min<uint32_t>(p.n_examples, (uint32_t)(c->num_sms * per_sm));
     if (p.max_groups) grid = std::min<uint32_t>(grid, p.max_groups);
     *full_groups = (uint32_t)(c->num_sms * per_sm);
@@ -970,7 +970,10 @@ static fwgpu_status shard_push_chunk(fwgpu_ctx *c, RowsParams rp, uint32_t *full
     ap.optimizer = c->optimizer; ap.ffm_lr = c->d.ffm_learning_rate; ap.ffm_mpt = -c->d.ffm_power_t;
     static const int apply_blocks_env = getenv("FWGPU_SHARD_APPLY_BLOCKS") ? atoi(getenv("FWGPU_SHARD_APPLY_BLOCKS")) : 0;
     if (!getenv("FWGPU_SHARD_NO_APPLY")) { // (diagnostic: time the push side alone)
-        k_apply_inbox<<<c->num_sms * (apply_blocks_env > 0 ? apply_blocks_env : (c->shard_overlap ? 1 : 4)), 256, 0, as>>>(ap);
+        int apply_per_sm = 0;
+        CUDA_TRY(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&apply_per_sm, k_apply_inbox, 256, 0));
+        apply_per_sm = std::max(1, apply_blocks_env > 0 ? apply_blocks_env : (c->shard_overlap ? std::min(apply_per_sm, 2) : apply_per_sm)); // one wave
+        k_apply_inbox<<<c->num_sms * apply_per_sm, 256, 0, as>>>(ap);
         c->launches++;
     }
     CUDA_TRY(c, cudaGetLastError());

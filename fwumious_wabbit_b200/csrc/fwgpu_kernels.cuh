@@ -1532,7 +1532,7 @@ struct ApplyParams {
     uint32_t optimizer; float ffm_lr, ffm_mpt;
 };
 constexpr int APPLY_UB = 3;
-__global__ void __launch_bounds__(256) k_apply_inbox(const ApplyParams p)
+__global__ void __launch_bounds__(256, 4) k_apply_inbox(const ApplyParams p)
 {
     const uint32_t lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, n_warps = (gridDim.x * blockDim.x) >> 5;
     uint32_t cnt[16], total = 0;

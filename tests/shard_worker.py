@@ -86,22 +86,25 @@ def main():
     #    D2 every rank trains its slice of one stream on the ONE model: gradient rows are pushed to the owners' inboxes, one
     #       NCCL all-gather per chunk, owners apply AdaGrad (k_learn_rows<PUSH> + k_apply_inbox).
     os.environ["FWGPU_SHARD_CHUNK"] = "2048"
-    wd = synth.workload("c3")
-    wd.mi.hogwild_max_inflight = 1
     n1 = 400
-    recs_d = wd.records(n1)
-    sh = fw.Regressor(wd.mi, device=rank, shard=(rank, world, prefix + ".d1"))
-    if rank == world - 1:
-        single = fw.Regressor(wd.mi, device=rank)
-        out["wide_seq_sharded"] = sh.learn_records(recs_d.reshape(-1), n_examples=n1, update=True)
-        out["wide_seq_single"] = single.learn_records(recs_d.reshape(-1), n_examples=n1, update=True)
-        sh.sync()
-        sw, sa = sh.get_ffm(); uw, ua = single.get_ffm()
-        out["wide_seq_tables_equal"] = np.array([np.array_equal(sw, uw), np.array_equal(sa, ua), np.array_equal(sh.get_lr_table(), single.get_lr_table())])
-        out["wide_seq_paths"] = np.array([sh.path_counts()["fixed_cta"], sh.path_counts()["general_examples"]])
-        single.close()
-    sh.shard_barrier()
-    sh.close()
+    for tag, setter in (("wide_seq", lambda mi: setattr(mi, "hogwild_ramp_div", SEQUENTIAL)),      # sequential mode: the general kernel
+                        ("wide_one", lambda mi: setattr(mi, "hogwild_max_inflight", 1))):            # one record in flight: the bulk-copy kernel
+        wd = synth.workload("c3")
+        setter(wd.mi)
+        recs_d = wd.records(n1)
+        sh = fw.Regressor(wd.mi, device=rank, shard=(rank, world, prefix + "." + tag))
+        if rank == world - 1:
+            single = fw.Regressor(wd.mi, device=rank)
+            out[tag + "_sharded"] = sh.learn_records(recs_d.reshape(-1), n_examples=n1, update=True)
+            out[tag + "_single"] = single.learn_records(recs_d.reshape(-1), n_examples=n1, update=True)
+            sh.sync()
+            sw, sa = sh.get_ffm(); uw, ua = single.get_ffm()
+            out[tag + "_tables_equal"] = np.array([np.array_equal(sw, uw), np.array_equal(sa, ua), np.array_equal(sh.get_lr_table(), single.get_lr_table())])
+            out[tag + "_tables_maxdiff"] = np.array([float(np.max(np.abs(sw - uw))), float(np.max(np.abs(sa - ua)))])
+            out[tag + "_paths"] = np.array([sh.path_counts()["fixed_cta"], sh.path_counts()["general_examples"]])
+            single.close()
+        sh.shard_barrier()
+        sh.close()
 
     n_per = int(os.environ.get("FWGPU_TEST_SHARD_N", "40000"))
     we = synth.workload("c3")

@@ -18,7 +18,5 @@ except Exception as e: print("$name: bench parse failed", e); print(open("gpurun
 PY
 }
 run default X=1
-run noapply FWGPU_SHARD_NO_APPLY=1
 run overlap FWGPU_SHARD_OVERLAP=1
-run overlap_apply2 FWGPU_SHARD_OVERLAP=1 FWGPU_SHARD_APPLY_BLOCKS=2
-run chunk16k FWGPU_SHARD_CHUNK=16384
+run overlap_apply1 FWGPU_SHARD_OVERLAP=1 FWGPU_SHARD_APPLY_BLOCKS=1
