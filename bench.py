@@ -57,6 +57,7 @@ def parse_args():
 STEP_EXAMPLES = {"c1": 10_000_000, "c2": 10_000_000, "c3": 2_000_000, "c4": 2_000_000, "c5": 1_000_000}
 CPU_SAMPLE = {"c1": 4_000_000, "c2": 2_000_000, "c3": 100_000, "c4": 100_000, "c5": 15_000}          # sequential, 1 thread
 CPU_SAMPLE_HOGWILD = {"c1": 16_000_000, "c2": 8_000_000, "c3": 1_000_000, "c4": 1_000_000, "c5": 100_000}  # multi-thread legs
+EXTRA_DEADLINE_S = 420
 KERNEL_NAME = {"c2": "k_learn_fixed<16,4,1,OPT_LUT> (16 lanes per record, two records per warp)",
                "c3": "k_learn_rows<0,LUT> (block per record: one bulk copy per row and array in, pair-owned in-place update, one bulk reduction per row and array out)",
                "c4": "k_learn_rows<0,LUT> (block per record: one bulk copy per row and array in, pair-owned in-place update, one bulk reduction per row and array out)",
@@ -132,6 +133,21 @@ class ClockSampler(threading.Thread):
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "note": self.err or "no samples"}
         return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(self.sm)}
+
+
+def nvlink_bytes(index):
+    """(tx_bytes, rx_bytes) summed over the GPU's NVLinks from the driver's data counters (`nvidia-smi nvlink -gt d`), or None."""
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        tx = rx = 0
+        for line in out.splitlines():
+            if "Data Tx" in line:
+                tx += int(line.split(":")[-1].strip().split()[0])
+            elif "Data Rx" in line:
+                rx += int(line.split(":")[-1].strip().split()[0])
+        return (tx * 1024, rx * 1024) if (tx or rx) else None
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def make_config(w, n, world, one_model, args, tags=()):
@@ -337,6 +353,8 @@ def measure(env, wname, n, steps, warmup, *, do_e2e=True, predict_only=False, un
     launches0 = re.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    nvl0 = nvlink_bytes(local_rank) if (one_model and world > 1 and rank == 0) else None
+    t_wall0 = time.perf_counter()
     ev0.record(stream)
     for i in range(steps):
         re.learn_dataset(ds, (warmup + i) * n, n, update=upd, sync=False)
@@ -344,6 +362,13 @@ def measure(env, wname, n, steps, warmup, *, do_e2e=True, predict_only=False, un
     sampler.sample()  # the queue is still draining here: a sample under load even for a very short region
     barrier()
     sampler.stop_flag = True
+    nvlink = None
+    if nvl0 is not None:
+        nvl1, wall = nvlink_bytes(local_rank), time.perf_counter() - t_wall0
+        if nvl1 is not None:  # driver counters of rank 0's GPU around the timed region (barriers included: a lower bound of the in-kernel rate)
+            nvlink = {"tx_bytes_per_example": (nvl1[0] - nvl0[0]) / (n * steps), "rx_bytes_per_example": (nvl1[1] - nvl0[1]) / (n * steps),
+                      "tx_gbs_over_wall": (nvl1[0] - nvl0[0]) / wall * 1e-9, "rx_gbs_over_wall": (nvl1[1] - nvl0[1]) / wall * 1e-9,
+                      "source": "nvidia-smi nvlink -gt d, GPU of rank 0, before / after the timed steps"}
     launches = re.launch_count() - launches0
     ms_local = ev0.elapsed_time(ev1)
     ms_total = max_over_ranks(ms_local)
@@ -431,6 +456,8 @@ def measure(env, wname, n, steps, warmup, *, do_e2e=True, predict_only=False, un
             "clocks": sampler.summary(), "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
             "per_rank_ms_per_step": per_rank_ms, "kernel_paths": counts,
         }
+        if nvlink:
+            out["nvlink"] = nvlink
     ds.free()
     re.close()
     L.fwgpu_host_free(hp)
@@ -455,6 +482,18 @@ def run_ours(args):
                    uniform=args.uniform_ids, one_model=one_model,
                    tags=(["c4x1: the 2^28-row table on one GPU"] if head == "c4" and world == 1 else []))
     extra = {}
+    # The headline is measured; whatever happens in the extras (a rank that dies inside a collective would leave the others
+    # waiting), the ONE JSON line still goes out: after EXTRA_DEADLINE_S every rank leaves, rank 0 printing what it has.
+    def _deadline():
+        if rank == 0:
+            line["extra"] = dict(extra, _note=f"extras cut off after {EXTRA_DEADLINE_S} s")
+            line["cpu_baseline"] = None
+            emit(line)
+        os._exit(0)
+
+    watchdog = threading.Timer(EXTRA_DEADLINE_S, _deadline)
+    watchdog.daemon = True
+    watchdog.start()
     if not args.no_extra and not args.predict_only and not args.uniform_ids:
         xs, xw = 3, 3  # extras: shorter runs, same timing rules (>= 3 warm-up steps, fresh data, device timing)
 
@@ -483,6 +522,7 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_block(synth.workload(head), args)
+    watchdog.cancel()
     if rank == 0:
         line["extra"] = extra
         line["cpu_baseline"] = cpu
