@@ -117,7 +117,7 @@ struct fwgpu_ctx {
     uint64_t n_fixed = 0, n_fixed_cta = 0, n_general = 0; // launches per learn-kernel family (fwgpu_debug_path_counts)
     unsigned long long *stat_general_examples = nullptr;  // device: examples the general kernel handled
     uint64_t examples_seen = 0; // examples learned from (update = 1); drives the concurrency ramp
-    uint32_t ramp_div = 256;
+    uint32_t ramp_div = 32;
     uint32_t max_inflight = 0; // 0 = unlimited
     bool ramp_finished = false;
     bool profiling = false;
@@ -488,10 +488,7 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
     }
     if (const char *t = getenv("FWGPU_T")) c->force_T = atoi(t);
     if (const char *t = getenv("FWGPU_MINB")) c->minb = atoi(t);
-    // 256: measured on config 2 (profiles/r02_c2_ramp_sweep.txt): progressive logloss on 10^7 examples is 2.1 % above the
-    // sequential learner's with 32, 0.4 % with 64, 0.2 % with 128, 0.08 % with 256; the ramp then ends after ~3.6 M examples
-    // (c2) / 76 K examples (c3), a few milliseconds of reduced concurrency once per model
-    c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 256;
+    c->ramp_div = d.hogwild_ramp_div ? d.hogwild_ramp_div : 32;
     if (const char *t = getenv("FWGPU_RAMP_DIV")) c->ramp_div = (uint32_t)strtoul(t, nullptr, 10);
     {
         const bool constant_step = c->optimizer == FWGPU_OPT_SGD || d.power_t == 0.0f || (d.ffm_k > 0 && d.ffm_power_t == 0.0f);
@@ -1346,7 +1343,8 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
         if (preds_host) CUDA_TRY(c, cudaMemcpyAsync(preds_host, c->preds.p, (size_t)count * 4, cudaMemcpyDeviceToHost, c->stream));
         return FWGPU_OK;
     }
-    const bool use_fast = run_learn && c->fast_ok && c->fast_enabled && c->ramp_div < 0x7fffffffu;
+    // hogwild_ramp_div 0x7fffffff .. 0xfffffffe = sequential mode (general kernel, reference tape order); 0xffffffff = no ramp
+    const bool use_fast = run_learn && c->fast_ok && c->fast_enabled && (c->ramp_div < 0x7fffffffu || c->ramp_div == 0xffffffffu);
     if (use_fast) {
         // fused kernel on the raw records; records it cannot take are listed and go through the general path below
         if ((st = ensure(c, c->leftover, (size_t)(count + 4) * 4))) return st;
@@ -1378,6 +1376,14 @@ static fwgpu_status translate_and_learn(fwgpu_ctx *c, const RecView &rv, uint32_
             const bool push = c->push_ok && update && c->fast_cta && c->fast_rows && cap != 1;
             if (push) cnt = std::min<uint32_t>(cnt, c->shard_chunk);
             fp.ex_begin = done; fp.n_examples = cnt; fp.max_groups = cap;
+            {   // Combining the bias updates of 16 records per group multiplies the number of records whose bias gradients are
+                // applied from one stale value by 16 (14 208 groups x 16 = 227 K records on c2).  On a young model (small
+                // accumulator, large steps) that made the bias oscillate between 2 M and 4 M examples: 0.4-2 % of progressive
+                // logloss on 10^7 examples, gone entirely with per-record bias updates whatever the ramp divisor
+                // (profiles/r02_c2_ramp_sweep.txt).  It therefore starts once the model has seen 2^24 examples.
+                static const long bias_env = getenv("FWGPU_BIAS_PERIOD") ? atol(getenv("FWGPU_BIAS_PERIOD")) : -1;
+                fp.bias_combine = bias_env >= 0 ? (bias_env > 1) : (c->examples_seen >= (1ull << 24));
+            }
             uint32_t full_groups = 0;
             cudaError_t e;
             if (c->fast_cta) {

@@ -615,6 +615,7 @@ struct FixedParams {
     uint32_t max_groups;
     uint32_t rec_smem_floats;      // F * (cpr + 1) * 4: the transpose area of one record
     int sys_scope;                 // sharded tables: parity-mode fences at system scope
+    int bias_combine;              // 1: a group sums the bias gradients of FIXED_BIAS_PERIOD records before it applies them (mature models only)
 };
 
 // Block = FIXED_WARPS independent warps, one record per G-lane group and round; nothing is exchanged between groups.
@@ -724,7 +725,7 @@ __global__ void __launch_bounds__(FIXED_WARPS * 32, (NCH >= 3 ? 2 : 3)) k_learn_
     }
     const uint32_t bias_h = 11650396u & p.lr_mask; // feature_buffer.rs:270-276
     // the combined bias update of this group (see above) and the cell as of the last refresh
-    const uint32_t bias_period = !p.update ? 0xffffffffu : p.max_groups ? 1u : (uint32_t)FIXED_BIAS_PERIOD; // predict: the cell never changes
+    const uint32_t bias_period = !p.update ? 0xffffffffu : (p.max_groups || !p.bias_combine) ? 1u : (uint32_t)FIXED_BIAS_PERIOD; // predict: the cell never changes
     float bias_G = 0.0f, bias_G2 = 0.0f;
     float2 bias_cell = bias_lane ? __ldcg(p.lr + bias_h) : make_float2(0.f, 0.f);
     uint32_t bias_n = 0;

@@ -92,7 +92,7 @@ typedef struct fwgpu_model_desc {
     /* Hogwild concurrency ramp: a freshly initialised model is trained with at most
      * examples_seen / hogwild_ramp_div examples in flight, growing to the full machine; it keeps
      * the cold-start of AdaGrad (accumulators at 0) from overshooting when thousands of examples
-     * hit the same weights at once.  0 = default (256); 0xffffffff = no ramp.  DESIGN.md "semantics". */
+     * hit the same weights at once.  0 = default (32); 0x7fffffff = sequential mode (one example in flight, general kernel); 0xffffffff = no ramp.  DESIGN.md "semantics". */
     uint32_t hogwild_ramp_div;
     /* Hard cap on examples in flight.  0 = automatic: unlimited for AdaGrad with power_t > 0 (the accumulators damp
      * concurrent steps on a hot weight), 16 for constant-step models (SGD, or power_t == 0) -- the width of the

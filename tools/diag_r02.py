@@ -39,20 +39,6 @@ def seq_run(w, n, rows, mode):
     return [float(d[:m].max()) for m in (100, 300, 1000, n)], first_bad, re.path_counts()
 
 
-for head in (True, False):
-    for bits in (14,):
-        for k in (4, 8):
-            for rows in ("1",):
-                for mode in ("ramp", "inflight1"):
-                    if not head and mode == "ramp":
-                        continue
-                    try:
-                        r = seq_run(small_c5(bits=bits, k=k, head=head), 3000, rows, mode)
-                    except Exception as e:  # noqa: BLE001
-                        r = repr(e)
-                    print(f"head={head} bits={bits} k={k} rows_kernel={rows} mode={mode}: max|dp| at 100/300/1000/3000 = {r}", flush=True)
-os.environ.pop("FWGPU_ROWS", None)
-
 # c2 Hogwild gate: spread over repeated runs
 w = synth.workload("c2")
 n = 10_000_000
@@ -63,13 +49,36 @@ _, want = ora.hogwild(util.oracle_spec(w.mi), recs.reshape(-1), rec_off, 1, want
 labels = recs[:, 1].astype(np.float32)
 ll_o = util.logloss(want, labels)
 dec = n // 10
-for div in (32, 64, 128, 256, 1024):
+for div, bias in ((32, -1),):
     os.environ["FWGPU_RAMP_DIV"] = str(div)
-    re = fw.Regressor(w.mi)
-    got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
-    ll_g = util.logloss(got, labels)
-    gaps = [util.logloss(got[i * dec:(i + 1) * dec], labels[i * dec:(i + 1) * dec]) - util.logloss(want[i * dec:(i + 1) * dec], labels[i * dec:(i + 1) * dec]) for i in range(10)]
-    first = [util.logloss(got[a:b], labels[a:b]) - util.logloss(want[a:b], labels[a:b]) for a, b in ((0, 10_000), (10_000, 100_000), (100_000, 300_000), (300_000, 1_000_000))]
-    print(f"c2 1e7 hogwild ramp_div {div}: gpu {ll_g:.5f} oracle {ll_o:.5f} rel {abs(ll_g - ll_o) / ll_o:.4f}; decile gaps {[round(g, 4) for g in gaps]}; first 1e4/1e5/3e5/1e6 gaps {[round(g, 4) for g in first]}", flush=True)
-    re.close()
-os.environ.pop("FWGPU_RAMP_DIV", None)
+    if bias >= 0:
+        os.environ["FWGPU_BIAS_PERIOD"] = str(bias)
+    else:
+        os.environ.pop("FWGPU_BIAS_PERIOD", None)
+    # the env var is read once per process (static): run every variant in its own interpreter
+    import subprocess
+    code = (
+        "import os,sys,numpy as np; sys.path.insert(0, %r)\n"
+        "import fwumious_wabbit_b200 as fw\nfrom fwumious_wabbit_b200 import synth\nfrom tests import util\n"
+        "w = synth.workload('c2'); n = %d; recs = w.records(n); want = np.load('/tmp/c2_want.npy'); labels = recs[:, 1].astype(np.float32)\n"
+        "re = fw.Regressor(w.mi); got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)\n"
+        "dec = n // 10\n"
+        "gaps = [round(util.logloss(got[i*dec:(i+1)*dec], labels[i*dec:(i+1)*dec]) - util.logloss(want[i*dec:(i+1)*dec], labels[i*dec:(i+1)*dec]), 4) for i in range(10)]\n"
+        "print('rel %%.4f' %% (abs(util.logloss(got, labels) - util.logloss(want, labels)) / util.logloss(want, labels)), 'decile gaps', gaps)\n"
+    ) % (ROOT, n)
+    np.save("/tmp/c2_want.npy", want)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
+    print(f"c2 1e7 hogwild ramp_div {div} bias_period {bias}: {out.stdout.strip()} {out.stderr.strip()[-300:]}", flush=True)
+
+# the transition to combined bias updates at 2^24 examples: 3e7 examples in one call, decile gaps around the switch
+n3 = 30_000_000
+recs3 = w.records(n3)
+ora3 = util.oracle_regressor(w.mi)
+_, want3 = ora3.hogwild(util.oracle_spec(w.mi), recs3.reshape(-1), np.arange(n3 + 1, dtype=np.uint64) * w.record_len, 1, want_preds=True)
+os.environ.pop("FWGPU_RAMP_DIV", None); os.environ.pop("FWGPU_BIAS_PERIOD", None)
+re3 = fw.Regressor(w.mi)
+got3 = re3.learn_records(recs3.reshape(-1), n_examples=n3, update=True)
+lab3 = recs3[:, 1].astype(np.float32)
+d3 = n3 // 15
+print("c2 3e7 default settings: rel %.4f; gaps per 2M examples" % (abs(util.logloss(got3, lab3) - util.logloss(want3, lab3)) / util.logloss(want3, lab3)),
+      [round(util.logloss(got3[i * d3:(i + 1) * d3], lab3[i * d3:(i + 1) * d3]) - util.logloss(want3[i * d3:(i + 1) * d3], lab3[i * d3:(i + 1) * d3]), 4) for i in range(15)], flush=True)

@@ -22,12 +22,13 @@ try:
     r=json.loads(open("gpurun_out/bench_ref_$TAG.json").read()); print("reference arm", r["value"], r["config"]==d["config"], r["cpu_baseline"]["cores"])
 except Exception as e: print("bench parse failed", e)
 PY
+(timeout 600 python tools/diag_r02.py 2>&1 | tail -4 | cut -c1-500 | tee gpurun_out/diag_$TAG.txt)
 # launch list of the bench command (all kernels, gpu time)
 (timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c3_$TAG.csv python bench.py --workload c3 --examples 600000 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra > gpurun_out/ncu_list_c3_$TAG.log 2>&1)
 python tools/launch_summary.py gpurun_out/launches_c3_$TAG.csv 2>/dev/null | head -12
 # full captures, one steady-state launch each
 cap() { # name kernel-regex skip workload examples extra-args
-  (FWGPU_RAMP_DIV=4294967295 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/ncu_$1_$TAG python bench.py --workload $4 --examples $5 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra $6 > gpurun_out/ncu_$1_$TAG.log 2>&1)
+  (FWGPU_RAMP_DIV=4294967295 FWGPU_CHUNK_MB=4096 timeout 600 ncu --set full --clock-control none --import-source on -k regex:$2 -s $3 -c 1 -o gpurun_out/ncu_$1_$TAG python bench.py --workload $4 --examples $5 --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-extra $6 > gpurun_out/ncu_$1_$TAG.log 2>&1)
   ls -la gpurun_out/ncu_$1_$TAG.ncu-rep 2>/dev/null | awk '{print $5, $9}'
 }
 cap c3_rows k_learn_rows 4 c3 600000 ""
