@@ -33,3 +33,39 @@ def test_gpu_arm_emits_every_contract_key():
     for key in ("bound", "achieved", "peak", "frac", "traffic", "h2d_bytes_per_step", "d2h_bytes_per_step", "cores", "kind", "sample", "sm_mhz", "sm_max_mhz", "reasons"):
         assert re.search(r'"%s"\s*:' % key, src), key
     assert "no CUDA device; the product has no CPU path" in src   # the GPU arm refuses to run without a GPU
+
+
+def test_both_arms_build_the_same_config_and_traffic_is_hash_checked():
+    """The reference arm and the GPU arm describe the workload with ONE function (the driver compares the two lines' configs),
+    and profiles/traffic_<workload>.json is only believed while it carries the hash of the kernel sources the bench runs on."""
+    sys.path.insert(0, ROOT)
+    import importlib
+
+    bench = importlib.import_module("bench")
+    from fwumious_wabbit_b200 import synth
+
+    w = synth.workload("c3")
+    a = bench.make_config(w, bench.STEP_EXAMPLES["c3"], 1, False, None)
+    b = bench.make_config(synth.workload("c3"), bench.STEP_EXAMPLES["c3"], 1, False, object())
+    assert a == b and a["examples_per_step_per_gpu"] == 2_000_000 and a["workload"].startswith("c3:")
+    assert "one model" in bench.make_config(w, 1, 8, True, None)["parallelism"] and "replicas x8" in bench.make_config(w, 1, 8, False, None)["parallelism"]
+    sha = bench.kernel_source_sha()
+    assert re.fullmatch(r"[0-9a-f]{16}", sha) and sha == bench.kernel_source_sha()
+    for name in ("c2", "c3", "c4x1", "c4x1_uniform"):
+        t = json.load(open(os.path.join(ROOT, "profiles", f"traffic_{name}.json")))
+        assert set(t) >= {"dram_bytes_per_example", "kernel_source_sha", "kernel", "examples_in_launch"}
+        assert t["dram_bytes_per_example"] > 0 and re.fullmatch(r"[0-9a-f]{16}", t["kernel_source_sha"])
+
+
+def test_nvlink_counter_parser(monkeypatch):
+    sys.path.insert(0, ROOT)
+    import bench
+
+    class R:
+        stdout = "GPU 0: NVIDIA B200\n\t Link 0: Data Tx: 100 KiB\n\t Link 0: Data Rx: 40 KiB\n\t Link 1: Data Tx: 28 KiB\n\t Link 1: Data Rx: 2 KiB\n"
+
+    monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: R())
+    assert bench.nvlink_bytes(0) == (128 * 1024, 42 * 1024)
+    R.stdout = "GPU 0: NVIDIA B200\n\t Link 0: Data Tx: N/A\n"
+    monkeypatch.setattr(bench.subprocess, "run", lambda *a, **k: (_ for _ in ()).throw(RuntimeError("no nvidia-smi")))
+    assert bench.nvlink_bytes(0) is None

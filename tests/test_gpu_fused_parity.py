@@ -184,7 +184,9 @@ def test_head_umma_subbatch_matches_batched_oracle(shape, monkeypatch):
     for l in range(re.nn_layer_count()):
         gw, ga = re.get_nn(l)
         msg, mx, bad = _table_report(f"nn{l}_w", gw, ora.nn_weights(l), 5e-6)
-        assert mx <= 5e-4 and bad <= max(4, gw.size // 2000), msg      # LUT bucket edges: a handful of weights take a 6 % different step
+        # LUT bucket edges: a weight whose accumulator lands on the other side of one takes a 6 % different step; measured 0.05 % of
+        # a layer's weights (the warm state comes from a Hogwild run, so the count moves from run to run): bound 0.2 %
+        assert mx <= 5e-4 and bad <= max(8, gw.size // 500), msg
         np.testing.assert_allclose(ga, ora.nn_acc(l), rtol=1e-3, atol=1e-7)
     # the whole stream: 8 sub-batches
     rec_off8 = np.arange(8 * n + 1, dtype=np.uint64) * w.record_len
