@@ -54,105 +54,145 @@ bool rust_parse_f32(const char *s, size_t a, size_t b, float *out)
     return true;
 }
 
+// ---- VW text line -> record (behaviour of parser.rs:214-461, pinned by its known-answer tests; structure is this file's own) ----
+// Three pieces: LineCursor walks the bytes of one line (the byte after the row -- the newline -- may be looked at, never
+// consumed), RecordWriter owns the output encoding of parser.rs:57-74 (a namespace's single weight-1 feature lives in its
+// header slot; anything else moves the namespace to (hash, f32) pairs behind the header), parse_line is the grammar
+//     line      := label [importance] junk* namespace*          label decided by the FIRST byte: '1', '-', or '|' (no label)
+//     namespace := '|' name [':' weight] feature*
+//     feature   := name [':' weight]                             (an f32 namespace reads the value out of the name)
+struct LineCursor {
+    const char *p; size_t pos, end; // row = p[0, end); p[end] exists (newline)
+    char peek() const { return p[pos]; }
+    bool in_row() const { return pos < end; }
+    void skip_spaces() { while (in_row() && p[pos] == ' ') pos++; }
+    void skip_word() { while (in_row() && p[pos] != ' ') pos++; }
+    void skip_until(char c) { while (in_row() && p[pos] != c) pos++; }
+    // one space-delimited word starting at pos: [b, e), with `split` = its first ':' (or e when there is none)
+    struct Word { size_t b, split, e; bool has_suffix() const { return split != e; } };
+    Word word()
+    {
+        Word w;
+        w.b = pos;
+        while (in_row() && p[pos] != ' ' && p[pos] != ':') pos++;
+        w.split = pos;
+        skip_word();
+        w.e = pos;
+        return w;
+    }
+    std::string text(size_t a, size_t b) const { return std::string(p + a, b - a); }
+};
+
+class RecordWriter {
+public:
+    RecordWriter(uint32_t *out, size_t cap, uint32_t n_ns) : out_(out), cap_(cap), len_(n_ns + HEADER_LEN)
+    {
+        for (size_t i = 0; i < len_; i++) out_[i] = NO_FEATURES;
+    }
+    void set_label(uint32_t v) { out_[LABEL_OFFSET] = v; }
+    void set_importance(float v) { memcpy(&out_[IMPORTANCE_OFFSET], &v, 4); }
+    void open_namespace(uint32_t index) { slot_ = index + HEADER_LEN; count_ = 0; first_pair_ = len_; }
+    // a categorical feature of weight exactly 1.0 that is the namespace's first: kept in the header slot (parser.rs:396-404)
+    bool try_inline(uint32_t hash) { if (count_ != 0) return false; out_[slot_] = hash; count_ = 1; return true; }
+    // any other feature: the namespace becomes a list of (hash, value bits) pairs; an inlined first feature is moved there first
+    bool push_pair(uint32_t hash, float value)
+    {
+        if (len_ + 4 > cap_) return false;
+        const uint32_t held = out_[slot_];
+        if (count_ == 1 && (held & IS_NOT_SINGLE_MASK) == 0) { out_[len_++] = held; out_[len_++] = FLOAT32_ONE; }
+        out_[len_++] = hash;
+        memcpy(&out_[len_++], &value, 4);
+        out_[slot_] = IS_NOT_SINGLE_MASK | (uint32_t)((first_pair_ << 16) + len_);
+        count_++;
+        return true;
+    }
+    int finish() { out_[0] = (uint32_t)len_; return (int)len_; }
+
+private:
+    uint32_t *out_; size_t cap_, len_, slot_ = HEADER_LEN, first_pair_ = 0; uint32_t count_ = 0;
+};
+
+// "flush" / "hogwild_load <file>" arrive on the same channel as examples (parser.rs:226-258)
+int classify_command(const char *p, size_t size)
+{
+    if (size >= 5 && !memcmp(p, "flush", 5)) return -2;
+    if (size >= strlen("hogwild_load ")) {
+        LineCursor c{p, 0, size};
+        size_t words = 0, first_len = 0;
+        while (c.in_row()) {
+            const size_t b = c.pos;
+            c.skip_word();
+            if (words++ == 0) first_len = c.pos - b;
+            c.skip_spaces();
+        }
+        if (words == 2 && first_len == 12 && !memcmp(p, "hogwild_load", 12)) return -3;
+    }
+    return -1;
+}
+
 // returns record length in words; 0 = empty; -1 error; -2 flush; -3 hogwild_load
 int parse_line(const Parser &P, const char *p, size_t size, uint32_t *out, size_t cap, std::string &err)
 {
     if (size == 0) return 0;
-    const size_t bufpos = P.n_ns + HEADER_LEN;
-    if (cap < bufpos) { err = "record buffer too small"; return -1; }
-    size_t olen = bufpos;
-    for (size_t i = 0; i < bufpos; i++) out[i] = NO_FEATURES;
-    size_t i_start, i_end = 0;
-    switch ((unsigned char)p[0]) {
-    case 0x31: out[LABEL_OFFSET] = 1; break;
-    case 0x2d: out[LABEL_OFFSET] = 0; break;
-    case 0x7c: out[LABEL_OFFSET] = NO_LABEL; break;
-    default: {
-        if (size >= 5 && !memcmp(p, "flush", 5)) return -2;
-        if (size >= strlen("hogwild_load ")) {
-            size_t ntok = 0, i = 0, first_len = 0;
-            while (i < size) {
-                size_t s0 = i;
-                while (i < size && p[i] != 0x20) i++;
-                if (ntok == 0) first_len = i - s0;
-                ntok++;
-                while (i < size && p[i] == 0x20) i++;
-            }
-            if (ntok == 2 && first_len == 12 && !memcmp(p, "hogwild_load", 12)) return -3;
-        }
-        err = "Cannot parse an example";
-        return -1;
-    }
-    }
-    const size_t rowlen = size - 1; // ignore last newline byte (parser.rs:270)
-    if (out[LABEL_OFFSET] == NO_LABEL) out[IMPORTANCE_OFFSET] = FLOAT32_ONE;
+    if (cap < P.n_ns + HEADER_LEN) { err = "record buffer too small"; return -1; }
+    RecordWriter rec(out, cap, P.n_ns);
+    LineCursor cur{p, 0, size - 1}; // the row ends before the line's last byte (its newline)
+    const char first = p[0];
+    if (first == '1') rec.set_label(1);
+    else if (first == '-') rec.set_label(0);
+    else if (first == '|') rec.set_label(NO_LABEL);
     else {
-        while (p[i_end] != 0x20 && i_end < rowlen) i_end++;
-        while (p[i_end] == 0x20 && i_end < rowlen) i_end++;
-        if (p[i_end] == 0x7c) out[IMPORTANCE_OFFSET] = FLOAT32_ONE;
-        else {
-            i_start = i_end;
-            while (p[i_end] != 0x20 && i_end < rowlen) i_end++;
-            float imp;
-            if (!rust_parse_f32(p, i_start, i_end, &imp)) { err = "Failed parsing example importance: " + std::string(p + i_start, i_end - i_start); return -1; }
-            if (imp < 0.0f) { char b[96]; snprintf(b, sizeof(b), "Example importance cannot be negative: %g! ", imp); err = b; return -1; }
-            memcpy(&out[IMPORTANCE_OFFSET], &imp, 4);
+        const int cmd = classify_command(p, size);
+        if (cmd == -1) err = "Cannot parse an example";
+        return cmd;
+    }
+    // importance: the word after the label, unless a namespace starts there
+    float importance = 1.0f;
+    if (first != '|') {
+        cur.skip_word();
+        cur.skip_spaces();
+        if (cur.peek() != '|') {
+            const size_t b = cur.pos;
+            cur.skip_word();
+            if (!rust_parse_f32(p, b, cur.pos, &importance)) { err = "Failed parsing example importance: " + cur.text(b, cur.pos); return -1; }
+            if (importance < 0.0f) { char msg[96]; snprintf(msg, sizeof(msg), "Example importance cannot be negative: %g! ", importance); err = msg; return -1; }
         }
     }
-    while (p[i_end] != 0x7c && i_end < rowlen) i_end++;
-    uint32_t cur_seed = 0;
-    size_t cur_off = HEADER_LEN, ns_start = 0;
-    bool cur_f32 = false;
-    float cur_w = 1.0f;
-    uint32_t cur_n = 0;
-    while (i_end < rowlen) {
-        while (p[i_end] == 0x20 && i_end < rowlen) i_end++;
-        i_start = i_end;
-        while (p[i_end] != 0x20 && p[i_end] != 0x3a && i_end < rowlen) i_end++;
-        const size_t first_end = i_end;
-        while (p[i_end] != 0x20 && i_end < rowlen) i_end++;
-        if (p[i_start] == 0x7c) {
-            i_start++;
-            if (first_end != i_end) {
-                if (!rust_parse_f32(p, first_end + 1, i_end, &cur_w)) { err = "Failed parsing namespace weight: " + std::string(p + first_end + 1, i_end - first_end - 1); return -1; }
-            } else cur_w = 1.0f;
-            auto it = P.by_name.find(std::string(p + i_start, first_end - i_start));
-            if (it == P.by_name.end()) { err = "Feature name was not predeclared in vw_namespace_map.csv: " + std::string(p + i_start, first_end - i_start); return -1; }
-            cur_seed = it->second.seed;
-            cur_off = it->second.index + HEADER_LEN;
-            cur_f32 = it->second.f32;
-            cur_n = 0;
-            ns_start = olen;
+    rec.set_importance(importance);
+    cur.skip_until('|'); // tags or anything else before the first namespace are ignored
+
+    const NsInfo *ns = nullptr;
+    float ns_weight = 1.0f;
+    while (cur.in_row()) {
+        cur.skip_spaces();
+        const LineCursor::Word w = cur.word(); // may be empty when only spaces were left: the reference hashes it as a feature too
+        if (p[w.b] == '|') {
+            ns_weight = 1.0f;
+            if (w.has_suffix() && !rust_parse_f32(p, w.split + 1, w.e, &ns_weight)) { err = "Failed parsing namespace weight: " + cur.text(w.split + 1, w.e); return -1; }
+            const std::string name = cur.text(w.b + 1, w.split);
+            const auto it = P.by_name.find(name);
+            if (it == P.by_name.end()) { err = "Feature name was not predeclared in vw_namespace_map.csv: " + name; return -1; }
+            ns = &it->second;
+            rec.open_namespace(ns->index);
         } else {
-            const uint32_t h = murmur3_32(p + i_start, first_end - i_start, cur_seed) & MASK31;
-            float fw = 1.0f;
-            if (first_end != i_end && !rust_parse_f32(p, first_end + 1, i_end, &fw)) { err = "Failed parsing feature weight: " + std::string(p + first_end + 1, i_end - first_end - 1); return -1; }
-            if (cur_n == 0 && !cur_f32 && cur_w == 1.0f && fw == 1.0f) out[cur_off] = h;
-            else {
-                if (olen + 4 > cap) { err = "record too long"; return -1; }
-                const uint32_t prev = out[cur_off];
-                if (cur_n == 1 && (prev & IS_NOT_SINGLE_MASK) == 0) { out[olen++] = prev; out[olen++] = FLOAT32_ONE; }
-                out[olen++] = h;
-                if (cur_f32) {
-                    const size_t fs = i_start + P.vw.namespace_skip_prefix;
-                    float fv = NAN;
-                    if (first_end != fs) {
-                        if (fs > first_end || !rust_parse_f32(p, fs, first_end, &fv)) { err = "Failed parsing feature value to float (for float namespace): " + std::string(p + i_start, first_end - i_start); return -1; }
-                    }
-                    memcpy(&out[olen++], &fv, 4);
-                    if (cur_w * fw != 1.0f) { err = "Namespaces that are f32 can not have weight attached neither to namespace nor to a single feature (basically they can' use :weight syntax"; return -1; }
-                } else {
-                    const float v = cur_w * fw;
-                    memcpy(&out[olen++], &v, 4);
+            const uint32_t hash = murmur3_32(p + w.b, w.split - w.b, ns ? ns->seed : 0) & MASK31;
+            float weight = 1.0f;
+            if (w.has_suffix() && !rust_parse_f32(p, w.split + 1, w.e, &weight)) { err = "Failed parsing feature weight: " + cur.text(w.split + 1, w.e); return -1; }
+            const bool is_f32 = ns && ns->f32;
+            if (!(!is_f32 && ns_weight == 1.0f && weight == 1.0f && rec.try_inline(hash))) {
+                float value = ns_weight * weight;
+                if (is_f32) { // the number is the feature's name after the skipped prefix; an empty name is NaN (parser.rs:416-433)
+                    const size_t vb = w.b + P.vw.namespace_skip_prefix;
+                    value = NAN;
+                    if (vb != w.split && (vb > w.split || !rust_parse_f32(p, vb, w.split, &value))) { err = "Failed parsing feature value to float (for float namespace): " + cur.text(w.b, w.split); return -1; }
                 }
-                out[cur_off] = IS_NOT_SINGLE_MASK | (uint32_t)((ns_start << 16) + olen);
+                if (!rec.push_pair(hash, value)) { err = "record too long"; return -1; }
+                if (is_f32 && ns_weight * weight != 1.0f) { err = "Namespaces that are f32 can not have weight attached neither to namespace nor to a single feature (basically they can' use :weight syntax"; return -1; }
             }
-            cur_n++;
         }
-        i_end++;
+        cur.pos = w.e + 1;
     }
-    out[0] = (uint32_t)olen;
-    return (int)olen;
+    return rec.finish();
 }
 
 // ---------------------------------------------------------------- files
