@@ -6,7 +6,7 @@
 //   16-byte ld.v4 / red.v4 / atom.v4                                               what round 1's sharded kernel issued
 // against the local table (same GPU) and against the peer's, one direction and both directions at once.
 //   build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/nvlink_bulk_microbench tools/nvlink_bulk_microbench.cu
-//   run  : tools/nvlink_bulk_microbench   (needs 2 GPUs with peer access)
+//   run  : tools/nvlink_bulk_microbench   (2 GPUs with peer access: the NVLink table; 1 GPU: the local skeleton of the wide kernel)
 #include <cuda_runtime.h>
 #include <cstdio>
 #include <cstdint>
@@ -130,7 +130,30 @@ int main()
 {
     int n = 0;
     CK(cudaGetDeviceCount(&n));
-    if (n < 2) { printf("needs 2 GPUs, found %d\n", n); return 0; }
+    if (n < 2) {
+        // one GPU: the local skeleton of the wide kernel's copy-engine traffic for an L2-sized and an HBM-sized table
+        // (what bounds k_learn_rows: bytes or the rate of row-sized bulk operations?)
+        Dev d0; d0.id = 0;
+        CK(cudaSetDevice(0));
+        CK(cudaMalloc(&d0.sink, 4)); CK(cudaStreamCreate(&d0.s)); CK(cudaEventCreate(&d0.a)); CK(cudaEventCreate(&d0.b));
+        cudaDeviceProp prop0; CK(cudaGetDeviceProperties(&prop0, 0));
+        for (uint64_t tb : {64ull << 20, 1024ull << 20}) {
+            CK(cudaMalloc(&d0.tab, tb + 4096)); CK(cudaMalloc(&d0.tab2, tb + 4096));
+            CK(cudaMemset(d0.tab, 0, tb)); CK(cudaMemset(d0.tab2, 0, tb));
+            uint32_t nr = (uint32_t)(tb / (ALIGN_FLOATS * 4)), p2 = 1; while (p2 * 2 <= nr) p2 *= 2;
+            for (int per_sm : {2, 4}) {
+                const int blocks0 = prop0.multiProcessorCount * per_sm; const uint32_t it0 = 400;
+                const double recs0 = (double)blocks0 * it0;
+                float l = timed<LOAD_BULK>(d0, d0.tab, d0.tab2, nullptr, nullptr, nullptr, p2 - 1, it0, blocks0);
+                float r = timed<RED_BULK>(d0, d0.tab, d0.tab2, nullptr, nullptr, nullptr, p2 - 1, it0, blocks0);
+                float q = timed<RECORD_BULK>(d0, d0.tab, d0.tab2, nullptr, nullptr, nullptr, p2 - 1, it0, blocks0);
+                printf("local, table 2 x %4llu MB, %d CTAs/SM: 39 bulk loads %6.2f M records/s | 39 bulk reductions %6.2f M records/s | record (78 loads + 78 reductions) %6.2f M records/s\n",
+                       (unsigned long long)(tb >> 20), per_sm, recs0 / l * 1e-3, recs0 / r * 1e-3, recs0 / q * 1e-3);
+            }
+            CK(cudaFree(d0.tab)); CK(cudaFree(d0.tab2));
+        }
+        return 0;
+    }
     int can = 0;
     CK(cudaDeviceCanAccessPeer(&can, 0, 1));
     if (!can) { printf("no peer access between GPU 0 and 1\n"); return 0; }
