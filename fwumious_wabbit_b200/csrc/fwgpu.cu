@@ -477,7 +477,7 @@ static fwgpu_status create_impl(const fwgpu_model_desc *desc, int device, fwgpu_
             // k_learn_rows: weight AND accumulator rows of one record in shared memory, pair units held in registers
             const uint32_t k4 = c->k / 4, lpp = (k4 == 1 || k4 == 2 || k4 == 4) ? k4 : 1;
             const size_t n_units = (size_t)c->F * (c->F - 1) / 2 * lpp;
-            const size_t smem_rows = (size_t)2 * c->F * c->Fk * 4 + 2048 * 4 + (size_t)((c->F + 3) & ~3u) * 4 + 64;
+            const size_t smem_rows = (size_t)2 * c->F * c->Fk * 4 + 2048 * 4 + 2 * (size_t)((c->F + 3) & ~3u) * 4 + 64;
             c->fast_rows = c->F >= 2 && n_units <= (size_t)ROWS_MAXU * 256 && smem_rows <= c->smem_optin;
             if (const char *t = getenv("FWGPU_ROWS")) c->fast_rows = c->fast_rows && atoi(t) != 0;
         }
@@ -915,7 +915,7 @@ template <int PHASE, int OPTK, bool PUSH> static cudaError_t launch_rows_k(fwgpu
     const bool writes = PHASE != 1 && p.update != 0;
     const size_t rows = (size_t)p.F * (p.Fk + (PUSH ? ROWS_HDR : 0)) * 4 + (PUSH ? 16 : 0);
     const size_t smem = rows + ((!PUSH && writes && p.optimizer != OPT_SGD) ? rows : 0) + ((!PUSH && writes && p.optimizer == OPT_LUT) ? 2048 * 4 : 0) +
-                        (size_t)((p.F + 3) & ~3u) * 4 + 8 * 4 + 16 +
+                        2 * (size_t)((p.F + 3) & ~3u) * 4 + 8 * 4 + 16 +
                         (p.max_groups == 1 ? (size_t)(p.n_combos + 1 + p.F * (p.F + 1) / 2) * 4 : 0); // parity mode: the tape
     cudaError_t e0 = ensure_dyn_smem(c, kern, smem);
     if (e0 != cudaSuccess) return e0;

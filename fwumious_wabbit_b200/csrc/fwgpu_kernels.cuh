@@ -1199,8 +1199,11 @@ __global__ void __launch_bounds__(256, (PHASE == 1 || PUSH ? 4 : 2)) k_learn_row
     float *W = reinterpret_cast<float *>(smem_raw) + (PUSH ? ROWS_HDR : 0u); // row e at W + e * RS (its header right in front of it)
     float *A = W + (size_t)F * RS;
     float *lut_s = A + (has_acc ? (size_t)F * RS : 0);
-    uint32_t *slots = reinterpret_cast<uint32_t *>(lut_s + (use_lut ? 2048 : 0));
-    float *red = reinterpret_cast<float *>(slots + ((F + 3) & ~3u));
+    // the record's header slots, double-buffered by record parity: a block's fast threads store record i+1's slots (before the
+    // barrier that publishes them) while slow ones may still read record i's
+    uint32_t *slots2 = reinterpret_cast<uint32_t *>(lut_s + (use_lut ? 2048 : 0));
+    const uint32_t slots_stride = (F + 3) & ~3u;
+    float *red = reinterpret_cast<float *>(slots2 + 2 * slots_stride);
     uint64_t *bar = reinterpret_cast<uint64_t *>(red + 8);
     float *terms = reinterpret_cast<float *>(bar + 2); // one-record-in-flight mode only: the sigmoid's inputs in tape order
 
@@ -1250,10 +1253,11 @@ __global__ void __launch_bounds__(256, (PHASE == 1 || PUSH ? 4 : 2)) k_learn_row
     uint32_t ex = p.ex_begin + blockIdx.x;
     const uint32_t ex_end = p.ex_begin + p.n_examples;
     uint32_t slot_next = (ex < ex_end && tid < F) ? __ldg(rec_ptr(ex) + 3 + my_field_ns) : 0x80000000u;
-    uint32_t parity = 0;
+    uint32_t parity = 0, rec_parity = 0;
 
-    for (; ex < ex_end; ex += n_blocks) {
+    for (; ex < ex_end; ex += n_blocks, rec_parity ^= 1u) {
         const uint32_t *rec = rec_ptr(ex);
+        uint32_t *slots = slots2 + rec_parity * slots_stride;
         // ---- translate (feature_buffer.rs:178-338), in-place slots only ----
         const uint32_t slot = slot_next;
         const bool absent = tid < F && slot == 0x80000000u;
