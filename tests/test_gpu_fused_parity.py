@@ -79,24 +79,28 @@ def test_fused_kernel_one_in_flight_bit_exact(name, n, kernel):
 
 @pytest.mark.parametrize("name,n,kernel", [("c2", 10_000, "fixed"), ("c3", 2_000, "fixed_cta")])
 def test_fused_kernel_one_in_flight_whole_stream(name, n, kernel):
-    """The same on the unfiltered stream: records whose windows overlap get their concurrent updates in hardware order, which
-    moves a shared slot's step by at most one look-up-table bucket (6 % of ONE step).  Predictions stay within 1e-3 of the
-    sequential oracle everywhere and within 1e-5 for 99 % of the stream; the touched cells are exactly the oracle's."""
+    """The same on the unfiltered stream: records whose rows share slots take their accumulators from atomics' return values
+    (the wide kernel detects them while the rows are in flight; the narrow kernel always uses atomics; LR duplicates are
+    ordered through an atomic too), i.e. in hardware order instead of the reference's feature order -- the same values up to
+    the order of two additions.  Predictions stay within 1e-5 of the sequential oracle for EVERY record (measured: 0.0) and
+    the tables within 2e-6 everywhere (measured: <= 1e-8); the touched cells are exactly the oracle's."""
     w = synth.workload(name)
     w.mi.hogwild_max_inflight = 1
     recs = w.records(n)
     ora, want = _oracle_run(w, recs)
     re = fw.Regressor(w.mi)
     got = re.learn_records(recs.reshape(-1), n_examples=n, update=True)
-    assert re.path_counts()[kernel] > 0
+    assert re.path_counts()[kernel] > 0 and re.path_counts()["general_examples"] == 0
     d = np.abs(got - want)
-    assert float(d.max()) <= 1e-3 and float(np.mean(d <= TOL)) >= 0.99, (float(d.max()), float(np.mean(d <= TOL)))
+    assert float(d.max()) <= TOL, float(d.max())
     wts, acc = re.get_ffm()
     msg, mx, bad = _table_report("ffm_w", wts, ora.ffm_weights, 2e-6)
-    assert mx <= 5e-3 and bad <= max(64, wts.size // 20_000), msg
+    assert bad == 0, msg
+    msg2, mx2, bad2 = _table_report("lr_w", re.get_lr_table()[:, 0], ora.lr_table[:, 0], 2e-6)
+    assert bad2 == 0, msg2
     assert np.array_equal(acc != 0.0, ora.ffm_acc != 0.0)
-    np.testing.assert_allclose(acc, ora.ffm_acc, rtol=1e-4, atol=1e-9)
-    print(msg, f"; max |dp| {float(d.max()):.2e}, within 1e-5: {float(np.mean(d <= TOL)):.4f}")
+    np.testing.assert_allclose(acc, ora.ffm_acc, rtol=1e-5, atol=1e-9)
+    print(msg, ";", msg2, f"; max |dp| {float(d.max()):.2e}")
 
 
 def test_fused_cta_phases_one_in_flight_match_oracle(monkeypatch):
@@ -198,7 +202,7 @@ def test_head_umma_subbatch_matches_batched_oracle(shape, monkeypatch):
     d8 = float(np.max(np.abs(got8 - want8)))
     print(f"first sub-batch max |dp| {err:.2e}; 8 sub-batches max |dp| {d8:.2e}; logloss {ll_g:.5f} vs {ll_o:.5f}")
     assert ll_o < 0.7 and abs(ll_g - ll_o) / ll_o < 0.01, (ll_g, ll_o)
-    assert d8 <= 5e-2, d8
+    assert d8 <= 1e-2, d8   # measured 6e-4 (small model) / 1.2e-3 (c5)
 
 
 def test_c5_full_shape_hogwild_logloss_gate(monkeypatch):
