@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -51,7 +52,7 @@ struct Flags {
 };
 const char *VALUE[] = {"data", "predictions", "final_regressor", "initial_regressor", "predictions_after", "holdout_after", "convert_inference_regressor",
                        "batch_size", "device", "hogwild_threads", "prediction_model_delay", nullptr};
-const char *BOOLS[] = {"cache", "testonly", "save_resume", "quiet", "predictions_stdout", "build_cache_without_training", "sequential", "hogwild_training", nullptr};
+const char *BOOLS[] = {"cache", "testonly", "save_resume", "quiet", "predictions_stdout", "build_cache_without_training", "sequential", "hogwild_training", "weight_quantization", nullptr};
 bool in(const char **l, const std::string &s) { for (; *l; l++) if (s == *l) return true; return false; }
 std::string long_name(const std::string &t) {
     if (t.rfind("--", 0) == 0) return t.substr(2);
@@ -150,22 +151,35 @@ int main(int argc, char **argv)
         }
         fwhost_regressor_close(reader);
     }
-    auto save = [&](const char *path, bool as_sgd) {
+    // --weight_quantization (main.rs:109, block_ffm.rs:835-848): the FFM weights go to the file as 16-bit buckets.  Only the
+    // conversion to an inference regressor also records that in the ModelInstance (main.rs:143-145), so that is the use the
+    // reference suggests; with --final_regressor the reference writes the buckets under an unchanged ModelInstance and so do we.
+    const bool quantize = fl.has("weight_quantization");
+    auto save = [&](const char *path, bool as_sgd, bool mark_quantized) {
         std::vector<std::vector<float>> payload(n_blocks);
-        std::vector<const void *> ptrs(n_blocks); std::vector<uint64_t> sizes(n_blocks); uint64_t total = 0;
+        std::vector<const void *> ptrs; std::vector<uint64_t> sizes; uint64_t total = 0;
+        std::vector<uint8_t> buckets;
         for (int b = 0; b < n_blocks; b++) {
             uint64_t n, by; fwgpu_block_len(ctx, blocks[b], &n, &by);
             payload[b].resize(by / 4);
             check(ctx, fwgpu_export_block(ctx, blocks[b], payload[b].data(), by), "export_block");
-            ptrs[b] = payload[b].data(); sizes[b] = by; total += n;
+            total += n;
+            if (quantize && blocks[b] == FWGPU_BLOCK_FFM) { // weights first, accumulators (if any) after them: block_ffm.rs:835-848
+                float mean = 0.0f;
+                buckets.resize(8 + 2 * (size_t)n);
+                if (fwhost_quantize_ffm_weights(payload[b].data(), n, buckets.data(), &mean)) die("cannot quantize an empty FFM block");
+                if (std::fabs(mean) > 10.0f) fprintf(stderr, "fwgpu: warning: mean FFM weight %g, the weights look exploded (quantization.rs:45-47)\n", mean);
+                ptrs.push_back(buckets.data()); sizes.push_back(buckets.size());
+                if (by > n * 4) { ptrs.push_back(payload[b].data() + n); sizes.push_back(by - n * 4); }
+            } else { ptrs.push_back(payload[b].data()); sizes.push_back(by); }
         }
-        std::string mj = mi_json;
-        if (as_sgd) { // main.rs:140-147: the inference regressor is written with optimizer SGD
-            size_t p = mj.find("\"optimizer\": \""); if (p != std::string::npos) { size_t e = mj.find('"', p + 14); mj.replace(p + 14, e - (p + 14), "SGD"); }
-        }
-        if (fwhost_regressor_write(path, vwmap_json.c_str(), mj.c_str(), total, ptrs.data(), sizes.data(), (uint32_t)n_blocks, err, sizeof(err))) die(err);
+        char *mj = fwhost_model_instance_for_save(mi_json.c_str(), as_sgd ? 1 : 0, mark_quantized ? 1 : 0, err, sizeof(err));
+        if (!mj) die(err);
+        const int rc = fwhost_regressor_write(path, vwmap_json.c_str(), mj, total, ptrs.data(), sizes.data(), (uint32_t)ptrs.size(), err, sizeof(err));
+        fwhost_free(mj);
+        if (rc) die(err);
     };
-    if (convert) { save(fl.get("convert_inference_regressor"), true); fwgpu_destroy(ctx); return 0; }
+    if (convert) { save(fl.get("convert_inference_regressor"), true, quantize); fwgpu_destroy(ctx); return 0; }
 
     // ---- input: cache or text (main.rs:173-239, cache.rs:68-131)
     const char *data = fl.get("data");
@@ -243,7 +257,7 @@ int main(int argc, char **argv)
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!quiet) fprintf(stderr, "fwgpu: Elapsed: %.2fs rows: %lld (%.0f rows/s)\n", secs, (long long)n_examples, n_examples / std::max(secs, 1e-9));
     if (pf) fclose(pf);
-    if (final_regressor) save(final_regressor, /*as_sgd=*/immutable); // an immutable ctx holds weights only: the file says SGD (persistence.rs:163-172)
+    if (final_regressor) save(final_regressor, /*as_sgd=*/immutable, /*mark_quantized=*/false); // an immutable ctx holds weights only: the file says SGD (persistence.rs:163-172)
     fwgpu_host_free(preds);
     fwhost_free(records); fwhost_free(rec_off);
     fwhost_model_desc_free(keep);

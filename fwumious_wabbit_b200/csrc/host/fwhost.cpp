@@ -223,7 +223,7 @@ const char *VALUE_FLAGS[] = {"data", "predictions", "final_regressor", "initial_
                              "predictions_after", "holdout_after", "hogwild_threads", "convert_inference_regressor", "transform", "prediction_model_delay",
                              "batch_size", "device", nullptr};
 const char *BOOL_FLAGS[] = {"cache", "testonly", "save_resume", "adaptive", "sgd", "noconstant", "vwcompat", "hogwild_training", "quiet", "predictions_stdout",
-                            "build_cache_without_training", "sequential", "invariant", "normalized", nullptr};
+                            "build_cache_without_training", "sequential", "invariant", "normalized", "weight_quantization", nullptr};
 const std::pair<const char *, const char *> SHORT_FLAGS[] = {{"d", "data"}, {"p", "predictions"}, {"f", "final_regressor"}, {"i", "initial_regressor"}, {"b", "bit_precision"},
                                                              {"l", "learning_rate"}, {"c", "cache"}, {"t", "testonly"}, {"q", "interactions"}};
 
@@ -640,6 +640,65 @@ int fwhost_regressor_read_quantized(void *r, float *dst, uint64_t n)
         done += cnt;
     }
     return 0;
+}
+// quantization.rs:19-75 quantize_ffm_weights, the writer of the 16-bit form: min and max of the block rounded to 4 decimals, 65 025
+// equal buckets between them, each weight's bucket number (round half away from zero) stored as an IEEE half (round to nearest even,
+// what half::f16::from_f32 does).  dst receives 8 + 2·n bytes.  *mean_out is the reference's sampled mean (every 10th weight), the
+// figure its "exploded weights" warning looks at.
+static uint16_t f32_to_half_rne(float v)
+{
+    uint32_t x;
+    memcpy(&x, &v, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u | ((x >> 13) & 0x3ffu) : 0u));
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                 // rounds to 65520 or more: infinity
+    if (x < 0x33000001u) return (uint16_t)sign;                               // at most 2^-25: zero (the tie goes to even)
+    uint32_t ex = x >> 23, man = x & 0x7fffffu, h;
+    if (ex < 113) {                                                           // half subnormal: value = m · 2^-24
+        man |= 0x800000u;
+        const uint32_t shift = 126 - ex;                                      // 14 … 24
+        h = man >> shift;
+        const uint32_t rem = man & ((1u << shift) - 1), halfway = 1u << (shift - 1);
+        if (rem > halfway || (rem == halfway && (h & 1))) h++;
+    } else {
+        h = ((ex - 112) << 10) | (man >> 13);
+        const uint32_t rem = man & 0x1fffu;
+        if (rem > 0x1000u || (rem == 0x1000u && (h & 1))) h++;                // a carry into the exponent is the right answer
+    }
+    return (uint16_t)(sign | h);
+}
+int fwhost_quantize_ffm_weights(const float *w, uint64_t n, void *dst, float *mean_out)
+{
+    if (!w || !dst || n == 0) return -1;
+    float lo = w[0], hi = w[0], mean = 0.0f;
+    uint64_t sampled = 0;
+    for (uint64_t i = 0; i < n; i++) {
+        hi = fmaxf(hi, w[i]);
+        lo = fminf(lo, w[i]);
+        if (i % 10 == 0) { sampled++; mean += w[i]; }
+    }
+    lo = roundf(lo * 10000.0f) / 10000.0f;
+    hi = roundf(hi * 10000.0f) / 10000.0f;
+    const float increment = (hi - lo) / 65025.0f;
+    if (mean_out) *mean_out = mean / (float)sampled;
+    uint8_t *out = (uint8_t *)dst;
+    memcpy(out, &increment, 4);
+    memcpy(out + 4, &lo, 4);
+    uint16_t *q = (uint16_t *)(out + 8);
+    for (uint64_t i = 0; i < n; i++) q[i] = f32_to_half_rne(roundf((w[i] - lo) / increment));
+    return 0;
+}
+// The ModelInstance a regressor file is written with: an inference regressor says optimizer SGD (main.rs:140-147,
+// persistence.rs:163-172), a quantized one dequantize_weights = true (main.rs:143-145).  Caller frees with fwhost_free.
+char *fwhost_model_instance_for_save(const char *mi_json, int as_sgd, int quantized, char *err, size_t errcap)
+{
+    try {
+        ModelInstanceH m = mi_from_json(json_parse(mi_json));
+        if (as_sgd) m.optimizer = FWGPU_OPT_SGD;
+        if (quantized) m.dequantize_weights = 1;
+        return dup_string(json_to_string(mi_to_json(m)));
+    } catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
 }
 int fwhost_regressor_skip(void *r, uint64_t bytes) { return fseek(((RegReader *)r)->f, (long)bytes, SEEK_CUR) == 0 ? 0 : -1; }
 void fwhost_regressor_close(void *r) { RegReader *rr = (RegReader *)r; if (rr) { if (rr->f) fclose(rr->f); delete rr; } }

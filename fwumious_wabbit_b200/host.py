@@ -47,6 +47,8 @@ def _L():
     L.fwhost_regressor_optimizer.argtypes, L.fwhost_regressor_optimizer.restype = [vp], C.c_uint32
     L.fwhost_regressor_dequantize.argtypes, L.fwhost_regressor_dequantize.restype = [vp], C.c_int
     L.fwhost_regressor_read_quantized.argtypes, L.fwhost_regressor_read_quantized.restype = [vp, vp, C.c_uint64], C.c_int
+    L.fwhost_quantize_ffm_weights.argtypes, L.fwhost_quantize_ffm_weights.restype = [vp, C.c_uint64, vp, vp], C.c_int
+    L.fwhost_model_instance_for_save.argtypes, L.fwhost_model_instance_for_save.restype = [cp, C.c_int, C.c_int, cp, sz], vp
     L.fwhost_regressor_close.argtypes, L.fwhost_regressor_close.restype = [vp], None
     L._host_bound = True
     return L
@@ -233,25 +235,44 @@ def _block_order(mi):
     return [_lib.BLOCK_LR] + ([_lib.BLOCK_FFM] if mi.ffm_k > 0 else []) + nn
 
 
-def save_regressor_to_filename(filename, mi: ModelInstance, vw: VwNamespaceMap, re):
-    """persistence.rs:76-92: header, vwmap JSON, ModelInstance JSON, total weight count, block payloads."""
+def quantize_ffm_weights(weights):
+    """quantization.rs:41-75: the 8-byte header {increment, min} and one 16-bit bucket per weight, as bytes (uint8 array)."""
+    w = np.ascontiguousarray(weights, dtype=np.float32)
+    out = np.empty(8 + 2 * w.size, dtype=np.uint8)
+    if _L().fwhost_quantize_ffm_weights(w.ctypes.data_as(C.c_void_p), w.size, out.ctypes.data_as(C.c_void_p), None) != 0:
+        raise ValueError("cannot quantize an empty FFM block")
+    return out
+
+
+def save_regressor_to_filename(filename, mi: ModelInstance, vw: VwNamespaceMap, re, quantize_weights=False):
+    """persistence.rs:76-92: header, vwmap JSON, ModelInstance JSON, total weight count, block payloads.
+    quantize_weights (the reference's --weight_quantization, main.rs:109,143-147) writes the FFM weights as 16-bit buckets
+    (block_ffm.rs:835-848); on an immutable regressor - the conversion to an inference regressor, the suggested use - the
+    ModelInstance in the file also says dequantize_weights = true, so that loaders know."""
     blocks, total = [], 0
     order = _block_order(mi)
     for b in order:
         n, _ = re.block_len(b)
         total += n
-        blocks.append(re.export_block(b))
-    if mi.ffm_k == 0:
-        pass
-    mi_json = model_instance_to_json(mi, vw)
-    if re.immutable:
-        j = json.loads(mi_json)
-        j["optimizer"] = "SGD"  # an inference regressor is written with mi.optimizer = SGD (main.rs:140-147)
-        mi_json = json.dumps(j)
+        payload = re.export_block(b)
+        if quantize_weights and b == _lib.BLOCK_FFM:
+            flat = payload.reshape(-1).view(np.float32)
+            blocks.append(quantize_ffm_weights(flat[:n]))
+            if flat.size > n:  # accumulators follow the weights unchanged
+                blocks.append(np.ascontiguousarray(flat[n:]))
+        else:
+            blocks.append(payload)
+    err = C.create_string_buffer(_ERR)
+    # an inference regressor is written with mi.optimizer = SGD (main.rs:140-147)
+    p = _L().fwhost_model_instance_for_save(model_instance_to_json(mi, vw).encode(), 1 if re.immutable else 0,
+                                            1 if (quantize_weights and re.immutable) else 0, err, _ERR)
+    if not p:
+        raise ValueError(err.value.decode())
+    mi_json = C.string_at(p)
+    _L().fwhost_free(p)
     ptrs = (C.c_void_p * len(blocks))(*[b.ctypes.data_as(C.c_void_p) for b in blocks])
     sizes = (C.c_uint64 * len(blocks))(*[b.nbytes for b in blocks])
-    err = C.create_string_buffer(_ERR)
-    if _L().fwhost_regressor_write(filename.encode(), vw.source_json.encode(), mi_json.encode(), total, ptrs, sizes, len(blocks), err, _ERR) != 0:
+    if _L().fwhost_regressor_write(filename.encode(), vw.source_json.encode(), mi_json, total, ptrs, sizes, len(blocks), err, _ERR) != 0:
         raise IOError(err.value.decode())
 
 

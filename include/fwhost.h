@@ -65,6 +65,12 @@ uint32_t fwhost_regressor_optimizer(void *reader);
 int fwhost_regressor_dequantize(void *reader);
 /* quantization.rs:77-95 dequantize_ffm_weights: reads the 8-byte header and n 16-bit buckets, writes n f32 weights */
 int fwhost_regressor_read_quantized(void *reader, float *dst, uint64_t n);
+/* quantization.rs:19-75 quantize_ffm_weights (the writer behind --weight_quantization): dst receives the 8-byte header
+ * {f32 increment, f32 min} and n 16-bit buckets, 8 + 2*n bytes; *mean_out (or NULL) the sampled mean the reference logs */
+int fwhost_quantize_ffm_weights(const float *weights, uint64_t n, void *dst, float *mean_out);
+/* The ModelInstance JSON a regressor file is written with: optimizer SGD for an inference regressor (main.rs:140-147,
+ * persistence.rs:163-172), dequantize_weights true for a quantized one (main.rs:143-145).  Free with fwhost_free. */
+char *fwhost_model_instance_for_save(const char *mi_json, int as_sgd, int quantized, char *err, size_t errcap);
 void fwhost_regressor_close(void *reader);
 
 /* ModelInstance JSON + vwmap JSON -> fwgpu_model_desc (struct fwgpu_model_desc of include/fwgpu.h, passed as void*). */

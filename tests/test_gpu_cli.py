@@ -206,3 +206,32 @@ def test_cli_prediction_model_delay(tmp_path):
 
     assert ll(f"{d}/p_0.txt") < ll(f"{d}/p_t.txt") - 0.05                       # training helps on this stream ...
     assert abs(ll(f"{d}/p_50.txt") - ll(f"{d}/p_0.txt")) < 0.03, (ll(f"{d}/p_50.txt"), ll(f"{d}/p_0.txt"))  # ... and a 50-example lag costs little
+
+
+def test_cli_weight_quantization(tmp_path):
+    """--convert_inference_regressor with --weight_quantization (main.rs:109, 136-148; quantization.rs): the FFM weights are
+    written as 16-bit buckets under a ModelInstance that says so, `-t -i` dequantizes them, and the predictions stay close
+    to the unquantized inference regressor's."""
+    import json
+
+    d = str(tmp_path)
+    generate(d, n_train=20000, n_eval=10)
+    ns = "--keep A --keep B --ffm_k 4 --ffm_field A --ffm_field B".split()
+    rest = "-l 0.1 --ffm_learning_rate 0.05 -b 18 --ffm_bit_precision 16 --adaptive --sgd --power_t 0.4".split()
+    tr, full, inf, q = f"{d}/train.vw", f"{d}/full.fw", f"{d}/inf.fw", f"{d}/q.fw"
+    run(ns + rest + ["--data", tr, "-f", full, "--save_resume"])
+    run(ns + rest + ["-i", full, "--convert_inference_regressor", inf])
+    run(ns + rest + ["-i", full, "--convert_inference_regressor", q, "--weight_quantization"])
+    n_f = (1 << 16) + 2 * 4
+    assert os.path.getsize(inf) - os.path.getsize(q) == 2 * n_f - 8 + 1   # half the FFM block, less the header, and "true" is a byte shorter than "false"
+    raw = open(q, "rb").read()
+    l1 = int.from_bytes(raw[8:16], "little")
+    l2 = int.from_bytes(raw[16 + l1:24 + l1], "little")
+    mi = json.loads(raw[24 + l1:24 + l1 + l2])
+    assert mi["optimizer"] == "SGD" and mi["dequantize_weights"] is True
+    run(ns + rest + ["-i", inf, "-d", tr, "-t", "-p", f"{d}/p_inf.txt"])
+    run(ns + rest + ["-i", q, "-d", tr, "-t", "-p", f"{d}/p_q.txt"])
+    p_inf, p_q = np.loadtxt(f"{d}/p_inf.txt"), np.loadtxt(f"{d}/p_q.txt")
+    assert len(p_inf) == len(p_q) == 20000 and len(np.unique(p_inf)) > 100, (len(p_inf), len(p_q), len(np.unique(p_inf)))
+    print("quantized vs plain inference regressor: max |dp| %.2e, mean |dp| %.2e, std p %.3f" % (np.max(np.abs(p_inf - p_q)), np.mean(np.abs(p_inf - p_q)), np.std(p_inf)))
+    assert np.max(np.abs(p_inf - p_q)) < 0.02 and np.mean(np.abs(p_inf - p_q)) < 2e-3

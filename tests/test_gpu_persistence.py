@@ -144,3 +144,46 @@ def test_quantized_inference_file_is_dequantized_on_load(tmp_path):
     assert np.array_equal(got, want)
     assert np.max(np.abs(got - w)) < 0.01            # half-float bucket numbers: coarse above bucket 2048, as in the reference
     assert np.array_equal(re.get_lr_table()[:, 0], lr_w)
+
+
+def test_weight_quantization_written_by_the_gpu_path(tmp_path):
+    """--convert_inference_regressor --weight_quantization (main.rs:136-148): the inference regressor's FFM block goes to the file
+    as the 8-byte header and one half-float bucket per weight (quantization.rs:41-75), its ModelInstance says SGD and
+    dequantize_weights = true, and loading the file gives back exactly what the reference's dequantizer computes from it."""
+    w = synth.workload("c2")
+    vw = host.VwNamespaceMap.new("".join(f"{c},feature{c}\n" for c in w.ns_names))
+    recs = w.records(60_000)
+    re = fw.Regressor(w.mi)
+    re.learn_records(recs[:50_000].reshape(-1), n_examples=50_000, update=True)
+    full, inf, q = (str(tmp_path / n) for n in ("full.fw", "inf.fw", "q.fw"))
+    host.save_regressor_to_filename(full, w.mi, vw, re)
+    mi_i, _, re_i = host.new_regressor_from_filename(full, immutable=True)
+    host.save_regressor_to_filename(inf, mi_i, vw, re_i)
+    host.save_regressor_to_filename(q, mi_i, vw, re_i, quantize_weights=True)
+    n_lr, n_f = 1 << 18, (1 << 20) + 32
+    import os
+    assert os.path.getsize(inf) - os.path.getsize(q) == 2 * n_f - 8 + len('"dequantize_weights": false') - len('"dequantize_weights": true')
+    mi_q, _, re_q = host.new_regressor_from_filename(q, immutable=True)
+    assert mi_q.optimizer == Optimizer.SGD
+    raw = open(q, "rb").read()
+    l1 = int.from_bytes(raw[8:16], "little")
+    l2 = int.from_bytes(raw[16 + l1:24 + l1], "little")
+    assert json.loads(raw[24 + l1:24 + l1 + l2])["dequantize_weights"] is True
+    body = 24 + l1 + l2 + 8
+    assert np.array_equal(np.frombuffer(raw, np.float32, n_lr, body), re_i.get_lr_table()[:, 0])   # the LR block is not quantized
+    inc, lo = np.frombuffer(raw, np.float32, 2, body + 4 * n_lr)
+    buckets = np.frombuffer(raw, np.float16, n_f, body + 4 * n_lr + 8)
+    assert len(raw) == body + 4 * n_lr + 8 + 2 * n_f
+    w_full, _ = re_i.get_ffm()
+    rnd = lambda x: (np.sign(x) * np.floor(np.abs(x) + np.float32(0.5))).astype(np.float32)
+    assert lo == np.float32(rnd(w_full.min() * np.float32(1e4)) / np.float32(1e4))
+    assert np.array_equal(buckets.view(np.uint16), rnd(((w_full - lo) / inc).astype(np.float32)).astype(np.float16).view(np.uint16))
+    w_q, _ = re_q.get_ffm()
+    assert np.array_equal(w_q, (lo + buckets.astype(np.float32) * inc).astype(np.float32))
+    assert np.max(np.abs(w_q - w_full)) <= 17 * inc
+    # what the quantization costs on held-out records: small against the spread of the predictions
+    held = recs[50_000:].reshape(-1)
+    p_i = re_i.learn_records(held, n_examples=10_000, update=False)
+    p_q = re_q.learn_records(held, n_examples=10_000, update=False)
+    print("quantized vs plain: max |dp| %.2e, mean |dp| %.2e, std p %.3f, max |dw| / increment %.2f" % (np.max(np.abs(p_i - p_q)), np.mean(np.abs(p_i - p_q)), np.std(p_i), np.max(np.abs(w_q - w_full)) / inc))
+    assert np.max(np.abs(p_i - p_q)) < 0.02 and np.mean(np.abs(p_i - p_q)) < 2e-3

@@ -247,3 +247,141 @@ def test_regressor_reader_reports_optimizer_and_dequantizes(tmp_path):
     L.fwhost_regressor_close(r)
     want = (np.float32(-3.0) + halves.astype(np.float32) * np.float32(0.25)).astype(np.float32)
     assert np.array_equal(out, want)
+
+
+def _quantize_restated(w):
+    """quantization.rs:19-75 in numpy: stats rounded to 4 decimals, 65 025 buckets, round half away from zero, f16 (RNE)."""
+    w = np.asarray(w, np.float32)
+    rnd = lambda x: (np.sign(x) * np.floor(np.abs(x) + np.float32(0.5))).astype(np.float32)  # f32::round
+    lo = np.float32(rnd(w.min() * np.float32(10000.0)) / np.float32(10000.0))
+    hi = np.float32(rnd(w.max() * np.float32(10000.0)) / np.float32(10000.0))
+    inc = np.float32(np.float32(hi - lo) / np.float32(65025.0))
+    with np.errstate(over="ignore"):
+        buckets = rnd(((w - lo) / inc).astype(np.float32)).astype(np.float16)
+    return inc, lo, buckets
+
+
+def test_quantize_ffm_weights_follows_the_reference_writer():  # quantization.rs:41-75 and its tests :98-150
+    import ctypes as C
+
+    L = host._L()
+    # the reference's own test vector (quantization.rs:101-116): statistics and the length of the output
+    w = np.array([0.51, 0.12, 0.11, 0.1232, 0.6123, 0.23], np.float32)
+    mean = C.c_float(0)
+    out = np.empty(8 + 2 * w.size, np.uint8)
+    assert L.fwhost_quantize_ffm_weights(w.ctypes.data_as(C.c_void_p), w.size, out.ctypes.data_as(C.c_void_p), C.byref(mean)) == 0
+    inc, lo = out[:8].view(np.float32)
+    assert out.size // 2 == 10                                    # test_quantize: 4 header pairs + 6 weights
+    assert mean.value == np.float32(0.51) and lo == np.float32(0.11)  # test_emit_statistics (mean samples every 10th weight)
+    assert inc == np.float32(np.float32(np.float32(0.6123) - np.float32(0.11)) / np.float32(65025.0))
+    # round trip (test_dequantize, quantization.rs:118-150): some weights come back exactly, all of them within 1e-4
+    back = lo + out[8:].view(np.float16).astype(np.float32) * inc
+    assert np.max(np.abs(back - w)) < 1e-4 and (back == w).sum() != 0
+    # every bucket number 0 .. 65 025: increment is exactly 1, the half-float conversion sees every integer incl. all its ties
+    ramp = np.arange(65026, dtype=np.float32)
+    out = host.quantize_ffm_weights(ramp)
+    assert np.array_equal(out[:8].view(np.float32), np.array([1.0, 0.0], np.float32))
+    assert np.array_equal(out[8:].view(np.uint16), ramp.astype(np.float16).view(np.uint16))
+    # a trained-looking block: bit-identical with the numpy restatement, header and buckets
+    rng = np.random.default_rng(11)
+    for scale, n in ((0.02, 200_001), (3.0, 50_000), (1e-4, 1000)):
+        w = rng.normal(0, scale, n).astype(np.float32)
+        w[::97] = 0.0
+        inc, lo, buckets = _quantize_restated(w)
+        out = host.quantize_ffm_weights(w)
+        assert np.array_equal(out[:8].view(np.float32), np.array([inc, lo], np.float32))
+        assert np.array_equal(out[8:].view(np.uint16), buckets.view(np.uint16))
+    with pytest.raises(ValueError):
+        host.quantize_ffm_weights(np.empty(0, np.float32))
+
+
+def test_quantized_file_written_by_the_host_layer_reads_back(tmp_path):  # block_ffm.rs:835-857, main.rs:140-147
+    import ctypes as C
+
+    L = host._L()
+    vw = host.VwNamespaceMap.new("A,a\nB,b\n")
+    mi_json = host.model_instance_json_from_cmdline(["--keep", "A", "--ffm_k", "2", "--ffm_field", "A", "--ffm_field", "B", "--adaptive",
+                                                     "--ffm_bit_precision", "10"], vw)
+    err = C.create_string_buffer(1024)
+    p = L.fwhost_model_instance_for_save(mi_json.encode(), 1, 1, err, 1024)
+    assert p, err.value
+    saved = json.loads(C.string_at(p).decode())
+    L.fwhost_free(p)
+    before = json.loads(mi_json)
+    assert before["optimizer"] == "AdagradLUT" and before["dequantize_weights"] is False
+    assert saved["optimizer"] == "SGD" and saved["dequantize_weights"] is True
+    assert {k: v for k, v in saved.items() if k not in ("optimizer", "dequantize_weights")} == \
+           {k: v for k, v in before.items() if k not in ("optimizer", "dequantize_weights")}
+    p = L.fwhost_model_instance_for_save(mi_json.encode(), 0, 0, err, 1024)
+    assert json.loads(C.string_at(p).decode()) == before
+    L.fwhost_free(p)
+    assert not L.fwhost_model_instance_for_save(b"{not json", 1, 1, err, 1024) and err.value
+    rng = np.random.default_rng(5)
+    lr_w = rng.normal(0, 0.1, 1 << 18).astype(np.float32)
+    w = rng.normal(0, 0.05, (1 << 10) + 4).astype(np.float32)
+    blocks = [lr_w, host.quantize_ffm_weights(w)]
+    ptrs = (C.c_void_p * 2)(*[b.ctypes.data_as(C.c_void_p) for b in blocks])
+    sizes = (C.c_uint64 * 2)(*[b.nbytes for b in blocks])
+    path = str(tmp_path / "q.fw").encode()
+    assert L.fwhost_regressor_write(path, vw.source_json.encode(), json.dumps(saved).encode(), lr_w.size + w.size, ptrs, sizes, 2, err, 1024) == 0
+    r = L.fwhost_regressor_open(path, err, 1024)
+    assert r and L.fwhost_regressor_optimizer(r) == Optimizer.SGD and L.fwhost_regressor_dequantize(r) == 1
+    got_lr, got = np.empty_like(lr_w), np.empty_like(w)
+    assert L.fwhost_regressor_read(r, got_lr.ctypes.data_as(C.c_void_p), lr_w.nbytes) == 0 and np.array_equal(got_lr, lr_w)
+    assert L.fwhost_regressor_read_quantized(r, got.ctypes.data_as(C.c_void_p), w.size) == 0
+    L.fwhost_regressor_close(r)
+    inc, lo, buckets = _quantize_restated(w)
+    assert np.array_equal(got, (lo + buckets.astype(np.float32) * inc).astype(np.float32))
+    assert np.max(np.abs(got - w)) <= 17 * inc    # buckets above 32 768 are 32 apart in half precision
+
+
+class _TablesOnly:
+    """Stands in for a regressor where there is no GPU: the two accessors save_regressor_to_filename uses."""
+
+    def __init__(self, blocks, immutable):
+        self.blocks, self.immutable = blocks, immutable
+
+    def block_len(self, b):
+        n, payload = self.blocks[b]
+        return n, payload.nbytes
+
+    def export_block(self, b):
+        return self.blocks[b][1]
+
+
+@pytest.mark.parametrize("immutable", [True, False])
+def test_save_regressor_with_weight_quantization(tmp_path, immutable):  # persistence.rs:55-97, block_ffm.rs:835-848, main.rs:136-148
+    import ctypes as C
+    from fwumious_wabbit_b200 import ModelInstance, _lib
+
+    vw = host.VwNamespaceMap.new("A,a\nB,b\n")
+    mi = ModelInstance.new_empty()
+    mi.bit_precision, mi.ffm_k, mi.ffm_bit_precision, mi.ffm_fields, mi.num_namespaces = 10, 2, 10, [[0], [1]], 2
+    mi.optimizer = Optimizer.SGD if immutable else Optimizer.AdagradLUT
+    rng = np.random.default_rng(8)
+    n_lr, n_f = 1 << 10, (1 << 10) + 4
+    per = 1 if immutable else 2
+    lr = rng.normal(0, 0.1, n_lr * per).astype(np.float32)
+    ffm = np.concatenate([rng.normal(0, 0.05, n_f), rng.random(n_f) if not immutable else []]).astype(np.float32)
+    re = _TablesOnly({_lib.BLOCK_LR: (n_lr, lr), _lib.BLOCK_FFM: (n_f, ffm)}, immutable)
+    path = str(tmp_path / "q.fw")
+    host.save_regressor_to_filename(path, mi, vw, re, quantize_weights=True)
+    L = host._L()
+    err = C.create_string_buffer(512)
+    r = L.fwhost_regressor_open(path.encode(), err, 512)
+    assert r, err.value
+    # only the conversion to an inference regressor records the quantization in the file (main.rs:143-145)
+    assert L.fwhost_regressor_dequantize(r) == (1 if immutable else 0)
+    assert L.fwhost_regressor_optimizer(r) == mi.optimizer and L.fwhost_regressor_weights_len(r) == n_lr + n_f
+    got_lr, got_w, got_acc = np.empty_like(lr), np.empty(n_f, np.float32), np.empty(n_f, np.float32)
+    assert L.fwhost_regressor_read(r, got_lr.ctypes.data_as(C.c_void_p), lr.nbytes) == 0 and np.array_equal(got_lr, lr)
+    assert L.fwhost_regressor_read_quantized(r, got_w.ctypes.data_as(C.c_void_p), n_f) == 0
+    inc, lo, buckets = _quantize_restated(ffm[:n_f])
+    assert np.array_equal(got_w, (lo + buckets.astype(np.float32) * inc).astype(np.float32))
+    if not immutable:  # the accumulators follow the buckets untouched
+        assert L.fwhost_regressor_read(r, got_acc.ctypes.data_as(C.c_void_p), 4 * n_f) == 0 and np.array_equal(got_acc, ffm[n_f:])
+    assert L.fwhost_regressor_read(r, got_acc.ctypes.data_as(C.c_void_p), 1) != 0  # nothing after the last block
+    L.fwhost_regressor_close(r)
+    # and without the flag the file is the plain one
+    host.save_regressor_to_filename(path, mi, vw, re)
+    assert open(path, "rb").read().endswith(lr.tobytes() + ffm.tobytes())
