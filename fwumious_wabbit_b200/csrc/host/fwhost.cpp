@@ -31,7 +31,14 @@ struct NsInfo { uint32_t index; uint32_t seed; bool f32; };
 struct Parser {
     VwMap vw;
     std::unordered_map<std::string, NsInfo> by_name; // the reference uses a radix tree (radix_tree.rs); any exact map is equivalent
+    const NsInfo *by_byte[256] = {nullptr};          // the same entries for one-byte names (the common case), no hashing
     uint32_t n_ns = 0;
+    const NsInfo *find(const char *name, size_t len) const
+    {
+        if (len == 1) return by_byte[(unsigned char)name[0]];
+        const auto it = by_name.find(std::string(name, len));
+        return it == by_name.end() ? nullptr : &it->second;
+    }
 };
 
 bool rust_parse_f32(const char *s, size_t a, size_t b, float *out)
@@ -169,10 +176,8 @@ int parse_line(const Parser &P, const char *p, size_t size, uint32_t *out, size_
         if (p[w.b] == '|') {
             ns_weight = 1.0f;
             if (w.has_suffix() && !rust_parse_f32(p, w.split + 1, w.e, &ns_weight)) { err = "Failed parsing namespace weight: " + cur.text(w.split + 1, w.e); return -1; }
-            const std::string name = cur.text(w.b + 1, w.split);
-            const auto it = P.by_name.find(name);
-            if (it == P.by_name.end()) { err = "Feature name was not predeclared in vw_namespace_map.csv: " + name; return -1; }
-            ns = &it->second;
+            ns = P.find(p + w.b + 1, w.split - (w.b + 1));
+            if (!ns) { err = "Feature name was not predeclared in vw_namespace_map.csv: " + cur.text(w.b + 1, w.split); return -1; }
             rec.open_namespace(ns->index);
         } else {
             const uint32_t hash = murmur3_32(p + w.b, w.split - w.b, ns ? ns->seed : 0) & MASK31;
@@ -398,6 +403,7 @@ void *fwhost_parser_new(const char *vwmap_json, char *err, size_t errcap)
         P->vw = vwmap_from_json(json_parse(vwmap_json));
         P->n_ns = P->vw.num_namespaces;
         for (auto &e : P->vw.entries) P->by_name[e.vwname] = NsInfo{e.index, murmur3_32(e.vwname.data(), e.vwname.size(), 0), e.f32}; // parser.rs:82-83
+        for (auto &kv : P->by_name) if (kv.first.size() == 1) P->by_byte[(unsigned char)kv.first[0]] = &kv.second; // nodes of an unordered_map do not move
         return P;
     } catch (const std::exception &e) { set_err(err, errcap, e.what()); return nullptr; }
 }
@@ -435,6 +441,10 @@ int64_t fwhost_parser_parse_text(void *parser, const char *text, size_t len, uin
     auto work = [&](int t) {
         size_t a = std::min(lines.size(), (size_t)t * per), b = std::min(lines.size(), a + per);
         std::vector<uint32_t> tmp(1 << 16);
+        if (b > a) { // one allocation per slab in the common case: a record word for every 6 bytes of text is typical of VW lines
+            slabs[t].reserve((lines[b - 1].first + lines[b - 1].second - lines[a].first) / 6 + 64);
+            lens[t].reserve(b - a);
+        }
         for (size_t i = a; i < b; i++) {
             const char *lp = text + lines[i].first;
             size_t ll = lines[i].second;
@@ -459,12 +469,20 @@ int64_t fwhost_parser_parse_text(void *parser, const char *text, size_t len, uin
         for (int t = 0; t < nt; t++) total += slabs[t].size();
         if (total > 0xffffffffull) { set_err(err, errcap, "input exceeds 2^32 record words (16 GiB): split it"); return -1; }
     }
-    for (int t = 0; t < nt; t++) {
-        if (words + slabs[t].size() > cap_words) { set_err(err, errcap, "record buffer too small"); return -1; }
-        if (!slabs[t].empty()) memcpy(out + words, slabs[t].data(), slabs[t].size() * 4);
-        uint64_t w = words;
-        for (uint32_t l : lens[t]) { rec_off[n++] = (uint32_t)w; w += l; }
-        words += slabs[t].size();
+    // every worker's slab goes to its place in `out`, and its record offsets to rec_off, again one thread per slab
+    std::vector<uint64_t> word_base(nt), rec_base(nt);
+    for (int t = 0; t < nt; t++) { word_base[t] = words; rec_base[t] = n; words += slabs[t].size(); n += lens[t].size(); }
+    if (words > cap_words) { set_err(err, errcap, "record buffer too small"); return -1; }
+    auto place = [&](int t) {
+        if (!slabs[t].empty()) memcpy(out + word_base[t], slabs[t].data(), slabs[t].size() * 4);
+        uint64_t w = word_base[t], i = rec_base[t];
+        for (uint32_t l : lens[t]) { rec_off[i++] = (uint32_t)w; w += l; }
+    };
+    if (nt == 1) place(0);
+    else {
+        std::vector<std::thread> movers;
+        for (int t = 0; t < nt; t++) movers.emplace_back(place, t);
+        for (auto &m : movers) m.join();
     }
     rec_off[n] = (uint32_t)words;
     if (n_words_out) *n_words_out = words;
@@ -513,34 +531,53 @@ int64_t fwhost_cache_read(const char *path, const char *expect_vwmap_json, uint3
     try {
         f = fopen(path, "rb");
         if (!f) throw std::runtime_error(std::string("cannot open ") + path);
+        // a plain cache is read straight into the buffer the caller gets; a compressed one is decoded first (cache.rs:89-125)
+        const bool compressed = cache_is_compressed(path);
         std::vector<uint8_t> image;
-        {
+        size_t pos = 0;
+        if (compressed) {
             fseek(f, 0, SEEK_END);
             const long sz = ftell(f);
             fseek(f, 0, SEEK_SET);
-            image.resize(sz > 0 ? (size_t)sz : 0);
-            if (!image.empty() && !read_exact(f, image.data(), image.size())) throw std::runtime_error("short read");
-            fclose(f);
-            f = nullptr;
+            std::vector<uint8_t> packed(sz > 0 ? (size_t)sz : 0);
+            if (!packed.empty() && !read_exact(f, packed.data(), packed.size())) throw std::runtime_error("short read");
+            image = lz4::decode_frames(packed.data(), packed.size());
         }
-        if (cache_is_compressed(path)) image = lz4::decode_frames(image.data(), image.size());
-        size_t pos = 0;
-        auto take = [&](void *dst, size_t n_) { if (image.size() - pos < n_) return false; memcpy(dst, image.data() + pos, n_); pos += n_; return true; };
+        auto take = [&](void *dst, size_t n_) {
+            if (!compressed) return read_exact(f, dst, n_);
+            if (image.size() - pos < n_) return false;
+            memcpy(dst, image.data() + pos, n_);
+            pos += n_;
+            return true;
+        };
         char magic[4];
         uint32_t version = 0;
         if (!take(magic, 4) || memcmp(magic, "FWCA", 4)) throw std::runtime_error("Cache header does not begin with magic bytes FWFW"); // sic, cache.rs:167
         if (!take(&version, 4) || version != CACHE_VERSION) throw std::runtime_error("Cache file version of this binary: 11, version of the cache file: " + std::to_string(version));
         uint64_t blen = 0;
-        if (!take(&blen, 8) || blen > image.size() - pos) throw std::runtime_error("truncated cache header");
-        std::string blob((const char *)image.data() + pos, blen);
-        pos += blen;
+        if (!take(&blen, 8) || blen > (1ull << 32)) throw std::runtime_error("truncated cache header");
+        std::string blob(blen, '\0');
+        if (blen && !take(&blob[0], blen)) throw std::runtime_error("truncated cache header");
         VwMap in_file = vwmap_from_json(json_parse(blob));
         if (expect_vwmap_json && !(in_file == vwmap_from_json(json_parse(expect_vwmap_json)))) throw std::runtime_error("vw_namespace_map.csv and the one from cache file differ");
-        uint64_t n_words = (uint64_t)(image.size() - pos) / 4;
+        uint64_t body_bytes;
+        if (compressed) body_bytes = image.size() - pos;
+        else {
+            const long here = ftell(f);
+            fseek(f, 0, SEEK_END);
+            body_bytes = (uint64_t)(ftell(f) - here);
+            fseek(f, here, SEEK_SET);
+        }
+        const uint64_t n_words = body_bytes / 4;
         if (n_words > 0xffffffffull) throw std::runtime_error("cache exceeds 2^32 record words (16 GiB): rec_off holds u32 word offsets");
         uint32_t *recs = (uint32_t *)malloc(std::max<uint64_t>(n_words, 1) * 4);
-        if (n_words) memcpy(recs, image.data() + pos, n_words * 4);
+        if (!recs) throw std::runtime_error("out of memory reading the cache");
+        if (n_words && !take(recs, n_words * 4)) { free(recs); throw std::runtime_error("short read"); }
+        fclose(f);
+        f = nullptr;
+        { std::vector<uint8_t>().swap(image); }
         std::vector<uint32_t> offs;
+        if (n_words) offs.reserve(n_words / std::max<uint32_t>(recs[0], HEADER_LEN) + 16); // exact when every record has the first one's length
         uint64_t w = 0;
         while (w < n_words) {
             uint32_t l = recs[w];

@@ -385,3 +385,70 @@ def test_save_regressor_with_weight_quantization(tmp_path, immutable):  # persis
     # and without the flag the file is the plain one
     host.save_regressor_to_filename(path, mi, vw, re)
     assert open(path, "rb").read().endswith(lr.tobytes() + ffm.tobytes())
+
+
+def test_cache_reader_edge_cases(tmp_path):  # cache.rs:133-182, 187-232: header checks, ragged records, an empty cache
+    vw = host.VwNamespaceMap.new("A,a\nB,b\n")
+    p = host.VowpalParser(vw)
+    lines = ["1 |A x |B y", "-1 2.5 |A x:2 z |B y", "|B q", "1 |A a b c d |B e:0.5"]
+    recs, offs = p.parse_text("\n".join(lines) + "\n")
+    assert np.diff(offs).tolist() == [5, 9, 5, 15]                     # ragged: inline slots and (hash, value) lists
+    path = str(tmp_path / "ragged.vw.fwcache")
+    host.cache_write(path, vw, recs)
+    r, off, _ = host.cache_read(path, vw)
+    assert np.array_equal(r, recs) and np.array_equal(off, offs)
+    good = open(path, "rb").read()
+    blob_len = int.from_bytes(good[8:16], "little")
+    body = 16 + blob_len
+
+    def damaged(data):
+        q = str(tmp_path / "damaged.vw.fwcache")
+        open(q, "wb").write(data)
+        return q
+
+    with pytest.raises(IOError, match="version of the cache file: 10"):
+        host.cache_read(damaged(good[:4] + (10).to_bytes(4, "little") + good[8:]), vw)
+    with pytest.raises(IOError, match="truncated cache header"):
+        host.cache_read(damaged(good[:16 + blob_len // 2]), vw)
+    with pytest.raises(IOError, match="corrupt record length"):      # a record that claims more words than the file holds
+        host.cache_read(damaged(good[:body] + (99).to_bytes(4, "little") + good[body + 4:]), vw)
+    with pytest.raises(IOError, match="corrupt record length"):      # a record shorter than its own header
+        host.cache_read(damaged(good[:body] + (2).to_bytes(4, "little") + good[body + 4:]), vw)
+    r, off, _ = host.cache_read(damaged(good[:body]), vw)               # header only: no records
+    assert r.size == 0 and off.tolist() == [0]
+    r, off, _ = host.cache_read(damaged(good + b"\x01\x02"), vw)        # trailing bytes short of a word are ignored
+    assert np.array_equal(r, recs)
+    with pytest.raises(IOError, match="cannot open"):
+        host.cache_read(str(tmp_path / "absent.fwcache"), vw)
+
+
+def test_parse_text_threads_agree(tmp_path):
+    """The batch parser gives the same records and offsets whatever the thread count (slabs are placed in line order), with
+    one-byte and longer namespace names and a last line without its newline; a blank line is an error, as in the reference
+    (parser.rs:226-258: anything that starts with neither a label nor '|' must be a command)."""
+    vw = host.VwNamespaceMap.new("A,a\nBB,b\nC,c:f32\n")
+    rnd = np.random.default_rng(2)
+    lines = []
+    for i in range(20_000):
+        parts = ["1" if rnd.random() < 0.5 else "-1"]
+        if rnd.random() < 0.2:
+            parts.append("%.2f" % (rnd.random() * 3))
+        parts.append("|A " + " ".join("f%d" % rnd.integers(0, 50) for _ in range(rnd.integers(1, 4))))
+        if rnd.random() < 0.7:
+            parts.append("|BB:%s w%d:%.1f" % ("2" if rnd.random() < 0.3 else "1", rnd.integers(0, 9), rnd.random()))
+        if rnd.random() < 0.5:
+            parts.append("|C %.3f" % rnd.normal())
+        lines.append(" ".join(parts))
+    text = "\n".join(lines)                                             # no newline after the last line
+    p = host.VowpalParser(vw)
+    base_r, base_o = p.parse_text(text, threads=1)
+    assert len(base_o) - 1 == sum(1 for l in lines if l)
+    for th in (2, 3, 8):
+        r, o = p.parse_text(text, threads=th)
+        assert np.array_equal(r, base_r) and np.array_equal(o, base_o)
+    one = np.concatenate([p.next_vowpal(l + "\n") for l in lines if l])
+    assert np.array_equal(one, base_r)
+    with pytest.raises(ValueError, match=r"Cannot parse an example \(line 3\)"):
+        p.parse_text("1 |A x\n1 |A y\n\n1 |A z\n")
+    with pytest.raises(ValueError, match=r"not predeclared in vw_namespace_map.csv: B \(line 2\)"):
+        p.parse_text("1 |A x\n1 |B y\n" * 2000, threads=4)
