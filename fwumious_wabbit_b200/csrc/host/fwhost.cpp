@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <thread>
+#include <unistd.h>
 #include <unordered_map>
 #include <vector>
 
@@ -572,7 +573,31 @@ int64_t fwhost_cache_read(const char *path, const char *expect_vwmap_json, uint3
         if (n_words > 0xffffffffull) throw std::runtime_error("cache exceeds 2^32 record words (16 GiB): rec_off holds u32 word offsets");
         uint32_t *recs = (uint32_t *)malloc(std::max<uint64_t>(n_words, 1) * 4);
         if (!recs) throw std::runtime_error("out of memory reading the cache");
-        if (n_words && !take(recs, n_words * 4)) { free(recs); throw std::runtime_error("short read"); }
+        if (n_words && compressed && !take(recs, n_words * 4)) { free(recs); throw std::runtime_error("short read"); }
+        if (n_words && !compressed) { // straight from the file into place; large bodies by several readers at once (page faults and copies overlap)
+            const uint64_t bytes = n_words * 4, base = (uint64_t)ftell(f);
+            const int fd = fileno(f);
+            const unsigned hw = std::thread::hardware_concurrency();
+            const uint64_t readers = std::max<uint64_t>(1, std::min<uint64_t>(std::min<uint64_t>(hw ? hw : 1, 16), bytes >> 24)); // >= 16 MiB each
+            const uint64_t per = ((bytes + readers - 1) / readers + 4095) & ~uint64_t(4095);
+            std::vector<int> failed(readers, 0);
+            auto pull = [&](uint64_t t) {
+                uint64_t a = std::min(bytes, t * per);
+                const uint64_t b = std::min(bytes, a + per);
+                while (a < b) {
+                    const ssize_t r = pread(fd, (char *)recs + a, (size_t)std::min<uint64_t>(b - a, 64u << 20), (off_t)(base + a));
+                    if (r <= 0) { failed[t] = 1; return; }
+                    a += (uint64_t)r;
+                }
+            };
+            if (readers == 1) pull(0);
+            else {
+                std::vector<std::thread> th;
+                for (uint64_t t = 0; t < readers; t++) th.emplace_back(pull, t);
+                for (auto &x : th) x.join();
+            }
+            for (int bad : failed) if (bad) { free(recs); throw std::runtime_error("short read"); }
+        }
         fclose(f);
         f = nullptr;
         { std::vector<uint8_t>().swap(image); }
