@@ -452,3 +452,66 @@ def test_parse_text_threads_agree(tmp_path):
         p.parse_text("1 |A x\n1 |A y\n\n1 |A z\n")
     with pytest.raises(ValueError, match=r"not predeclared in vw_namespace_map.csv: B \(line 2\)"):
         p.parse_text("1 |A x\n1 |B y\n" * 2000, threads=4)
+
+
+def test_parser_fuzz_against_the_oracle_parser():
+    """Two independent restatements of parser.rs:214-461 — the host layer's (C++, cursor + record writer) and the oracle's (C, the
+    reference's loop structure) — on 60 000 generated lines: labels, importances, tags, unknown / repeated / weighted / multi-byte
+    / f32 namespaces, weighted and empty features, runs of spaces, commands and garbage.  Same records bit for bit, or the same
+    kind of failure with the same message."""
+    import random
+
+    vw = host.VwNamespaceMap.new("A,a\nBB,b\nC,c:f32\nD,d\n")
+    names = [None] * vw.num_namespaces
+    for e in vw.source["entries"]:
+        names[e["namespace_index"]] = e["namespace_vwname"]
+    hp = host.VowpalParser(vw)
+    op = fo.Parser(names, ns_is_f32=vw.ns_is_f32(), namespace_skip_prefix=vw.source["namespace_skip_prefix"])
+    rnd = random.Random(7)
+    good_floats = ["1", "1.0", "2", "0.5", "1e3", "1e-3", ".5", "5.", "NONE", "-0.0", "+2", "inf", "nan"]
+    bad_floats = ["abc", "", "1.5e", "0x10", "1_0", "١", "-1"]
+
+    def number(p_bad):
+        return rnd.choice(bad_floats if rnd.random() < p_bad else good_floats)
+
+    def feature(f32):
+        if f32:
+            w = rnd.choice(["3.5", "-2", "1e2", "0", "NONE"]) if rnd.random() < 0.93 else rnd.choice(["x", "", "1.2.3"])
+        else:
+            w = rnd.choice(["x", "y1", "feat", "", "Z" * rnd.randint(1, 12), "3.5", "é", "|", "q\t", "a-b_c"])
+        if rnd.random() < (0.03 if f32 else 0.25):
+            w += ":" + number(0.05)
+        return w
+
+    def line():
+        r = rnd.random()
+        parts = ["1" if r < 0.42 else "-1" if r < 0.84 else "" if r < 0.94 else rnd.choice(["0", "2", "1.0", "-", "x", "flush", "hogwild_load f", "hogwild_load", " 1"])]
+        if rnd.random() < 0.2:
+            parts.append(number(0.1))
+        if rnd.random() < 0.1:
+            parts.append("'tag")
+        for _ in range(rnd.randint(0, 5)):
+            ns = rnd.choice(["A", "BB", "C", "D", "A", "D"]) if rnd.random() < 0.97 else rnd.choice(["E", "", "B"])
+            parts.append("|" + ns + (":" + number(0.05) if rnd.random() < (0.02 if ns == "C" else 0.15) else ""))
+            parts.extend(feature(ns == "C") for _ in range(rnd.randint(0, 4)))
+        s = "".join(p + " " * (1 if rnd.random() < 0.9 else rnd.randint(0, 3)) for p in parts)
+        return (s.rstrip(" ") if rnd.random() < 0.5 else s) + "\n"
+
+    def outcome(parse, flush, hogwild, l):
+        try:
+            return "ok", parse(l).tolist()
+        except ValueError as e:
+            return "error", str(e)[:40]
+        except flush:
+            return "flush", None
+        except hogwild:
+            return "hogwild_load", None
+
+    kinds = {}
+    for _ in range(60_000):
+        l = line()
+        a = outcome(op.parse, fo.FlushCommand, fo.HogwildLoadCommand, l)
+        b = outcome(hp.next_vowpal, host.FlushCommand, host.HogwildLoadCommand, l)
+        assert a == b, (l, a, b)
+        kinds[a[0]] = kinds.get(a[0], 0) + 1
+    assert kinds["ok"] > 20_000 and kinds["error"] > 5_000 and kinds["flush"] > 10 and kinds["hogwild_load"] > 10, kinds
