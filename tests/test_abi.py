@@ -137,3 +137,40 @@ def test_model_desc_layout_matches_everywhere(tmp_path):
     for n in c_names:
         assert int(got[n]) == getattr(_lib.ModelDesc, n).offset, n
     assert int(got["batch"]) == ctypes.sizeof(_lib.Batch)
+
+
+def test_rust_extern_block_matches_the_header():
+    """Every `pub fn` in INTEGRATION.md's extern "C" block is a prototype of include/fwgpu.h with the same parameters in the
+    same order and equivalent types (a drifted binding compiles and then corrupts the call)."""
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "fwgpu.h")).read(), flags=re.S)
+    protos = {}
+    for ret, name, args in re.findall(r"\n((?:const )?\w+ \*?)\s*(fwgpu_\w+)\(([^)]*)\);", hdr):
+        protos[name] = (ret.strip(), [a.strip() for a in args.replace("\n", " ").split(",")] if args.strip() not in ("", "void") else [])
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r'extern "C" \{(.*?)\n\}', md, re.S).group(1)
+    block = re.sub(r"//[^\n]*", "", block)
+    fns = re.findall(r"pub fn (\w+)\((.*?)\)\s*(?:->\s*([^;]+))?;", block, re.S)
+    assert len(fns) >= 9
+
+    def c_to_rust(t):
+        t = re.sub(r"\s+", " ", t).strip()
+        t = re.sub(r" (\w+)$", "", t) if not t.endswith("*") else t      # drop the parameter name
+        t = t.replace("fwgpu_status", "i32")
+        table = {"int": "c_int", "uint32_t": "u32", "uint64_t": "u64", "float": "f32", "void": "c_void", "char": "c_char", "fwgpu_ctx": "FwgpuCtx",
+                 "fwgpu_model_desc": "FwgpuModelDesc", "i32": "i32"}
+        m = re.match(r"(const )?(\w+) ?(\**)$", t)
+        assert m, t
+        const, base, stars = m.group(1), table[m.group(2)], m.group(3)
+        out = base
+        for i in range(len(stars)):
+            out = ("*const " if (const and i == 0) else "*mut ") + out
+        return out
+
+    for name, args, ret in fns:
+        assert name in protos, f"{name} is not declared in include/fwgpu.h"
+        c_ret, c_args = protos[name]
+        r_args = [a.split(":", 1)[1].strip() for a in re.sub(r"\s+", " ", args).split(",") if a.strip()]
+        # a C parameter "type *name" / "type name": split the name off before comparing
+        want = [c_to_rust(re.sub(r"(\w+)$", "", a).strip() if not a.rstrip().endswith("*") else a) for a in c_args]
+        assert r_args == want, (name, r_args, want)
+        assert (ret or "").strip() == ("" if c_ret == "void" else c_to_rust(c_ret)), (name, ret, c_ret)
