@@ -174,3 +174,20 @@ def test_rust_extern_block_matches_the_header():
         want = [c_to_rust(re.sub(r"(\w+)$", "", a).strip() if not a.rstrip().endswith("*") else a) for a in c_args]
         assert r_args == want, (name, r_args, want)
         assert (ret or "").strip() == ("" if c_ret == "void" else c_to_rust(c_ret)), (name, ret, c_ret)
+
+
+def test_ctypes_bindings_have_the_headers_arity():
+    """Every function the Python mirror binds with argtypes takes as many parameters as its prototype in include/*.h."""
+    from fwumious_wabbit_b200 import host
+
+    L = host._L()
+    checked = 0
+    for h in ("fwgpu.h", "fwhost.h"):
+        hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", h)).read(), flags=re.S)
+        for _, name, args in re.findall(r"\n((?:const )?\w+ \*?)\s*(fw(?:gpu|host)_\w+)\(([^)]*)\);", hdr):
+            n = 0 if args.strip() in ("", "void") else len(args.split(","))
+            at = getattr(L, name).argtypes
+            if at is not None:
+                assert len(at) == n, (name, len(at), n)
+                checked += 1
+    assert checked >= 50
